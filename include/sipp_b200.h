@@ -1,0 +1,149 @@
+/*
+ * sipp_b200.h -- C ABI of the B200-native SIPP prover hot path (libsipp_b200.so).
+ *
+ * This is the drop-in boundary for qope/SIPP's native prover: a Rust host keeps `Transcript`, the arkworks
+ * types and the `sipp_prove_native` / `sipp_verify_native` signatures, and calls these entry points where
+ * the reference calls into plonky2-bn254-pairing / arkworks (see INTEGRATION.md for the `extern "C"` block).
+ * The reference has no FFI of its own; each entry point cites the reference line(s) it replaces.
+ *
+ * Conventions
+ *   - All functions return 0 (SIPP_OK) on success or a negative sipp_status; none of them unwinds.
+ *     sipp_last_error() returns a thread-local message for the last failure.
+ *   - Byte formats = ark-serialize canonical little-endian integers, uncompressed, WITHOUT flag bits
+ *     (`Fq::into_bigint().to_bytes_le()`):
+ *        Fq 32 B | Fr 32 B | G1Affine = x||y 64 B | G2Affine = x.c0||x.c1||y.c0||y.c1 128 B
+ *        Fq12 = c0.c0.c0, c0.c0.c1, c0.c1.c0, ..., c1.c2.c1 (12 x 32 B = 384 B, arkworks nested order)
+ *     The point at infinity is all-zero bytes (ark's `infinity == true` has x = y = 0).
+ *   - Host pointers unless a parameter is documented as a device pointer.  The caller owns every buffer.
+ *   - One host thread per sipp_ctx; contexts are independent (one per GPU shard / per SIPP instance).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with SIPP_ERR_CUDA.
+ */
+#ifndef SIPP_B200_H
+#define SIPP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SIPP_OK = 0,
+    SIPP_ERR_CUDA = -1,        /* no device / CUDA runtime failure */
+    SIPP_ERR_ARG = -2,         /* bad argument (null pointer, n == 0, n not a power of two where required) */
+    SIPP_ERR_LENGTH = -3,      /* A.len() != B.len()          -- reference panics: prover_native.rs:16,27 */
+    SIPP_ERR_ZERO_CHALLENGE = -4, /* x.inverse().unwrap()     -- reference panics: prover_native.rs:58 */
+    SIPP_ERR_SHORT_PROOF = -5, /* proof.pop().unwrap()        -- reference panics: verifier_native.rs:31,40,42 */
+    SIPP_ERR_ENCODING = -6,    /* a field element >= p */
+    SIPP_ERR_VERIFY = -7       /* Err("Verification failed")  -- verifier_native.rs:83 */
+} sipp_status;
+
+typedef struct sipp_ctx sipp_ctx;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int sipp_init(int device);            /* select the CUDA device of this process (one process per GPU) */
+int sipp_shutdown(void);
+const char *sipp_last_error(void);
+int sipp_device_count(void);          /* 0 when no usable GPU: callers must treat that as fatal */
+
+#define SIPP_OPT_FE_NORMALISATION 1   /* 0 = exact exponent (p^12-1)/r [default, SURVEY A.1 H1], 1 = arkworks multiple */
+#define SIPP_OPT_FQ12_ORDER 2         /* transcript order of Fq12: 0 = MyFq12 w-basis [default, SURVEY A.2 H2], 1 = nested */
+#define SIPP_OPT_PROFILE 3            /* 1 = record per-kernel CUDA-event timings (sipp_get_stats) */
+int sipp_set_option(int option, int value);
+int sipp_get_option(int option);
+
+/* ---- prover context: device-resident A, B of the current round ---------------------------------------- */
+/* uploads A (n x 64 B) and B (n x 128 B); `let mut A = A.to_vec(); let mut B = B.to_vec();` prover_native.rs:30-31 */
+int sipp_ctx_create(const uint8_t *A, const uint8_t *B, size_t n, sipp_ctx **out);
+/* same, from DEVICE buffers already in boundary format (no host traffic) */
+int sipp_ctx_create_from_device(const void *dA, const void *dB, size_t n, sipp_ctx **out);
+int sipp_ctx_destroy(sipp_ctx *ctx);
+size_t sipp_ctx_len(const sipp_ctx *ctx);                     /* current n */
+/* Z = inner_product(A, B)                                      prover_native.rs:29  (and :15-23) */
+int sipp_ctx_inner_product(sipp_ctx *ctx, uint8_t out[384]);
+/* Z_L = inner_product(A2, B1), Z_R = inner_product(A1, B2)     prover_native.rs:46-49 */
+int sipp_ctx_cross_products(sipp_ctx *ctx, uint8_t zl[384], uint8_t zr[384]);
+/* A <- A1 + x A2, B <- B1 + x^-1 B2, n <- n/2                   prover_native.rs:60-74 */
+int sipp_ctx_fold(sipp_ctx *ctx, const uint8_t x[32], const uint8_t x_inv[32]);
+/* current A, B back to the host (final_A / final_B: verifier_native.rs:74-75; every round in tests) */
+int sipp_ctx_read(sipp_ctx *ctx, uint8_t *A_out, uint8_t *B_out);
+
+/* ---- multi-GPU: strided shards exchange 384-byte partial Miller products ------------------------------- */
+/* Writes this shard's un-exponentiated partial products (device format, SIPP_PARTIAL_BYTES each) to DEVICE memory
+ * `d_out`, on `stream` (a cudaStream_t, may be NULL): 1 partial for `which` = 0 (Z), 2 for `which` = 1 (Z_L, Z_R).
+ * The host all-gathers them (NCCL) and every rank, or rank 0, calls sipp_combine_partials. */
+#define SIPP_PARTIAL_BYTES 384
+int sipp_ctx_partial_products(sipp_ctx *ctx, int which, void *d_out, void *stream);
+/* product over `count` gathered partial sets (layout [rank][nprod][384 B], DEVICE memory), one final exponentiation
+ * per product, results to HOST `out` (nprod x 384 B, boundary format) */
+int sipp_combine_partials(const void *d_partials, int count, int nprod, uint8_t *out, void *stream);
+
+/* ---- stand-alone operations --------------------------------------------------------------------------- */
+/* pairing(a, b)                                                verifier_native.rs:80, prover_native.rs:20 */
+int sipp_pairing(const uint8_t a[64], const uint8_t b[128], uint8_t out[384]);
+/* pub fn inner_product(A, B) -> Fq12                           prover_native.rs:15 */
+int sipp_inner_product(const uint8_t *A, const uint8_t *B, size_t n, uint8_t out[384]);
+/* x.inverse() in Fr                                            prover_native.rs:58 */
+int sipp_fr_inverse(const uint8_t x[32], uint8_t out[32]);
+/* Z_L.pow(x) * Z * Z_R.pow(inv_x)                              verifier_native.rs:59-61 */
+int sipp_gt_fold(const uint8_t zl[384], const uint8_t z[384], const uint8_t zr[384], const uint8_t x[32],
+                 const uint8_t x_inv[32], uint8_t out[384]);
+
+/* ---- Fiat-Shamir transcript (host; Poseidon over Goldilocks)  transcript_native.rs:14-66 ---------------- */
+typedef struct { uint64_t state[4]; } sipp_transcript;
+void sipp_transcript_new(sipp_transcript *t);                                          /* :19-23 */
+void sipp_transcript_append(sipp_transcript *t, const uint64_t *msg, size_t n);        /* :25-30 */
+void sipp_transcript_append_fq12(sipp_transcript *t, const uint8_t f[384]);            /* :32-40 */
+void sipp_transcript_append_g1(sipp_transcript *t, const uint8_t a[64]);               /* :42-46 */
+void sipp_transcript_append_g2(sipp_transcript *t, const uint8_t b[128]);              /* :48-54 */
+void sipp_transcript_get_challenge(const sipp_transcript *t, uint8_t x[32]);           /* :56-65 */
+/* absorb n (A_i, B_i) pairs in order: the loop at prover_native.rs:36-39 / verifier_native.rs:25-28 */
+void sipp_transcript_append_pairs(sipp_transcript *t, const uint8_t *A, const uint8_t *B, size_t n);
+void sipp_poseidon_permute(uint64_t state[12]);
+
+/* ---- whole protocol with the C++ host transcript inside (what the Python mirror and bench.py call) ------ */
+/* pub fn sipp_prove_native(A, B) -> Vec<Fq12>                  prover_native.rs:26-80
+ * proof: (2 log2 n + 1) x 384 B in the returned (reversed) order [Z_R(last), Z_L(last), ..., Z_R(1), Z_L(1), Z] */
+int sipp_prove_native(const uint8_t *A, size_t a_len, const uint8_t *B, size_t b_len, uint8_t *proof);
+size_t sipp_proof_len(size_t n);      /* number of Fq12 elements = 2 log2 n + 1 */
+/* same protocol on an existing context (inputs already resident in HBM); A/B host copies feed the transcript */
+int sipp_ctx_prove(sipp_ctx *ctx, const uint8_t *A, const uint8_t *B, uint8_t *proof);
+/* pub fn sipp_verify_native(A, B, proof) -> Result<SIPPStatement>   verifier_native.rs:14-85
+ * returns SIPP_OK for Ok(statement), SIPP_ERR_VERIFY for Err; the statement's computed members are written to
+ * final_A[64], final_B[128], final_Z[384] when non-NULL (A, B, Z are the caller's own inputs: statements.rs:80-88) */
+int sipp_verify_native(const uint8_t *A, size_t a_len, const uint8_t *B, size_t b_len, const uint8_t *proof, size_t proof_len,
+                       uint8_t *final_A, uint8_t *final_B, uint8_t *final_Z);
+
+/* ---- synthetic inputs and instrumentation --------------------------------------------------------------- */
+/* A_i = [a_i]G1, B_i = [b_i]G2 with the documented SplitMix64 scalar stream (same as oracle_seeded_inputs);
+ * generated on the GPU into DEVICE buffers dA (n x 64 B), dB (n x 128 B) in boundary format */
+int sipp_seeded_inputs_device(uint64_t seed, size_t n, void *dA, void *dB);
+int sipp_seeded_inputs(uint64_t seed, size_t n, uint8_t *A, uint8_t *B);
+
+typedef struct {
+    uint64_t launches;          /* kernels launched since the last reset */
+    uint64_t miller_pairs;      /* pairs pushed through the Miller-loop kernel */
+    uint64_t miller_launches;
+    double miller_ms;           /* CUDA-event time of the Miller-loop kernels (SIPP_OPT_PROFILE = 1) */
+    double reduce_fe_ms;        /* product reduction + final exponentiation */
+    double fold_ms;             /* G1 + G2 fold kernels */
+    uint64_t fold_points;       /* folded indices (one G1 + one G2 output each) */
+    double transcript_ms;       /* host Poseidon time on the critical path */
+    double other_ms;
+} sipp_stats;
+int sipp_get_stats(sipp_stats *out);
+int sipp_reset_stats(void);
+
+/* ---- test / benchmark hooks (exercise single device functions so every layer can be checked against the oracle) -- */
+/* op: 0 fq_mul (PTX carry chains), 1 fq_mul (portable), 2 add, 3 sub, 4 inv, 5 neg; elements 32 B */
+int sipp_test_fq_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t count);
+/* op: 0 mul, 1 sqr, 2 inv, 3..5 frobenius^1..3, 6 conj, 7 cyclotomic sqr, 8 cyclotomic ^x; elements 384 B */
+int sipp_test_fq12_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t count);
+/* which: 0 mad.lo.u32 chains, 1 mad.wide.u32 chains, 2 lo/hi carry chains, 3 fq_mul PTX, 4 fq_mul portable.
+ * returns operations per second (IMAD instructions for 0-2, Fq multiplications for 3-4) in *ops_per_s */
+int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's native SIPP interface, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as
+  /root/reference/src/prover_native.rs:15   pub fn inner_product(A, B) -> Fq12
+  /root/reference/src/prover_native.rs:26   pub fn sipp_prove_native(A, B) -> Vec<Fq12>
+  /root/reference/src/verifier_native.rs:14 pub fn sipp_verify_native(A, B, proof) -> Result<SIPPStatement>
+  /root/reference/src/transcript_native.rs:14-66 Transcript
+  /root/reference/src/statements.rs:80-88   SIPPStatement
+
+Values are arkworks canonical little-endian bytes (see include/sipp_b200.h): a G1Affine is 64 bytes, a G2Affine
+128 bytes, an Fq12 384 bytes, an Fr 32 bytes.  `A` / `B` may be a list of per-point byte strings (like
+`&[G1Affine]`) or one contiguous buffer.  Where the reference panics this module raises (AssertionError for the
+`assert_eq!`, SippError otherwise); where it returns `Err` it raises VerificationError.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import List, Sequence, Union
+
+from . import _lib
+from ._lib import SippError
+
+G1_BYTES, G2_BYTES, FQ12_BYTES, FR_BYTES = 64, 128, 384, 32
+Points = Union[bytes, bytearray, memoryview, Sequence[bytes]]
+
+
+class VerificationError(Exception):
+    """anyhow!("Verification failed")  (verifier_native.rs:83)"""
+
+
+@dataclass
+class SIPPStatement:
+    """statements.rs:80-88"""
+    A: List[bytes]
+    B: List[bytes]
+    Z: bytes
+    final_A: bytes
+    final_B: bytes
+    final_Z: bytes
+
+
+def _flat(points: Points, size: int) -> bytes:
+    if isinstance(points, (bytes, bytearray, memoryview)):
+        b = bytes(points)
+    else:
+        b = b"".join(bytes(p) for p in points)
+    if len(b) % size:
+        raise ValueError("buffer length %d is not a multiple of %d" % (len(b), size))
+    return b
+
+
+def _split(b: bytes, size: int) -> List[bytes]:
+    return [b[i:i + size] for i in range(0, len(b), size)]
+
+
+def inner_product(A: Points, B: Points) -> bytes:
+    """prod_i e(A_i, B_i)  (prover_native.rs:15-23)"""
+    a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+    assert len(a) // G1_BYTES == len(b) // G2_BYTES, "assert_eq!(A.len(), B.len())"  # prover_native.rs:16
+    _lib.require_gpu_once()
+    out = ctypes.create_string_buffer(FQ12_BYTES)
+    _lib.check(_lib.load().sipp_inner_product(a, b, len(a) // G1_BYTES, out))
+    return out.raw
+
+
+def pairing(a: bytes, b: bytes) -> bytes:
+    """plonky2_bn254_pairing::pairing::pairing(a, b) as used at verifier_native.rs:80"""
+    _lib.require_gpu_once()
+    out = ctypes.create_string_buffer(FQ12_BYTES)
+    _lib.check(_lib.load().sipp_pairing(bytes(a), bytes(b), out))
+    return out.raw
+
+
+def sipp_prove_native(A: Points, B: Points) -> List[bytes]:
+    """prover_native.rs:26-80; returns the proof as a list of 2 log2(n) + 1 Fq12 byte strings."""
+    a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+    na, nb = len(a) // G1_BYTES, len(b) // G2_BYTES
+    assert na == nb, "assert_eq!(A.len(), B.len())"  # prover_native.rs:27
+    _lib.require_gpu_once()
+    lib = _lib.load()
+    plen = lib.sipp_proof_len(na)
+    if plen == 0:
+        raise SippError(_lib.ERR_ARG, "n must be a non-zero power of two")
+    proof = ctypes.create_string_buffer(FQ12_BYTES * plen)
+    _lib.check(lib.sipp_prove_native(a, na, b, nb, proof))
+    return _split(proof.raw, FQ12_BYTES)
+
+
+def sipp_verify_native(A: Points, B: Points, proof: Sequence[bytes]) -> SIPPStatement:
+    """verifier_native.rs:14-85; returns the SIPPStatement or raises VerificationError."""
+    a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+    p = _flat(proof, FQ12_BYTES)
+    na, nb = len(a) // G1_BYTES, len(b) // G2_BYTES
+    _lib.require_gpu_once()
+    fa, fb, fz = (ctypes.create_string_buffer(s) for s in (G1_BYTES, G2_BYTES, FQ12_BYTES))
+    rc = _lib.load().sipp_verify_native(a, na, b, nb, p, len(p) // FQ12_BYTES, fa, fb, fz)
+    if rc == _lib.ERR_VERIFY:
+        raise VerificationError("Verification failed")
+    _lib.check(rc)
+    return SIPPStatement(A=_split(a, G1_BYTES), B=_split(b, G2_BYTES), Z=p[-FQ12_BYTES:], final_A=fa.raw, final_B=fb.raw, final_Z=fz.raw)
+
+
+class Transcript:
+    """transcript_native.rs:14-66 (host code: usable without a GPU)."""
+
+    def __init__(self):
+        self._t = _lib.TranscriptState()
+        _lib.load().sipp_transcript_new(ctypes.byref(self._t))
+
+    @property
+    def state(self) -> List[int]:
+        return list(self._t.state)
+
+    def append(self, message: Sequence[int]) -> None:
+        arr = (ctypes.c_uint64 * max(1, len(message)))(*message)
+        _lib.load().sipp_transcript_append(ctypes.byref(self._t), arr, len(message))
+
+    def append_fq12(self, x: bytes) -> None:
+        assert len(x) == FQ12_BYTES
+        _lib.load().sipp_transcript_append_fq12(ctypes.byref(self._t), bytes(x))
+
+    def append_g1(self, p: bytes) -> None:
+        assert len(p) == G1_BYTES
+        _lib.load().sipp_transcript_append_g1(ctypes.byref(self._t), bytes(p))
+
+    def append_g2(self, x: bytes) -> None:
+        assert len(x) == G2_BYTES
+        _lib.load().sipp_transcript_append_g2(ctypes.byref(self._t), bytes(x))
+
+    def get_challenge(self) -> bytes:
+        out = ctypes.create_string_buffer(FR_BYTES)
+        _lib.load().sipp_transcript_get_challenge(ctypes.byref(self._t), out)
+        return out.raw
+
+
+class ProverContext:
+    """Round-granular access to the device-resident prover state (sipp_ctx_*): what a host that keeps its own
+    transcript calls between challenges (prover_native.rs:29, :48-49, :60-74)."""
+
+    def __init__(self, A: Points = None, B: Points = None, device_ptrs=None, n=None):
+        _lib.require_gpu_once()
+        self._h = ctypes.c_void_p()
+        lib = _lib.load()
+        if device_ptrs is not None:
+            _lib.check(lib.sipp_ctx_create_from_device(device_ptrs[0], device_ptrs[1], n, ctypes.byref(self._h)))
+        else:
+            a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+            assert len(a) // G1_BYTES == len(b) // G2_BYTES
+            _lib.check(lib.sipp_ctx_create(a, b, len(a) // G1_BYTES, ctypes.byref(self._h)))
+
+    def __len__(self):
+        return _lib.load().sipp_ctx_len(self._h)
+
+    def inner_product(self) -> bytes:
+        out = ctypes.create_string_buffer(FQ12_BYTES)
+        _lib.check(_lib.load().sipp_ctx_inner_product(self._h, out))
+        return out.raw
+
+    def cross_products(self):
+        zl, zr = ctypes.create_string_buffer(FQ12_BYTES), ctypes.create_string_buffer(FQ12_BYTES)
+        _lib.check(_lib.load().sipp_ctx_cross_products(self._h, zl, zr))
+        return zl.raw, zr.raw
+
+    def fold(self, x: bytes, x_inv: bytes) -> None:
+        _lib.check(_lib.load().sipp_ctx_fold(self._h, bytes(x), bytes(x_inv)))
+
+    def read(self):
+        n = len(self)
+        a, b = ctypes.create_string_buffer(G1_BYTES * n), ctypes.create_string_buffer(G2_BYTES * n)
+        _lib.check(_lib.load().sipp_ctx_read(self._h, a, b))
+        return a.raw, b.raw
+
+    def prove(self, A: Points, B: Points) -> List[bytes]:
+        a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+        lib = _lib.load()
+        plen = lib.sipp_proof_len(len(self))
+        proof = ctypes.create_string_buffer(FQ12_BYTES * plen)
+        _lib.check(lib.sipp_ctx_prove(self._h, a, b, proof))
+        return _split(proof.raw, FQ12_BYTES)
+
+    def partial_products(self, which: int, d_out: int, stream: int = 0) -> None:
+        _lib.check(_lib.load().sipp_ctx_partial_products(self._h, which, d_out, stream))
+
+    def close(self):
+        if self._h:
+            _lib.load().sipp_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def combine_partials(d_partials: int, count: int, nprod: int, stream: int = 0) -> List[bytes]:
+    out = ctypes.create_string_buffer(FQ12_BYTES * nprod)
+    _lib.check(_lib.load().sipp_combine_partials(d_partials, count, nprod, out, stream))
+    return _split(out.raw, FQ12_BYTES)
+
+
+def fr_inverse(x: bytes) -> bytes:
+    out = ctypes.create_string_buffer(FR_BYTES)
+    _lib.check(_lib.load().sipp_fr_inverse(bytes(x), out))
+    return out.raw
+
+
+def seeded_inputs(seed: int, n: int):
+    """A_i = [a_i]G1, B_i = [b_i]G2 with the documented SplitMix64 scalar stream, generated on the GPU."""
+    _lib.require_gpu_once()
+    a, b = ctypes.create_string_buffer(G1_BYTES * n), ctypes.create_string_buffer(G2_BYTES * n)
+    _lib.check(_lib.load().sipp_seeded_inputs(seed, n, a, b))
+    return a.raw, b.raw
+
+
+def stats(reset=False) -> dict:
+    s = _lib.Stats()
+    _lib.check(_lib.load().sipp_get_stats(ctypes.byref(s)))
+    if reset:
+        _lib.load().sipp_reset_stats()
+    return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+
+def set_option(option: int, value: int) -> None:
+    _lib.check(_lib.load().sipp_set_option(option, value))

@@ -1,0 +1,346 @@
+// fq.cuh -- BN254 base field Fq on 8 x 32-bit limbs, Montgomery form (R = 2^256), for sm_100a.
+//
+// Replaces ark-ff `Fp256<MontBackend<FqConfig,4>>` arithmetic that every call on the reference hot path
+// bottoms out in (/root/reference/src/prover_native.rs:20,63,68 via ark-bn254 0.4).
+//
+// Multiplication is an interleaved (CIOS) Montgomery product kept in TWO accumulators so that every
+// 32x32->64 partial product lands on a 64-bit aligned register pair: even-indexed limbs of `a` (and of p)
+// feed the "aligned" accumulator, odd-indexed limbs feed the accumulator that sits 32 bits higher.  Each row
+// is one `mad.lo.cc / madc.hi.cc` carry chain (ptxas fuses each lo/hi pair into one IMAD.WIDE.U32 with
+// carry), the two rows of a step are independent chains (ILP 2), and the per-step shift by one limb is a
+// role swap of the two accumulators plus a one-limb fix-up -- no data movement.
+//
+// The same row primitives have a plain-C++ host implementation (only used by tests/hostcheck, which runs the
+// *device algorithms* on the CPU against the oracle; the product never computes on the host).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+// device-only under nvcc: the host never computes field arithmetic in the product (no CPU fallback)
+#define SIPP_HD __device__ __forceinline__
+#define SIPP_HD_NOINLINE static __device__ __noinline__
+#else
+#define SIPP_HD inline
+#define SIPP_HD_NOINLINE inline
+#endif
+
+namespace sipp {
+
+struct Fq {
+    uint32_t l[8];
+};
+
+// p, little-endian 32-bit limbs
+#define SIPP_P0 0xd87cfd47u
+#define SIPP_P1 0x3c208c16u
+#define SIPP_P2 0x6871ca8du
+#define SIPP_P3 0x97816a91u
+#define SIPP_P4 0x8181585du
+#define SIPP_P5 0xb85045b6u
+#define SIPP_P6 0xe131a029u
+#define SIPP_P7 0x30644e72u
+#define SIPP_PINV 0xe4866389u  // -p^-1 mod 2^32
+
+SIPP_HD uint32_t fq_p_limb(int i) {
+    switch (i) {
+        case 0: return SIPP_P0; case 1: return SIPP_P1; case 2: return SIPP_P2; case 3: return SIPP_P3;
+        case 4: return SIPP_P4; case 5: return SIPP_P5; case 6: return SIPP_P6; default: return SIPP_P7;
+    }
+}
+
+// R mod p (Montgomery one) and R^2 mod p
+SIPP_HD Fq fq_one() { return Fq{{0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}}; }
+SIPP_HD Fq fq_r2() { return Fq{{0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u}}; }
+SIPP_HD Fq fq_zero() { return Fq{{0, 0, 0, 0, 0, 0, 0, 0}}; }
+
+// ---------------------------------------------------------------------------------------------------------
+// row primitives
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+
+// acc[0..7] = (a0, a2, a4, a6) * b laid out as four aligned 64-bit products (no accumulate)
+__device__ __forceinline__ void row_mul(uint32_t* acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]), "=&r"(acc[7])
+        : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+
+// acc[0..7] += (a0, a2, a4, a6) * b ; carry out of limb 7 is added into `top`
+__device__ __forceinline__ void row_mad_carry(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+
+// acc[0..7] += (a0, a2, a4, a6) * b ; no carry out (caller guarantees the bound)
+__device__ __forceinline__ void row_mad(uint32_t* acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+
+// The role swap of one CIOS step:  x0 += y[1] (carry c);  y <- (y >> 64) + (a1, a3, a5, a7) * b + c
+__device__ __forceinline__ void row_shift_mad(uint32_t& x0, uint32_t* y, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t b) {
+    asm("add.cc.u32 %8, %8, %1;\n\t"
+        "madc.lo.cc.u32 %0, %9, %13, %2;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %4;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %6;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, 0;\n\t"
+        "madc.hi.u32 %7, %12, %13, 0;"
+        : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]), "+r"(x0)
+        : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
+}
+
+// r = (x >> 32) + y  over 8 limbs (x[0] is known to be zero)
+__device__ __forceinline__ void merge_acc(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+        : "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]),
+          "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+}
+
+// r = a + b over 8 limbs, returns carry out
+__device__ __forceinline__ uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+}
+
+// r = a - b over 8 limbs, returns borrow (1 if a < b)
+__device__ __forceinline__ uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c & 1u;
+}
+
+#else  // host emulation of the same primitives (tests/hostcheck only)
+
+inline void row_mul(uint32_t* acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+    const uint32_t a[4] = {a0, a2, a4, a6};
+    for (int j = 0; j < 4; j++) {
+        uint64_t p = (uint64_t)a[j] * b;
+        acc[2 * j] = (uint32_t)p; acc[2 * j + 1] = (uint32_t)(p >> 32);
+    }
+}
+inline uint32_t row_mad_host(uint32_t* acc, const uint32_t* base, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b, uint32_t cin) {
+    const uint32_t a[4] = {a0, a2, a4, a6};
+    uint64_t carry = cin;
+    for (int j = 0; j < 4; j++) {
+        uint64_t p = (uint64_t)a[j] * b;
+        uint64_t lo = (uint64_t)(uint32_t)p + base[2 * j] + carry;
+        uint64_t hi = (p >> 32) + base[2 * j + 1] + (lo >> 32);
+        acc[2 * j] = (uint32_t)lo; acc[2 * j + 1] = (uint32_t)hi; carry = hi >> 32;
+    }
+    return (uint32_t)carry;
+}
+inline void row_mad_carry(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+    uint32_t base[8]; for (int i = 0; i < 8; i++) base[i] = acc[i];
+    top += row_mad_host(acc, base, a0, a2, a4, a6, b, 0);
+}
+inline void row_mad(uint32_t* acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+    uint32_t base[8]; for (int i = 0; i < 8; i++) base[i] = acc[i];
+    row_mad_host(acc, base, a0, a2, a4, a6, b, 0);
+}
+inline void row_shift_mad(uint32_t& x0, uint32_t* y, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t b) {
+    uint64_t s = (uint64_t)x0 + y[1];
+    x0 = (uint32_t)s;
+    uint32_t base[8] = {y[2], y[3], y[4], y[5], y[6], y[7], 0, 0};
+    row_mad_host(y, base, a1, a3, a5, a7, b, (uint32_t)(s >> 32));
+}
+inline void merge_acc(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)y[i] + (i < 7 ? x[i + 1] : 0); r[i] = (uint32_t)c; c >>= 32; }
+}
+inline uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + b[i]; r[i] = (uint32_t)c; c >>= 32; }
+    return (uint32_t)c;
+}
+inline uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint64_t br = 0;
+    for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a[i] - b[i] - br; r[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    return (uint32_t)br;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// field operations (all inputs and outputs canonical: in [0, p))
+// ---------------------------------------------------------------------------------------------------------
+SIPP_HD void fq_cond_sub_p(uint32_t* r) {  // r in [0, 2p) -> [0, p)
+    const uint32_t P[8] = {SIPP_P0, SIPP_P1, SIPP_P2, SIPP_P3, SIPP_P4, SIPP_P5, SIPP_P6, SIPP_P7};
+    uint32_t t[8];
+    uint32_t borrow = sub8(t, r, P);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+SIPP_HD Fq fq_add(const Fq& a, const Fq& b) {
+    Fq r;
+    add8(r.l, a.l, b.l);  // < 2p < 2^255: no carry out
+    fq_cond_sub_p(r.l);
+    return r;
+}
+
+SIPP_HD Fq fq_sub(const Fq& a, const Fq& b) {
+    const uint32_t P[8] = {SIPP_P0, SIPP_P1, SIPP_P2, SIPP_P3, SIPP_P4, SIPP_P5, SIPP_P6, SIPP_P7};
+    Fq r;
+    uint32_t t[8];
+    uint32_t borrow = sub8(r.l, a.l, b.l);
+    add8(t, r.l, P);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = borrow ? t[i] : r.l[i];
+    return r;
+}
+
+SIPP_HD bool fq_is_zero(const Fq& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0; }
+SIPP_HD bool fq_eq(const Fq& a, const Fq& b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a.l[i] ^ b.l[i];
+    return d == 0;
+}
+
+SIPP_HD Fq fq_neg(const Fq& a) {
+    const uint32_t P[8] = {SIPP_P0, SIPP_P1, SIPP_P2, SIPP_P3, SIPP_P4, SIPP_P5, SIPP_P6, SIPP_P7};
+    Fq r;
+    sub8(r.l, P, a.l);
+    bool z = fq_is_zero(a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = z ? 0u : r.l[i];
+    return r;
+}
+
+SIPP_HD Fq fq_dbl(const Fq& a) { return fq_add(a, a); }
+
+// one CIOS step on the accumulator pair (x = aligned, y = 32 bits higher); roles swap between steps
+SIPP_HD void fq_mont_reduce_step(uint32_t* x, uint32_t* y) {
+    uint32_t m = x[0] * SIPP_PINV;
+    row_mad(y, SIPP_P1, SIPP_P3, SIPP_P5, SIPP_P7, m);
+    row_mad_carry(x, y[7], SIPP_P0, SIPP_P2, SIPP_P4, SIPP_P6, m);
+}
+SIPP_HD void fq_mont_first_step(uint32_t* x, uint32_t* y, const Fq& a, uint32_t b) {
+    row_mul(y, a.l[1], a.l[3], a.l[5], a.l[7], b);
+    row_mul(x, a.l[0], a.l[2], a.l[4], a.l[6], b);
+    fq_mont_reduce_step(x, y);
+}
+SIPP_HD void fq_mont_step(uint32_t* x, uint32_t* y, const Fq& a, uint32_t b) {
+    // incoming: value = y_arr + x_arr[1] + 2^32 (x_arr >> 64) with x_arr[0] == 0.  `x` here is the NEW aligned
+    // accumulator (the old y), `y` the new high accumulator (the old x).
+    row_shift_mad(x[0], y, a.l[1], a.l[3], a.l[5], a.l[7], b);
+    row_mad_carry(x, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b);
+    fq_mont_reduce_step(x, y);
+}
+
+SIPP_HD Fq fq_mul(const Fq& a, const Fq& b) {
+    uint32_t e[8], o[8];
+    fq_mont_first_step(e, o, a, b.l[0]);
+    fq_mont_step(o, e, a, b.l[1]);
+    fq_mont_step(e, o, a, b.l[2]);
+    fq_mont_step(o, e, a, b.l[3]);
+    fq_mont_step(e, o, a, b.l[4]);
+    fq_mont_step(o, e, a, b.l[5]);
+    fq_mont_step(e, o, a, b.l[6]);
+    fq_mont_step(o, e, a, b.l[7]);
+    // after the last step the aligned accumulator is `o` (o[0] == 0), the high one is `e`
+    Fq r;
+    merge_acc(r.l, o, e);
+    fq_cond_sub_p(r.l);
+    return r;
+}
+
+SIPP_HD Fq fq_sqr(const Fq& a) { return fq_mul(a, a); }
+
+// portable reference multiplication (64-bit C arithmetic, no inline PTX); used by the K0 parity test to
+// cross-check the carry-chain version on the device and as the "naive" arm of the microbenchmark
+SIPP_HD Fq fq_mul_portable(const Fq& a, const Fq& b) {
+    uint32_t t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * SIPP_PINV;
+        c = (uint64_t)m * fq_p_limb(0) + t[0]; c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) { c += (uint64_t)m * fq_p_limb(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+    fq_cond_sub_p(r.l);
+    return r;
+}
+
+SIPP_HD Fq fq_to_mont(const Fq& canonical) { return fq_mul(canonical, fq_r2()); }
+SIPP_HD Fq fq_from_mont(const Fq& a) { return fq_mul(a, Fq{{1, 0, 0, 0, 0, 0, 0, 0}}); }
+
+// a^(p-2) by square-and-multiply over the bits of p-2 (uniform control flow: the exponent is a constant)
+SIPP_HD_NOINLINE Fq fq_inv(const Fq& a) {
+    Fq acc = fq_one();
+    for (int i = 7; i >= 0; i--) {
+        uint32_t w = fq_p_limb(i) - (i == 0 ? 2u : 0u);  // p-2: low limb 0xd87cfd47 - 2, no borrow
+        for (int b = 31; b >= 0; b--) {
+            acc = fq_sqr(acc);
+            if ((w >> b) & 1u) acc = fq_mul(acc, a);
+        }
+    }
+    return acc;
+}
+
+}  // namespace sipp

@@ -1,0 +1,33 @@
+// launch.h -- host-callable launch wrappers of the kernels (one translation unit per kernel group so that the
+// groups compile in parallel).  Every wrapper returns the cudaError_t of the launch as an int (0 = success).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace sipp {
+
+// Product `y` of a launch pairs A[a_off[y] + j] with B[b_off[y] + j], j < m.
+struct MillerJob {
+    size_t a_off[2];
+    size_t b_off[2];
+    size_t m;
+};
+struct Scalar256 {
+    uint32_t w[8];
+};
+
+#define SIPP_MILLER_BLOCK 64
+
+int launch_codec_decode(const uint32_t* in, uint32_t* out, size_t n_fq, int* flags, cudaStream_t s);
+int launch_codec_encode(const uint32_t* in, uint32_t* out, size_t n_fq, cudaStream_t s);
+int launch_miller_block(const uint32_t* A, const uint32_t* B, const MillerJob& job, int nprod, uint32_t* partials, cudaStream_t s);
+int launch_reduce_fe(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s);
+int launch_gt_fold(const uint32_t* in, const Scalar256& x, const Scalar256& xinv, uint32_t* out, cudaStream_t s);
+int launch_fold(uint32_t* A, uint32_t* B, size_t h, const Scalar256& x, const Scalar256& xinv, cudaStream_t s);
+int launch_seeded_inputs(uint64_t seed, size_t n, uint32_t* dA, uint32_t* dB, cudaStream_t s);
+int launch_test_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s);
+int launch_test_fq12_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s);
+int launch_microbench(int which, int blocks, int threads, void* out, int iters, uint32_t seed, double* ops_per_thread, cudaStream_t s);
+
+}  // namespace sipp

@@ -1,0 +1,723 @@
+// sipp_b200.cu -- C ABI implementation (include/sipp_b200.h): CUDA launches + the host prover / verifier loops.
+//
+// Host control flow mirrors /root/reference/src/prover_native.rs:26-80 and verifier_native.rs:14-85 line by line
+// (cited inline); all group / field arithmetic runs in the kernels of kernels.cuh.  There is no CPU arithmetic
+// fallback: every compute entry point returns SIPP_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sipp_b200.h"
+#include "launch.h"
+
+using namespace sipp;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0;
+int g_sm_count = 148;
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int kind;  // 0 miller, 1 reduce_fe, 2 fold, 3 other
+};
+std::vector<TimedSpan> g_spans;
+sipp_stats g_stats;
+
+int fail(int code, const char* what) {
+    g_err = what;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return SIPP_ERR_CUDA;
+}
+#define CK(call)                                         \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+int ensure_init() {
+    if (g_device >= 0) return SIPP_OK;
+    return sipp_init(0);
+}
+
+struct Span {
+    int idx = -1;
+    Span(int kind, cudaStream_t s) {
+        if (!g_opt_profile) return;
+        TimedSpan t;
+        t.kind = kind;
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, s);
+        g_spans.push_back(t);
+        idx = (int)g_spans.size() - 1;
+        stream = s;
+    }
+    ~Span() {
+        if (idx >= 0) cudaEventRecord(g_spans[idx].b, stream);
+    }
+    cudaStream_t stream = nullptr;
+};
+
+void collect_spans() {
+    for (auto& t : g_spans) {
+        cudaEventSynchronize(t.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        if (t.kind == 0) g_stats.miller_ms += ms;
+        else if (t.kind == 1) g_stats.reduce_fe_ms += ms;
+        else if (t.kind == 2) g_stats.fold_ms += ms;
+        else g_stats.other_ms += ms;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    g_spans.clear();
+}
+
+size_t log2_exact(size_t n) {
+    size_t r = 0;
+    while (n > 1) { n >>= 1; r++; }
+    return r;
+}
+bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+
+Scalar256 scalar_from_bytes(const uint8_t* b) {
+    Scalar256 s;
+    memcpy(s.w, b, 32);
+    return s;
+}
+
+// device scratch shared by all contexts of this process (one host thread per process by contract)
+struct Scratch {
+    uint32_t* partials = nullptr;  // [blocks][2][96]
+    size_t partial_blocks = 0;
+    uint32_t* out = nullptr;       // 4 x 96 words device result
+    uint8_t* h_out = nullptr;      // pinned mirror
+    int* flag = nullptr;
+} g_scr;
+
+int scratch_reserve(size_t blocks) {
+    if (!g_scr.out) {
+        CK(cudaMalloc(&g_scr.out, 4 * 96 * sizeof(uint32_t)));
+        CK(cudaMallocHost(&g_scr.h_out, 4 * 384));
+        CK(cudaMalloc(&g_scr.flag, sizeof(int)));
+    }
+    if (blocks > g_scr.partial_blocks) {
+        if (g_scr.partials) CK(cudaFree(g_scr.partials));
+        size_t cap = blocks < 1024 ? 1024 : blocks;
+        CK(cudaMalloc(&g_scr.partials, cap * 2 * 96 * sizeof(uint32_t)));
+        g_scr.partial_blocks = cap;
+    }
+    return SIPP_OK;
+}
+
+}  // namespace
+
+struct sipp_ctx {
+    uint32_t* dA = nullptr;  // n x 16 words, Montgomery
+    uint32_t* dB = nullptr;  // n x 32 words
+    size_t n = 0, cap = 0;
+};
+
+namespace {
+
+// decode boundary bytes already on the device (d_bytes) into Montgomery limbs (d_out); n_fq field elements
+int launch_decode(const uint32_t* d_bytes, uint32_t* d_out, size_t n_fq, cudaStream_t s, bool check) {
+    if (check) CK(cudaMemsetAsync(g_scr.flag, 0, sizeof(int), s));
+    Span sp(3, s);
+    int e = launch_codec_decode(d_bytes, d_out, n_fq, check ? g_scr.flag : nullptr, s);
+    if (e) return cuda_fail((cudaError_t)e, "k_codec_decode");
+    g_stats.launches++;
+    return SIPP_OK;
+}
+
+// launches the Miller kernel for `nprod` products of m pairs each; returns the number of partial sets (blocks)
+int launch_miller(const sipp_ctx* c, int nprod, const MillerJob& job, uint32_t* d_partials, size_t* blocks_out, cudaStream_t s) {
+    size_t blocks = (job.m + SIPP_MILLER_BLOCK - 1) / SIPP_MILLER_BLOCK;
+    {
+        Span sp(0, s);
+        int e = launch_miller_block(c->dA, c->dB, job, nprod, d_partials, s);
+        if (e) return cuda_fail((cudaError_t)e, "k_miller_block");
+    }
+    g_stats.launches++;
+    g_stats.miller_launches++;
+    g_stats.miller_pairs += job.m * (size_t)nprod;
+    *blocks_out = blocks;
+    return SIPP_OK;
+}
+
+int launch_reduce(const uint32_t* d_partials, int count, int nprod, uint32_t* d_out, bool final_exp, cudaStream_t s) {
+    Span sp(1, s);
+    int e = launch_reduce_fe(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s);
+    if (e) return cuda_fail((cudaError_t)e, "k_reduce_fe");
+    g_stats.launches++;
+    return SIPP_OK;
+}
+
+// products for the current round: which = 0 -> Z over all n pairs; which = 1 -> Z_L, Z_R over the crossed halves
+int ctx_products_to_device(sipp_ctx* c, int which, size_t* blocks_out, int* nprod_out, cudaStream_t s) {
+    MillerJob job;
+    int nprod;
+    if (which == 0) {
+        nprod = 1;
+        job.a_off[0] = 0; job.b_off[0] = 0; job.a_off[1] = 0; job.b_off[1] = 0;
+        job.m = c->n;
+    } else {
+        if (c->n < 2) return fail(SIPP_ERR_ARG, "cross products need n >= 2");
+        size_t h = c->n / 2;
+        nprod = 2;
+        job.a_off[0] = h; job.b_off[0] = 0;  // Z_L = inner_product(A2, B1)   prover_native.rs:48
+        job.a_off[1] = 0; job.b_off[1] = h;  // Z_R = inner_product(A1, B2)   prover_native.rs:49
+        job.m = h;
+    }
+    size_t blocks = (job.m + SIPP_MILLER_BLOCK - 1) / SIPP_MILLER_BLOCK;
+    int rc = scratch_reserve(blocks);
+    if (rc) return rc;
+    rc = launch_miller(c, nprod, job, g_scr.partials, blocks_out, s);
+    if (rc) return rc;
+    *nprod_out = nprod;
+    return SIPP_OK;
+}
+
+int ctx_products(sipp_ctx* c, int which, uint8_t* out0, uint8_t* out1) {
+    size_t blocks;
+    int nprod;
+    int rc = ctx_products_to_device(c, which, &blocks, &nprod, g_stream);
+    if (rc) return rc;
+    rc = launch_reduce(g_scr.partials, (int)blocks, nprod, g_scr.out, true, g_stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, (size_t)nprod * 384, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    memcpy(out0, g_scr.h_out, 384);
+    if (nprod == 2) memcpy(out1, g_scr.h_out + 384, 384);
+    return SIPP_OK;
+}
+
+int ctx_alloc(size_t n, sipp_ctx** out) {
+    sipp_ctx* c = new sipp_ctx();
+    c->n = c->cap = n;
+    cudaError_t e = cudaMalloc(&c->dA, n * 16 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&c->dB, n * 32 * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        if (c->dA) cudaFree(c->dA);
+        delete c;
+        return cuda_fail(e, "cudaMalloc(ctx)");
+    }
+    *out = c;
+    return SIPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sipp_last_error(void) { return g_err.c_str(); }
+
+int sipp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int sipp_init(int device) {
+    int n = sipp_device_count();
+    if (n <= 0) return fail(SIPP_ERR_CUDA, "no CUDA device: libsipp_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(SIPP_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    if (g_device != device) {
+        if (g_stream) cudaStreamDestroy(g_stream);
+        g_stream = nullptr;
+        g_scr = Scratch();
+    }
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g_sm_count = prop.multiProcessorCount;
+    g_device = device;
+    return SIPP_OK;
+}
+
+int sipp_shutdown(void) {
+    if (g_device < 0) return SIPP_OK;
+    collect_spans();
+    if (g_scr.partials) cudaFree(g_scr.partials);
+    if (g_scr.out) cudaFree(g_scr.out);
+    if (g_scr.h_out) cudaFreeHost(g_scr.h_out);
+    if (g_scr.flag) cudaFree(g_scr.flag);
+    g_scr = Scratch();
+    if (g_stream) cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+    g_device = -1;
+    return SIPP_OK;
+}
+
+int sipp_set_option(int option, int value) {
+    switch (option) {
+        case SIPP_OPT_FE_NORMALISATION: g_opt_fe_norm = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_FQ12_ORDER: g_opt_fq12_order = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_PROFILE: g_opt_profile = value ? 1 : 0; return SIPP_OK;
+        default: return fail(SIPP_ERR_ARG, "unknown option");
+    }
+}
+int sipp_get_option(int option) {
+    switch (option) {
+        case SIPP_OPT_FE_NORMALISATION: return g_opt_fe_norm;
+        case SIPP_OPT_FQ12_ORDER: return g_opt_fq12_order;
+        case SIPP_OPT_PROFILE: return g_opt_profile;
+        default: return -1;
+    }
+}
+
+int sipp_get_stats(sipp_stats* out) {
+    if (!out) return fail(SIPP_ERR_ARG, "null stats");
+    if (g_device >= 0) collect_spans();
+    *out = g_stats;
+    return SIPP_OK;
+}
+int sipp_reset_stats(void) {
+    if (g_device >= 0) collect_spans();
+    memset(&g_stats, 0, sizeof g_stats);
+    return SIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ contexts
+int sipp_ctx_create_from_device(const void* dA, const void* dB, size_t n, sipp_ctx** out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!dA || !dB || !out || n == 0) return fail(SIPP_ERR_ARG, "sipp_ctx_create: null pointer or n == 0");
+    rc = scratch_reserve(1);
+    if (rc) return rc;
+    sipp_ctx* c;
+    rc = ctx_alloc(n, &c);
+    if (rc) return rc;
+    launch_decode((const uint32_t*)dA, c->dA, n * 2, g_stream, true);
+    launch_codec_decode((const uint32_t*)dB, c->dB, n * 4, g_scr.flag, g_stream);
+    g_stats.launches++;
+    int flag = 0;
+    cudaError_t e = cudaMemcpyAsync(&flag, g_scr.flag, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess) { sipp_ctx_destroy(c); return cuda_fail(e, "decode"); }
+    if (flag) { sipp_ctx_destroy(c); return fail(SIPP_ERR_ENCODING, "input coordinate >= p"); }
+    *out = c;
+    return SIPP_OK;
+}
+
+int sipp_ctx_create(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!A || !B || !out || n == 0) return fail(SIPP_ERR_ARG, "sipp_ctx_create: null pointer or n == 0");
+    uint8_t *tA = nullptr, *tB = nullptr;
+    CK(cudaMalloc(&tA, n * 64));
+    cudaError_t e = cudaMalloc(&tB, n * 128);
+    if (e != cudaSuccess) { cudaFree(tA); return cuda_fail(e, "cudaMalloc"); }
+    e = cudaMemcpyAsync(tA, A, n * 64, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tB, B, n * 128, cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) { cudaFree(tA); cudaFree(tB); return cuda_fail(e, "H2D"); }
+    rc = sipp_ctx_create_from_device(tA, tB, n, out);
+    cudaFree(tA);
+    cudaFree(tB);
+    return rc;
+}
+
+int sipp_ctx_destroy(sipp_ctx* c) {
+    if (!c) return SIPP_OK;
+    if (c->dA) cudaFree(c->dA);
+    if (c->dB) cudaFree(c->dB);
+    delete c;
+    return SIPP_OK;
+}
+
+size_t sipp_ctx_len(const sipp_ctx* c) { return c ? c->n : 0; }
+
+int sipp_ctx_inner_product(sipp_ctx* c, uint8_t out[384]) {
+    if (!c || !out) return fail(SIPP_ERR_ARG, "null argument");
+    return ctx_products(c, 0, out, nullptr);
+}
+
+int sipp_ctx_cross_products(sipp_ctx* c, uint8_t zl[384], uint8_t zr[384]) {
+    if (!c || !zl || !zr) return fail(SIPP_ERR_ARG, "null argument");
+    return ctx_products(c, 1, zl, zr);
+}
+
+int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
+    if (!c || !x || !x_inv) return fail(SIPP_ERR_ARG, "null argument");
+    if (c->n < 2) return fail(SIPP_ERR_ARG, "fold needs n >= 2");
+    size_t h = c->n / 2;
+    Scalar256 kx = scalar_from_bytes(x), ki = scalar_from_bytes(x_inv);
+    {
+        Span sp(2, g_stream);
+        // new_A = a1 + a2.mul(x)  prover_native.rs:60-64;  new_B = b1 + b2.mul(inv_x)  :65-69
+        int e = launch_fold(c->dA, c->dB, h, kx, ki, g_stream);
+        if (e) return cuda_fail((cudaError_t)e, "k_fold");
+    }
+    g_stats.launches += 2;
+    g_stats.fold_points += h;
+    c->n = h;                                                                       // n = n / 2   :74
+    return SIPP_OK;
+}
+
+int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
+    if (!c) return fail(SIPP_ERR_ARG, "null ctx");
+    size_t n = c->n;
+    uint32_t* tmp;
+    CK(cudaMalloc(&tmp, n * 32 * sizeof(uint32_t)));
+    cudaError_t e = cudaSuccess;
+    if (A_out) {
+        launch_codec_encode(c->dA, tmp, n * 2, g_stream);
+        g_stats.launches++;
+        e = cudaMemcpyAsync(A_out, tmp, n * 64, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    }
+    if (B_out && e == cudaSuccess) {
+        launch_codec_encode(c->dB, tmp, n * 4, g_stream);
+        g_stats.launches++;
+        e = cudaMemcpyAsync(B_out, tmp, n * 128, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "sipp_ctx_read");
+    return SIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU pieces
+int sipp_ctx_partial_products(sipp_ctx* c, int which, void* d_out, void* stream) {
+    if (!c || !d_out) return fail(SIPP_ERR_ARG, "null argument");
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+    size_t blocks;
+    int nprod;
+    int rc = ctx_products_to_device(c, which, &blocks, &nprod, s);
+    if (rc) return rc;
+    return launch_reduce(g_scr.partials, (int)blocks, nprod, (uint32_t*)d_out, false, s);
+}
+
+int sipp_combine_partials(const void* d_partials, int count, int nprod, uint8_t* out, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!d_partials || !out || count < 1 || nprod < 1 || nprod > 2) return fail(SIPP_ERR_ARG, "bad argument");
+    rc = scratch_reserve(1);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+    rc = launch_reduce((const uint32_t*)d_partials, count, nprod, g_scr.out, true, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, (size_t)nprod * 384, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(out, g_scr.h_out, (size_t)nprod * 384);
+    return SIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone
+int sipp_inner_product(const uint8_t* A, const uint8_t* B, size_t n, uint8_t out[384]) {
+    if (!out) return fail(SIPP_ERR_ARG, "null argument");
+    if (n == 0) {  // fold(Fq12::one(), ...) over an empty iterator
+        memset(out, 0, 384);
+        out[0] = 1;
+        return ensure_init();
+    }
+    sipp_ctx* c;
+    int rc = sipp_ctx_create(A, B, n, &c);
+    if (rc) return rc;
+    rc = sipp_ctx_inner_product(c, out);
+    sipp_ctx_destroy(c);
+    return rc;
+}
+
+int sipp_pairing(const uint8_t a[64], const uint8_t b[128], uint8_t out[384]) { return sipp_inner_product(a, b, 1, out); }
+
+int sipp_gt_fold(const uint8_t zl[384], const uint8_t z[384], const uint8_t zr[384], const uint8_t x[32], const uint8_t x_inv[32],
+                 uint8_t out[384]) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!zl || !z || !zr || !x || !x_inv || !out) return fail(SIPP_ERR_ARG, "null argument");
+    rc = scratch_reserve(1);
+    if (rc) return rc;
+    uint32_t* d_in;
+    CK(cudaMalloc(&d_in, 3 * 384));
+    cudaMemcpyAsync(d_in, zl, 384, cudaMemcpyHostToDevice, g_stream);
+    cudaMemcpyAsync(d_in + 96, z, 384, cudaMemcpyHostToDevice, g_stream);
+    cudaMemcpyAsync(d_in + 192, zr, 384, cudaMemcpyHostToDevice, g_stream);
+    {
+        Span sp(3, g_stream);
+        launch_gt_fold(d_in, scalar_from_bytes(x), scalar_from_bytes(x_inv), g_scr.out, g_stream);
+    }
+    g_stats.launches++;
+    cudaError_t e = cudaMemcpyAsync(g_scr.h_out, g_scr.out, 384, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    cudaFree(d_in);
+    if (e != cudaSuccess) return cuda_fail(e, "sipp_gt_fold");
+    memcpy(out, g_scr.h_out, 384);
+    return SIPP_OK;
+}
+
+// Fr inverse on the host: x^(r-2) with 64-bit Montgomery arithmetic (one per round; prover_native.rs:58)
+int sipp_fr_inverse(const uint8_t x[32], uint8_t out[32]) {
+    typedef unsigned __int128 u128;
+    static const uint64_t M[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+    static const uint64_t R2[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull};
+    const uint64_t INV = 0xc2e1f593efffffffull;
+    if (!x || !out) return fail(SIPP_ERR_ARG, "null argument");
+    auto geq = [](const uint64_t* a, const uint64_t* b) {
+        for (int i = 3; i >= 0; i--)
+            if (a[i] != b[i]) return a[i] > b[i];
+        return true;
+    };
+    auto mul = [&](uint64_t* r, const uint64_t* a, const uint64_t* b) {
+        uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 4; i++) {
+            u128 c = 0;
+            for (int j = 0; j < 4; j++) { c += (u128)a[j] * b[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+            uint64_t m = t[0] * INV;
+            c = (u128)m * M[0] + t[0]; c >>= 64;
+            for (int j = 1; j < 4; j++) { c += (u128)m * M[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+        }
+        if (t[4] || geq(t, M)) {
+            uint64_t borrow = 0;
+            for (int i = 0; i < 4; i++) { u128 d = (u128)t[i] - M[i] - borrow; t[i] = (uint64_t)d; borrow = (uint64_t)(d >> 64) & 1; }
+        }
+        memcpy(r, t, 32);
+    };
+    uint64_t v[4];
+    memcpy(v, x, 32);
+    if (geq(v, M)) return fail(SIPP_ERR_ENCODING, "scalar >= r");
+    if (!(v[0] | v[1] | v[2] | v[3])) return fail(SIPP_ERR_ZERO_CHALLENGE, "challenge is zero: x.inverse().unwrap() panics in the reference");
+    uint64_t base[4], acc[4], one[4] = {1, 0, 0, 0};
+    mul(base, v, R2);
+    mul(acc, one, R2);
+    uint64_t e[4] = {M[0] - 2, M[1], M[2], M[3]};
+    for (int i = 255; i >= 0; i--) {
+        mul(acc, acc, acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) mul(acc, acc, base);
+    }
+    mul(acc, acc, one);
+    memcpy(out, acc, 32);
+    return SIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ protocol
+size_t sipp_proof_len(size_t n) { return is_pow2(n) ? 2 * log2_exact(n) + 1 : 0; }
+
+int sipp_ctx_prove(sipp_ctx* c, const uint8_t* A, const uint8_t* B, uint8_t* proof) {
+    if (!c || !A || !B || !proof) return fail(SIPP_ERR_ARG, "null argument");
+    size_t n = c->n;
+    if (!is_pow2(n)) return fail(SIPP_ERR_ARG, "n must be a power of two (the reference halves n every round)");
+    size_t np = sipp_proof_len(n);
+    std::vector<uint8_t> fwd(np * 384);  // proof in push order; reversed at the end (prover_native.rs:78)
+    size_t k = 0;
+
+    // register A and B (prover_native.rs:36-39): a strictly serial 8n-permutation hash chain.  It does not depend on
+    // anything the GPU computes, so it runs on a host thread while the GPU computes Z and the first Z_L, Z_R.
+    sipp_transcript tr;
+    sipp_transcript_new(&tr);
+    auto t0 = std::chrono::steady_clock::now();
+    std::thread absorb([&]() { sipp_transcript_append_pairs(&tr, A, B, n); });
+
+    int rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                       // let Z = inner_product(A, B);   :29
+    k++;
+    bool first = true;
+    while (rc == SIPP_OK && n > 1) {                                          // :45
+        uint8_t* zl = &fwd[384 * k];
+        uint8_t* zr = &fwd[384 * (k + 1)];
+        rc = sipp_ctx_cross_products(c, zl, zr);                              // :46-49
+        if (rc) break;
+        if (first) {
+            auto t1 = std::chrono::steady_clock::now();
+            absorb.join();
+            auto t2 = std::chrono::steady_clock::now();
+            (void)t0; (void)t1;
+            g_stats.transcript_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();  // exposed wait only
+            sipp_transcript_append_fq12(&tr, &fwd[0]);                        // proof.push(Z); transcript.append_fq12(Z)  :42-43
+            first = false;
+        }
+        auto h0 = std::chrono::steady_clock::now();
+        sipp_transcript_append_fq12(&tr, zl);                                 // :52-53
+        sipp_transcript_append_fq12(&tr, zr);                                 // :54-55
+        k += 2;
+        uint8_t x[32], xinv[32];
+        sipp_transcript_get_challenge(&tr, x);                                // :57
+        rc = sipp_fr_inverse(x, xinv);                                        // :58
+        g_stats.transcript_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        if (rc) break;
+        rc = sipp_ctx_fold(c, x, xinv);                                       // :60-74
+        n = c->n;
+    }
+    if (absorb.joinable()) absorb.join();
+    if (rc) return rc;
+    for (size_t i = 0; i < np; i++) memcpy(proof + 384 * i, &fwd[384 * (np - 1 - i)], 384);  // proof.reverse()  :78
+    return SIPP_OK;
+}
+
+int sipp_prove_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t b_len, uint8_t* proof) {
+    if (a_len != b_len) return fail(SIPP_ERR_LENGTH, "assert_eq!(A.len(), B.len()) failed");  // prover_native.rs:27
+    if (!is_pow2(a_len)) return fail(SIPP_ERR_ARG, "n must be a non-zero power of two");
+    sipp_ctx* c;
+    int rc = sipp_ctx_create(A, B, a_len, &c);
+    if (rc) return rc;
+    rc = sipp_ctx_prove(c, A, B, proof);
+    sipp_ctx_destroy(c);
+    return rc;
+}
+
+int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t b_len, const uint8_t* proof, size_t proof_len, uint8_t* final_A,
+                       uint8_t* final_B, uint8_t* final_Z) {
+    if (!A || !B || !proof) return fail(SIPP_ERR_ARG, "null argument");
+    if (a_len != b_len) return fail(SIPP_ERR_LENGTH, "A.len() != B.len()");
+    size_t n = a_len;
+    if (!is_pow2(n)) return fail(SIPP_ERR_ARG, "n must be a non-zero power of two");
+    if (proof_len < sipp_proof_len(n)) return fail(SIPP_ERR_SHORT_PROOF, "proof.pop().unwrap() on an empty proof");  // verifier_native.rs:31,40,42
+    sipp_ctx* c;
+    int rc = sipp_ctx_create(A, B, n, &c);
+    if (rc) return rc;
+    sipp_transcript tr;
+    sipp_transcript_new(&tr);
+    sipp_transcript_append_pairs(&tr, A, B, n);                               // :25-28
+    size_t top = proof_len;
+    uint8_t Z[384];
+    memcpy(Z, proof + 384 * --top, 384);                                      // let original_Z = proof.pop().unwrap();  :31
+    sipp_transcript_append_fq12(&tr, Z);                                      // :33
+    while (n > 1) {                                                           // :35
+        const uint8_t* zl = proof + 384 * --top;                              // :40
+        sipp_transcript_append_fq12(&tr, zl);
+        const uint8_t* zr = proof + 384 * --top;                              // :42
+        sipp_transcript_append_fq12(&tr, zr);
+        uint8_t x[32], xinv[32];
+        sipp_transcript_get_challenge(&tr, x);                                // :45
+        rc = sipp_fr_inverse(x, xinv);                                        // :46
+        if (rc) break;
+        rc = sipp_ctx_fold(c, x, xinv);                                       // :48-57
+        if (rc) break;
+        uint8_t nz[384];
+        rc = sipp_gt_fold(zl, Z, zr, x, xinv, nz);                            // :59-61
+        if (rc) break;
+        memcpy(Z, nz, 384);
+        n = c->n;
+    }
+    uint8_t fa[64], fb[128], e[384];
+    if (!rc) rc = sipp_ctx_read(c, fa, fb);                                   // final_A: A[0], final_B: B[0]   :74-75
+    if (!rc) rc = sipp_ctx_inner_product(c, e);                               // pairing(final_A, final_B)      :80
+    sipp_ctx_destroy(c);
+    if (rc) return rc;
+    if (final_A) memcpy(final_A, fa, 64);
+    if (final_B) memcpy(final_B, fb, 128);
+    if (final_Z) memcpy(final_Z, Z, 384);
+    if (memcmp(e, Z, 384) != 0) return fail(SIPP_ERR_VERIFY, "Verification failed");  // :81-84
+    return SIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ inputs
+int sipp_seeded_inputs_device(uint64_t seed, size_t n, void* dA, void* dB) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!dA || !dB || n == 0) return fail(SIPP_ERR_ARG, "bad argument");
+    {
+        Span sp(3, g_stream);
+        launch_seeded_inputs(seed, n, (uint32_t*)dA, (uint32_t*)dB, g_stream);
+    }
+    g_stats.launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g_stream));
+    return SIPP_OK;
+}
+
+int sipp_seeded_inputs(uint64_t seed, size_t n, uint8_t* A, uint8_t* B) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!A || !B || n == 0) return fail(SIPP_ERR_ARG, "bad argument");
+    uint8_t *dA, *dB;
+    CK(cudaMalloc(&dA, n * 64));
+    cudaError_t e = cudaMalloc(&dB, n * 128);
+    if (e != cudaSuccess) { cudaFree(dA); return cuda_fail(e, "cudaMalloc"); }
+    rc = sipp_seeded_inputs_device(seed, n, dA, dB);
+    if (!rc) {
+        e = cudaMemcpy(A, dA, n * 64, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(B, dB, n * 128, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "D2H");
+    }
+    cudaFree(dA);
+    cudaFree(dB);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ test hooks
+int sipp_test_fq_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t count) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!a || !out || count == 0) return fail(SIPP_ERR_ARG, "bad argument");
+    uint32_t *da, *db = nullptr, *dout;
+    CK(cudaMalloc(&da, count * 32));
+    CK(cudaMalloc(&dout, count * 32));
+    if (b) { CK(cudaMalloc(&db, count * 32)); CK(cudaMemcpy(db, b, count * 32, cudaMemcpyHostToDevice)); }
+    CK(cudaMemcpy(da, a, count * 32, cudaMemcpyHostToDevice));
+    launch_test_fq_op(op, da, db, dout, count, g_stream);
+    g_stats.launches++;
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, count * 32, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(dout); if (db) cudaFree(db);
+    if (e != cudaSuccess) return cuda_fail(e, "sipp_test_fq_op");
+    return SIPP_OK;
+}
+
+int sipp_test_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t count) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!a || !out || count == 0) return fail(SIPP_ERR_ARG, "bad argument");
+    uint32_t *da, *db = nullptr, *dout;
+    CK(cudaMalloc(&da, count * 384));
+    CK(cudaMalloc(&dout, count * 384));
+    if (b) { CK(cudaMalloc(&db, count * 384)); CK(cudaMemcpy(db, b, count * 384, cudaMemcpyHostToDevice)); }
+    CK(cudaMemcpy(da, a, count * 384, cudaMemcpyHostToDevice));
+    launch_test_fq12_op(op, da, db, dout, count, g_stream);
+    g_stats.launches++;
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, count * 384, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(dout); if (db) cudaFree(db);
+    if (e != cudaSuccess) return cuda_fail(e, "sipp_test_fq12_op");
+    return SIPP_OK;
+}
+
+int sipp_microbench(int which, int iters, double* ops_per_s, double* ms_out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!ops_per_s || iters < 1) return fail(SIPP_ERR_ARG, "bad argument");
+    const int threads = 256;
+    const int blocks = g_sm_count * 8;
+    uint64_t* d_out;
+    CK(cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(uint64_t)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double per_thread_ops = 0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {  // first repetition is the warm-up
+        CK(cudaEventRecord(a, g_stream));
+        if (launch_microbench(which, blocks, threads, d_out, iters, 12345u + rep, &per_thread_ops, g_stream)) {
+            cudaFree(d_out);
+            return fail(SIPP_ERR_ARG, "unknown microbenchmark or launch failure");
+        }
+        g_stats.launches++;
+        CK(cudaEventRecord(b, g_stream));
+        CK(cudaEventSynchronize(b));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    *ops_per_s = per_thread_ops * threads * blocks / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return SIPP_OK;
+}
+
+}  // extern "C"

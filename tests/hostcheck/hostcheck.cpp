@@ -1,0 +1,82 @@
+// hostcheck.cpp -- TEST HARNESS ONLY.  Compiles the *device* arithmetic headers (sipp_b200/csrc/*.cuh) for the
+// host with g++ so that the kernels' algorithms (tower, Miller loop, final exponentiation, folds, codecs) can be
+// checked against the oracle on a machine without a GPU.  The PTX carry chains are replaced by the plain-C++
+// emulation in fq.cuh; everything above them is the exact code the GPU runs.  Never linked into the product.
+#include <cstring>
+
+#include "../../sipp_b200/csrc/codec.cuh"
+#include "../../sipp_b200/csrc/pairing.cuh"
+#include "../../sipp_b200/csrc/coop.cuh"
+
+using namespace sipp;
+
+static const uint32_t* W(const uint8_t* p) { return reinterpret_cast<const uint32_t*>(p); }
+static uint32_t* W(uint8_t* p) { return reinterpret_cast<uint32_t*>(p); }
+
+extern "C" {
+
+// op: 0 mul (carry-chain algorithm), 1 mul (portable), 2 add, 3 sub, 4 inv, 5 neg
+int hc_fq_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t count) {
+    for (size_t i = 0; i < count; i++) {
+        Fq x = fq_decode(W(a + 32 * i)), y = b ? fq_decode(W(b + 32 * i)) : fq_zero(), r;
+        switch (op) {
+            case 0: r = fq_mul(x, y); break;
+            case 1: r = fq_mul_portable(x, y); break;
+            case 2: r = fq_add(x, y); break;
+            case 3: r = fq_sub(x, y); break;
+            case 4: r = fq_inv(x); break;
+            case 5: r = fq_neg(x); break;
+            default: return -1;
+        }
+        fq_encode(W(out + 32 * i), r);
+    }
+    return 0;
+}
+
+// op: 0 mul, 1 sqr, 2 inv, 3..5 frob1..3, 6 conj, 7 cyc_sqr, 8 cyc_exp_x, 9 sparse (b holds l0,l1,l3 in its first 192 bytes)
+int hc_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fq12 x = fq12_decode(W(a)), r;
+    Fq12 y = b ? fq12_decode(W(b)) : fq12_one();
+    switch (op) {
+        case 0: r = fq12_mul(x, y); break;
+        case 1: r = fq12_sqr(x); break;
+        case 2: r = fq12_inv(x); break;
+        case 3: case 4: case 5: r = fq12_frob(x, op - 2); break;
+        case 6: r = fq12_conj(x); break;
+        case 7: r = fq12_cyc_sqr(x); break;
+        case 8: r = fq12_cyc_exp_x(x); break;
+        case 9: r = fq12_mul_sparse(x, fq2_decode(W(b)), fq2_decode(W(b + 64)), fq2_decode(W(b + 128))); break;
+        default: return -1;
+    }
+    fq12_encode(W(out), r);
+    return 0;
+}
+
+int hc_pairing(const uint8_t* a, const uint8_t* b, uint8_t* out, int ark_norm) {
+    Fq12 f = miller_loop(g1_decode(W(a)), g2_decode(W(b)));
+    fq12_encode(W(out), final_exponentiation(f, ark_norm != 0));
+    return 0;
+}
+
+// product of Miller loops then one final exponentiation, exactly as the GPU pipeline composes it
+int hc_inner_product(const uint8_t* A, const uint8_t* B, size_t n, uint8_t* out) {
+    Fq12 acc = fq12_one();
+    for (size_t i = 0; i < n; i++) acc = fq12_mul(acc, miller_loop(g1_decode(W(A + 64 * i)), g2_decode(W(B + 128 * i))));
+    fq12_encode(W(out), final_exponentiation(acc, false));
+    return 0;
+}
+
+int hc_fold_g1(const uint8_t* p1, const uint8_t* p2, const uint8_t* k, uint8_t* out) {
+    G1A r = jac_to_affine(fold_point_jac(g1_decode(W(p1)), g1_decode(W(p2)), W(k)));
+    g1_encode(W(out), r);
+    return 0;
+}
+int hc_fold_g2(const uint8_t* p1, const uint8_t* p2, const uint8_t* k, uint8_t* out) {
+    G2A r = jac_to_affine(fold_point_jac(g2_decode(W(p1)), g2_decode(W(p2)), W(k)));
+    g2_encode(W(out), r);
+    return 0;
+}
+
+#include "hostcheck_coop.inc"
+
+}  // extern "C"

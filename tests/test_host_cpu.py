@@ -1,0 +1,112 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the header declares,
+fails loudly without a GPU, and its Poseidon transcript (host code, like the reference's) matches the golden vectors."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+H = bytes.fromhex
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "sipp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sipp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), "libsipp_b200.so does not export %s" % name
+
+
+def test_no_gpu_fails_loudly():
+    from sipp_b200 import _lib
+    import sipp_b200
+    lib = _lib.load()
+    if lib.sipp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(sipp_b200.SippError) as ei:
+        sipp_b200.inner_product(bytes(64), bytes(128))
+    assert ei.value.code == _lib.ERR_CUDA and "no CPU fallback" in str(ei.value)
+    out = ctypes.create_string_buffer(384)
+    assert lib.sipp_prove_native(bytes(64), 1, bytes(128), 1, out) == _lib.ERR_CUDA
+
+
+def test_product_does_not_reference_oracle():
+    """the product package must not import / link the oracle"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sipp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "sipp_oracle" not in txt and "libsipp_oracle" not in txt, f
+
+
+def test_poseidon_and_transcript_golden(golden):
+    import sipp_b200
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    g = golden["poseidon"]
+
+    def perm(st):
+        arr = (ctypes.c_uint64 * 12)(*st)
+        lib.sipp_poseidon_permute(arr)
+        return ["%016x" % v for v in arr]
+    assert perm([0] * 12) == g["perm_zero"]
+    assert perm(list(range(12))) == g["perm_iota"]
+    assert perm([2**64 - 2**32] * 12) == g["perm_pm1"]
+    t = sipp_b200.Transcript()
+    t.append([1])
+    # hash_no_pad(state || [1]) with zero state == hash of [0,0,0,0,1]
+    pg, tg = golden["pairing_gen"], golden["transcript"]
+    t = sipp_b200.Transcript()
+    t.append_g1(H(pg["a"])); assert ["%016x" % v for v in t.state] == tg["after_g1"]
+    t.append_g2(H(pg["b"])); assert ["%016x" % v for v in t.state] == tg["after_g2"]
+    t.append_fq12(H(pg["exact"])); assert ["%016x" % v for v in t.state] == tg["after_fq12"]
+    st = t.state
+    assert t.get_challenge().hex() == tg["challenge"]
+    assert t.state == st
+
+
+def test_transcript_matches_oracle_random(oracle):
+    import random
+    import sipp_b200
+    rng = random.Random(9)
+    t, ot = sipp_b200.Transcript(), oracle.Transcript()
+    for _ in range(40):
+        n = rng.choice([0, 1, 3, 4, 5, 12, 16, 32, 96])
+        msg = [rng.choice([0, 1, 2**32 - 1, rng.randrange(2**32)]) for _ in range(n)]
+        t.append(msg); ot.append(msg)
+        assert t.state == ot.state
+        assert t.get_challenge() == ot.get_challenge()
+
+
+def test_fr_inverse_host(oracle):
+    import random
+    import sipp_b200
+    R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    rng = random.Random(4)
+    for v in [1, 2, R - 1] + [rng.randrange(1, R) for _ in range(20)]:
+        inv = int.from_bytes(sipp_b200.fr_inverse(v.to_bytes(32, "little")), "little")
+        assert inv * v % R == 1
+    with pytest.raises(sipp_b200.SippError) as ei:
+        sipp_b200.fr_inverse(bytes(32))
+    assert ei.value.code == -4  # zero challenge: the reference panics on unwrap()
+
+
+def test_shard_indices():
+    from sipp_b200.sharded import shard_indices
+    n, G = 64, 8
+    owned = [shard_indices(n, r, G) for r in range(G)]
+    assert sorted(sum(owned, [])) == list(range(n))
+    # i and its fold partner i + n/2 live on the same rank while n >= 2G
+    m = n
+    while m >= 2 * G:
+        for i in range(m // 2):
+            assert i % G == (i + m // 2) % G
+        m //= 2
