@@ -204,6 +204,17 @@ int ctx_products(sipp_ctx* c, int which, uint8_t* out0, uint8_t* out1) {
     return SIPP_OK;
 }
 
+// make `later` wait for everything already enqueued on `earlier`
+cudaError_t order_after(cudaStream_t later, cudaStream_t earlier) {
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(ev, earlier);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(later, ev, 0);
+    cudaEventDestroy(ev);
+    return e;
+}
+
 int ctx_alloc(size_t n, sipp_ctx** out) {
     sipp_ctx* c = new sipp_ctx();
     c->n = c->cap = n;
@@ -394,11 +405,17 @@ int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
 int sipp_ctx_partial_products(sipp_ctx* c, int which, void* d_out, void* stream) {
     if (!c || !d_out) return fail(SIPP_ERR_ARG, "null argument");
     cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+    // the caller's stream (e.g. torch's current stream, which NCCL orders against) must see the folds issued on the
+    // library stream, and later library work must see these launches
+    if (s != g_stream) CK(order_after(s, g_stream));
     size_t blocks;
     int nprod;
     int rc = ctx_products_to_device(c, which, &blocks, &nprod, s);
     if (rc) return rc;
-    return launch_reduce(g_scr.partials, (int)blocks, nprod, (uint32_t*)d_out, false, s);
+    rc = launch_reduce(g_scr.partials, (int)blocks, nprod, (uint32_t*)d_out, false, s);
+    if (rc) return rc;
+    if (s != g_stream) CK(order_after(g_stream, s));
+    return SIPP_OK;
 }
 
 int sipp_combine_partials(const void* d_partials, int count, int nprod, uint8_t* out, void* stream) {
@@ -408,6 +425,7 @@ int sipp_combine_partials(const void* d_partials, int count, int nprod, uint8_t*
     rc = scratch_reserve(1);
     if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+    if (s != g_stream) CK(order_after(s, g_stream));
     rc = launch_reduce((const uint32_t*)d_partials, count, nprod, g_scr.out, true, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, (size_t)nprod * 384, cudaMemcpyDeviceToHost, s));
@@ -640,8 +658,9 @@ int sipp_seeded_inputs(uint64_t seed, size_t n, uint8_t* A, uint8_t* B) {
     if (e != cudaSuccess) { cudaFree(dA); return cuda_fail(e, "cudaMalloc"); }
     rc = sipp_seeded_inputs_device(seed, n, dA, dB);
     if (!rc) {
-        e = cudaMemcpy(A, dA, n * 64, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(B, dB, n * 128, cudaMemcpyDeviceToHost);
+        e = cudaMemcpyAsync(A, dA, n * 64, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(B, dB, n * 128, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "D2H");
     }
     cudaFree(dA);
@@ -657,12 +676,13 @@ int sipp_test_fq_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, si
     uint32_t *da, *db = nullptr, *dout;
     CK(cudaMalloc(&da, count * 32));
     CK(cudaMalloc(&dout, count * 32));
-    if (b) { CK(cudaMalloc(&db, count * 32)); CK(cudaMemcpy(db, b, count * 32, cudaMemcpyHostToDevice)); }
-    CK(cudaMemcpy(da, a, count * 32, cudaMemcpyHostToDevice));
+    if (b) { CK(cudaMalloc(&db, count * 32)); CK(cudaMemcpyAsync(db, b, count * 32, cudaMemcpyHostToDevice, g_stream)); }
+    CK(cudaMemcpyAsync(da, a, count * 32, cudaMemcpyHostToDevice, g_stream));
     launch_test_fq_op(op, da, db, dout, count, g_stream);
     g_stats.launches++;
     cudaError_t e = cudaStreamSynchronize(g_stream);
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout, count * 32, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, count * 32, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
     cudaFree(da); cudaFree(dout); if (db) cudaFree(db);
     if (e != cudaSuccess) return cuda_fail(e, "sipp_test_fq_op");
     return SIPP_OK;
@@ -675,12 +695,13 @@ int sipp_test_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, 
     uint32_t *da, *db = nullptr, *dout;
     CK(cudaMalloc(&da, count * 384));
     CK(cudaMalloc(&dout, count * 384));
-    if (b) { CK(cudaMalloc(&db, count * 384)); CK(cudaMemcpy(db, b, count * 384, cudaMemcpyHostToDevice)); }
-    CK(cudaMemcpy(da, a, count * 384, cudaMemcpyHostToDevice));
+    if (b) { CK(cudaMalloc(&db, count * 384)); CK(cudaMemcpyAsync(db, b, count * 384, cudaMemcpyHostToDevice, g_stream)); }
+    CK(cudaMemcpyAsync(da, a, count * 384, cudaMemcpyHostToDevice, g_stream));
     launch_test_fq12_op(op, da, db, dout, count, g_stream);
     g_stats.launches++;
     cudaError_t e = cudaStreamSynchronize(g_stream);
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout, count * 384, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, count * 384, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
     cudaFree(da); cudaFree(dout); if (db) cudaFree(db);
     if (e != cudaSuccess) return cuda_fail(e, "sipp_test_fq12_op");
     return SIPP_OK;

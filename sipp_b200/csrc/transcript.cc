@@ -16,23 +16,23 @@ typedef unsigned __int128 u128;
 const uint64_t GL_P = 0xFFFFFFFF00000001ull;
 const uint64_t EPS = 0xFFFFFFFFull;  // 2^64 mod p
 
-// values are kept as arbitrary u64 representatives mod p and canonicalised only on output
+// values are kept as arbitrary u64 representatives mod p and canonicalised only on output.  All helpers are
+// branch-free (data-dependent branches on field values mispredict half the time).
 inline uint64_t gl_add(uint64_t a, uint64_t b) {
     uint64_t r = a + b;
-    if (r < a) {  // wrapped: 2^64 = EPS
-        r += EPS;
-        if (r < EPS) r += EPS;
-    }
-    return r;
+    uint64_t c = r < a;             // wrapped: 2^64 = EPS (mod p)
+    uint64_t t = r + ((0 - c) & EPS);
+    uint64_t c2 = t < r;
+    return t + ((0 - c2) & EPS);
 }
 inline uint64_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hh = hi >> 32, hl = hi & EPS;
-    uint64_t t = lo - hh;  // 2^96 = -1
-    if (lo < hh) t -= EPS;
-    uint64_t m = hl * EPS;  // 2^64 = 2^32 - 1
+    uint64_t t = lo - hh;           // 2^96 = -1
+    t -= (0 - (uint64_t)(lo < hh)) & EPS;
+    uint64_t m = hl * EPS;          // 2^64 = 2^32 - 1
     uint64_t r = t + m;
-    if (r < m) r += EPS;
+    r += (0 - (uint64_t)(r < m)) & EPS;
     return r;
 }
 inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }
@@ -40,27 +40,27 @@ inline uint64_t gl_pow7(uint64_t x) {
     uint64_t x2 = gl_mul(x, x), x3 = gl_mul(x2, x), x4 = gl_mul(x2, x2);
     return gl_mul(x3, x4);
 }
-inline uint64_t gl_canon(uint64_t a) { return a >= GL_P ? a - GL_P : a; }
+inline uint64_t gl_canon(uint64_t a) { return a - ((0 - (uint64_t)(a >= GL_P)) & GL_P); }
 
 const uint64_t MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 
 // out[r] = sum_i s[(i + r) mod 12] * CIRC[i] + 8 s[0] [r == 0].  Split into 32-bit halves so that the twelve
-// 12-term dot products stay inside u64 (12 * 41 * 2^32 < 2^42) and vectorise.
-inline void mds_layer(uint64_t* s) {
-    uint64_t lo[24], hi[24];
+// 12-term dot products stay inside u64 (12 * 41 * 2^32 < 2^42); the inner loops run over r with unit stride so the
+// compiler vectorises them (AVX2: 3 vectors per 12 lanes).
+inline void mds_layer(uint64_t* __restrict__ s) {
+    alignas(32) uint64_t lo[24], hi[24], alo[12], ahi[12];
     for (int i = 0; i < 12; i++) {
         lo[i] = lo[i + 12] = s[i] & EPS;
         hi[i] = hi[i + 12] = s[i] >> 32;
+        alo[i] = 0;
+        ahi[i] = 0;
     }
-    uint64_t alo[12], ahi[12];
-    for (int r = 0; r < 12; r++) {
-        uint64_t a = 0, b = 0;
-        for (int i = 0; i < 12; i++) {
-            a += lo[i + r] * MDS_CIRC[i];
-            b += hi[i + r] * MDS_CIRC[i];
+    for (int i = 0; i < 12; i++) {
+        const uint64_t c = MDS_CIRC[i];
+        for (int r = 0; r < 12; r++) {
+            alo[r] += lo[i + r] * c;
+            ahi[r] += hi[i + r] * c;
         }
-        alo[r] = a;
-        ahi[r] = b;
     }
     alo[0] += lo[0] * 8;
     ahi[0] += hi[0] * 8;
@@ -70,9 +70,153 @@ inline void mds_layer(uint64_t* s) {
         uint64_t l = (uint64_t)v, h = (uint64_t)(v >> 64);  // h < 2^11
         uint64_t m = h * EPS;
         uint64_t x = l + m;
-        if (x < m) x += EPS;
+        x += (0 - (uint64_t)(x < m)) & EPS;
         s[r] = x;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Partial rounds in "sparse matrix" form (Poseidon paper, appendix on equivalent matrices; plonky2 uses the same
+// trick).  With M = [[m00, v],[w, Mh]] and the S-box acting on lane 0 only, the 22 rounds
+//      x <- M * Sbox0(x + c_t)
+// are rewritten, exactly, as
+//      u  = diag(1, Minit) * (x + first)
+//      u <- Msparse_t * (Sbox0(u) + post_t e0),   Msparse_t = [[m00, vhat_t], [w_t, I]]
+// where `first`, `post`, `Minit`, `vhat_t`, `w_t` are derived once at start-up from the MDS matrix and the round
+// constants by 11x11 / 12x12 inversions over Goldilocks.  Each sparse round costs 22 field multiplications instead
+// of a 12x12 matrix-vector product.
+// ---------------------------------------------------------------------------------------------------------
+struct FastPartial {
+    uint64_t first[12];
+    uint64_t post[22];
+    uint64_t init[11][11];  // u_i = sum_j init[i][j] y_j over lanes 1..11
+    uint64_t vhat[22][11];
+    uint64_t w[22][11];
+    uint64_t m00;
+};
+FastPartial g_fp;
+
+uint64_t gl_sub(uint64_t a, uint64_t b) { return gl_add(gl_canon(a), GL_P - gl_canon(b)); }
+uint64_t gl_inv(uint64_t a) {  // a^(p-2)
+    uint64_t e = GL_P - 2, r = 1, b = gl_canon(a);
+    while (e) {
+        if (e & 1) r = gl_mul(r, b);
+        b = gl_mul(b, b);
+        e >>= 1;
+    }
+    return gl_canon(r);
+}
+// inverse of an n x n matrix (row-major, n <= 12) by Gauss-Jordan elimination
+void mat_inverse(const uint64_t* a, uint64_t* inv, int n) {
+    uint64_t m[12][24];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) { m[i][j] = gl_canon(a[i * n + j]); m[i][n + j] = i == j; }
+    for (int col = 0; col < n; col++) {
+        int piv = col;
+        while (m[piv][col] == 0) piv++;
+        if (piv != col)
+            for (int j = 0; j < 2 * n; j++) { uint64_t t = m[piv][j]; m[piv][j] = m[col][j]; m[col][j] = t; }
+        uint64_t pi = gl_inv(m[col][col]);
+        for (int j = 0; j < 2 * n; j++) m[col][j] = gl_canon(gl_mul(m[col][j], pi));
+        for (int r = 0; r < n; r++) {
+            if (r == col || m[r][col] == 0) continue;
+            uint64_t f = m[r][col];
+            for (int j = 0; j < 2 * n; j++) m[r][j] = gl_canon(gl_sub(m[r][j], gl_mul(f, m[col][j])));
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) inv[i * n + j] = m[i][n + j];
+}
+
+void init_fast_partial() {
+    uint64_t M[12][12], Minv[144];
+    for (int r = 0; r < 12; r++)
+        for (int c = 0; c < 12; c++) M[r][c] = MDS_CIRC[(c - r + 12) % 12] + ((r == 0 && c == 0) ? 8 : 0);
+    mat_inverse(&M[0][0], Minv, 12);
+    // constants: push every round-constant vector back through M^-1; lane 0 of the pulled-back vector is added after
+    // the previous round's S-box, the other lanes merge into the previous round's constants
+    uint64_t c[22][12];
+    for (int t = 0; t < 22; t++)
+        for (int i = 0; i < 12; i++) c[t][i] = SIPP_POSEIDON_RC[12 * (4 + t) + i];
+    for (int t = 21; t >= 1; t--) {
+        uint64_t d[12];
+        for (int r = 0; r < 12; r++) {
+            uint64_t acc = 0;
+            for (int k = 0; k < 12; k++) acc = gl_add(acc, gl_mul(Minv[r * 12 + k], c[t][k]));
+            d[r] = gl_canon(acc);
+        }
+        g_fp.post[t - 1] = d[0];
+        for (int i = 1; i < 12; i++) c[t - 1][i] = gl_canon(gl_add(c[t - 1][i], d[i]));
+    }
+    g_fp.post[21] = 0;
+    for (int i = 0; i < 12; i++) g_fp.first[i] = c[0][i];
+    // matrices: Mcur = Msparse_t * diag(1, Mh_t), then Mcur <- diag(1, Mh_t) * M for the round before
+    uint64_t cur[12][12];
+    for (int r = 0; r < 12; r++)
+        for (int k = 0; k < 12; k++) cur[r][k] = M[r][k];
+    g_fp.m00 = M[0][0];
+    for (int t = 21; t >= 0; t--) {
+        uint64_t Mh[121], Mhi[121];
+        for (int i = 0; i < 11; i++)
+            for (int j = 0; j < 11; j++) Mh[i * 11 + j] = cur[i + 1][j + 1];
+        mat_inverse(Mh, Mhi, 11);
+        for (int j = 0; j < 11; j++) {  // vhat = v * Mh^-1 (row vector)
+            uint64_t acc = 0;
+            for (int k = 0; k < 11; k++) acc = gl_add(acc, gl_mul(cur[0][k + 1], Mhi[k * 11 + j]));
+            g_fp.vhat[t][j] = gl_canon(acc);
+            g_fp.w[t][j] = gl_canon(cur[j + 1][0]);
+        }
+        uint64_t nxt[12][12];  // diag(1, Mh) * M
+        for (int k = 0; k < 12; k++) nxt[0][k] = M[0][k];
+        for (int i = 0; i < 11; i++)
+            for (int k = 0; k < 12; k++) {
+                uint64_t acc = 0;
+                for (int j = 0; j < 11; j++) acc = gl_add(acc, gl_mul(Mh[i * 11 + j], M[j + 1][k]));
+                nxt[i + 1][k] = gl_canon(acc);
+            }
+        if (t == 0) {
+            for (int i = 0; i < 11; i++)
+                for (int j = 0; j < 11; j++) g_fp.init[i][j] = Mh[i * 11 + j];
+        }
+        for (int r = 0; r < 12; r++)
+            for (int k = 0; k < 12; k++) cur[r][k] = nxt[r][k];
+    }
+}
+struct FastPartialInit {
+    FastPartialInit() { init_fast_partial(); }
+} g_fp_init;
+
+// sum of 11 products of canonical-or-not u64 values, reduced once: accumulate the 128-bit products in three limbs
+inline uint64_t dot11(const uint64_t* a, const uint64_t* b) {
+    u128 lo = 0;
+    uint64_t hi = 0;  // counts overflows of the 128-bit accumulator
+    for (int i = 0; i < 11; i++) {
+        u128 p = (u128)a[i] * b[i];
+        lo += p;
+        hi += lo < p;
+    }
+    // value = lo + hi * 2^128, and 2^128 = 2^64 * 2^64 = EPS^2 = 2^64 - 2^33 + 1 ... reduce hi separately:
+    // 2^128 mod p = (2^32 - 1)^2 mod p = 2^64 - 2^33 + 1 - p = -2^32 mod p  => hi * 2^128 = -(hi << 32)
+    uint64_t r = gl_reduce128(lo);
+    uint64_t t = hi << 32;  // hi <= 11
+    return gl_sub(r, t);
+}
+
+inline void partial_rounds(uint64_t* s) {
+    uint64_t u[12];
+    for (int i = 0; i < 12; i++) u[i] = gl_canon(gl_add(s[i], g_fp.first[i]));
+    {
+        uint64_t t[11];
+        for (int i = 0; i < 11; i++) t[i] = dot11(g_fp.init[i], u + 1);
+        for (int i = 0; i < 11; i++) u[i + 1] = t[i];
+    }
+    for (int r = 0; r < 22; r++) {
+        uint64_t x = gl_add(gl_pow7(u[0]), g_fp.post[r]);
+        uint64_t d = gl_add(gl_mul(x, g_fp.m00), dot11(g_fp.vhat[r], u + 1));
+        for (int i = 0; i < 11; i++) u[i + 1] = gl_add(u[i + 1], gl_mul(x, g_fp.w[r][i]));
+        u[0] = d;
+    }
+    for (int i = 0; i < 12; i++) s[i] = u[i];
 }
 
 }  // namespace
@@ -85,11 +229,8 @@ void sipp_poseidon_permute(uint64_t s[12]) {
         for (int i = 0; i < 12; i++) s[i] = gl_pow7(gl_add(s[i], SIPP_POSEIDON_RC[12 * rnd + i]));
         mds_layer(s);
     }
-    for (int k = 0; k < 22; k++, rnd++) {
-        for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], SIPP_POSEIDON_RC[12 * rnd + i]);
-        s[0] = gl_pow7(s[0]);
-        mds_layer(s);
-    }
+    partial_rounds(s);
+    rnd += 22;
     for (int k = 0; k < 4; k++, rnd++) {
         for (int i = 0; i < 12; i++) s[i] = gl_pow7(gl_add(s[i], SIPP_POSEIDON_RC[12 * rnd + i]));
         mds_layer(s);
