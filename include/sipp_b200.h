@@ -49,6 +49,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
 #define SIPP_OPT_FE_NORMALISATION 1   /* 0 = exact exponent (p^12-1)/r [default, SURVEY A.1 H1], 1 = arkworks multiple */
 #define SIPP_OPT_FQ12_ORDER 2         /* transcript order of Fq12: 0 = MyFq12 w-basis [default, SURVEY A.2 H2], 1 = nested */
 #define SIPP_OPT_PROFILE 3            /* 1 = record per-kernel CUDA-event timings (sipp_get_stats) */
+#define SIPP_OPT_PIPELINE 4           /* 1 = split Miller loop: line kernel + 6-lane cooperative accumulation and final
+                                         exponentiation [default]; 0 = one Miller loop per thread (first-round baseline) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 
@@ -137,7 +139,8 @@ int sipp_reset_stats(void);
 /* ---- test / benchmark hooks (exercise single device functions so every layer can be checked against the oracle) -- */
 /* op: 0 fq_mul (PTX carry chains), 1 fq_mul (portable), 2 add, 3 sub, 4 inv, 5 neg; elements 32 B */
 int sipp_test_fq_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t count);
-/* op: 0 mul, 1 sqr, 2 inv, 3..5 frobenius^1..3, 6 conj, 7 cyclotomic sqr, 8 cyclotomic ^x; elements 384 B */
+/* op: 0 mul, 1 sqr, 2 inv, 3..5 frobenius^1..3, 6 conj, 7 cyclotomic sqr, 8 cyclotomic ^x; elements 384 B.
+ * op + 20 runs the 6-lane cooperative version (29 = cooperative final exponentiation) */
 int sipp_test_fq12_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t count);
 /* which: 0 mad.lo.u32 chains, 1 mad.wide.u32 chains, 2 lo/hi carry chains, 3 fq_mul PTX, 4 fq_mul portable.
  * returns operations per second (IMAD instructions for 0-2, Fq multiplications for 3-4) in *ops_per_s */

@@ -22,7 +22,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
-int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0;
+int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0, g_opt_pipeline = 1;
 int g_sm_count = 148;
 
 struct TimedSpan {
@@ -105,6 +105,8 @@ struct Scratch {
     uint32_t* out = nullptr;       // 4 x 96 words device result
     uint8_t* h_out = nullptr;      // pinned mirror
     int* flag = nullptr;
+    uint32_t* lines = nullptr;     // split pipeline: [nprod][mc][91][80 words]
+    size_t lines_bytes = 0;
 } g_scr;
 
 int scratch_reserve(size_t blocks) {
@@ -118,6 +120,17 @@ int scratch_reserve(size_t blocks) {
         size_t cap = blocks < 1024 ? 1024 : blocks;
         CK(cudaMalloc(&g_scr.partials, cap * 2 * 96 * sizeof(uint32_t)));
         g_scr.partial_blocks = cap;
+    }
+    return SIPP_OK;
+}
+
+int lines_reserve(size_t bytes) {
+    if (bytes > g_scr.lines_bytes) {
+        if (g_scr.lines) CK(cudaFree(g_scr.lines));
+        g_scr.lines = nullptr;
+        g_scr.lines_bytes = 0;
+        CK(cudaMalloc(&g_scr.lines, bytes));
+        g_scr.lines_bytes = bytes;
     }
     return SIPP_OK;
 }
@@ -159,7 +172,8 @@ int launch_miller(const sipp_ctx* c, int nprod, const MillerJob& job, uint32_t* 
 
 int launch_reduce(const uint32_t* d_partials, int count, int nprod, uint32_t* d_out, bool final_exp, cudaStream_t s) {
     Span sp(1, s);
-    int e = launch_reduce_fe(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s);
+    int e = g_opt_pipeline ? launch_reduce_fe_coop(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s)
+                           : launch_reduce_fe(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s);
     if (e) return cuda_fail((cudaError_t)e, "k_reduce_fe");
     g_stats.launches++;
     return SIPP_OK;
@@ -181,12 +195,44 @@ int ctx_products_to_device(sipp_ctx* c, int which, size_t* blocks_out, int* npro
         job.a_off[1] = 0; job.b_off[1] = h;  // Z_R = inner_product(A1, B2)   prover_native.rs:49
         job.m = h;
     }
-    size_t blocks = (job.m + SIPP_MILLER_BLOCK - 1) / SIPP_MILLER_BLOCK;
-    int rc = scratch_reserve(blocks);
-    if (rc) return rc;
-    rc = launch_miller(c, nprod, job, g_scr.partials, blocks_out, s);
-    if (rc) return rc;
     *nprod_out = nprod;
+    if (!g_opt_pipeline) {
+        size_t blocks = (job.m + SIPP_MILLER_BLOCK - 1) / SIPP_MILLER_BLOCK;
+        int rc = scratch_reserve(blocks);
+        if (rc) return rc;
+        return launch_miller(c, nprod, job, g_scr.partials, blocks_out, s);
+    }
+    // split pipeline: L (lines -> HBM) then A (6-lane cooperative accumulation), in chunks that bound the line buffer
+    const size_t per_pair = lines_bytes_per_pair();
+    const size_t cap_bytes = (size_t)6 << 30;
+    size_t mc = job.m;
+    if (mc * (size_t)nprod * per_pair > cap_bytes) mc = cap_bytes / ((size_t)nprod * per_pair);
+    const size_t groups_target = (size_t)g_sm_count * 2 * 20;
+    int kpg = (int)((mc + groups_target - 1) / groups_target);
+    if (kpg < 1) kpg = 1;
+    size_t total_blocks = 0;
+    for (size_t c0 = 0; c0 < job.m; c0 += mc) {
+        size_t cur = job.m - c0 < mc ? job.m - c0 : mc;
+        total_blocks += (size_t)accum_blocks(cur, kpg);
+    }
+    int rc = scratch_reserve(total_blocks);
+    if (rc) return rc;
+    rc = lines_reserve(mc * (size_t)nprod * per_pair);
+    if (rc) return rc;
+    size_t block_off = 0;
+    for (size_t c0 = 0; c0 < job.m; c0 += mc) {
+        size_t cur = job.m - c0 < mc ? job.m - c0 : mc;
+        Span sp(0, s);
+        int e = launch_lines(c->dA, c->dB, job, nprod, c0, cur, g_scr.lines, s);
+        if (e) return cuda_fail((cudaError_t)e, "k_lines");
+        e = launch_accum(g_scr.lines, cur, nprod, kpg, g_scr.partials, (int)block_off, s);
+        if (e) return cuda_fail((cudaError_t)e, "k_accum");
+        block_off += (size_t)accum_blocks(cur, kpg);
+        g_stats.launches += 2;
+        g_stats.miller_launches++;
+    }
+    g_stats.miller_pairs += job.m * (size_t)nprod;
+    *blocks_out = total_blocks;
     return SIPP_OK;
 }
 
@@ -266,6 +312,7 @@ int sipp_shutdown(void) {
     if (g_scr.out) cudaFree(g_scr.out);
     if (g_scr.h_out) cudaFreeHost(g_scr.h_out);
     if (g_scr.flag) cudaFree(g_scr.flag);
+    if (g_scr.lines) cudaFree(g_scr.lines);
     g_scr = Scratch();
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
@@ -278,6 +325,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_FE_NORMALISATION: g_opt_fe_norm = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_FQ12_ORDER: g_opt_fq12_order = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_PROFILE: g_opt_profile = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_PIPELINE: g_opt_pipeline = value ? 1 : 0; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -286,6 +334,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_FE_NORMALISATION: return g_opt_fe_norm;
         case SIPP_OPT_FQ12_ORDER: return g_opt_fq12_order;
         case SIPP_OPT_PROFILE: return g_opt_profile;
+        case SIPP_OPT_PIPELINE: return g_opt_pipeline;
         default: return -1;
     }
 }
@@ -697,7 +746,8 @@ int sipp_test_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, 
     CK(cudaMalloc(&dout, count * 384));
     if (b) { CK(cudaMalloc(&db, count * 384)); CK(cudaMemcpyAsync(db, b, count * 384, cudaMemcpyHostToDevice, g_stream)); }
     CK(cudaMemcpyAsync(da, a, count * 384, cudaMemcpyHostToDevice, g_stream));
-    launch_test_fq12_op(op, da, db, dout, count, g_stream);
+    if (op >= 20) launch_test_coop_op(op - 20, da, db, dout, count, g_stream);
+    else launch_test_fq12_op(op, da, db, dout, count, g_stream);
     g_stats.launches++;
     cudaError_t e = cudaStreamSynchronize(g_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, count * 384, cudaMemcpyDeviceToHost, g_stream);

@@ -6,6 +6,7 @@
 
 #include "../../sipp_b200/csrc/codec.cuh"
 #include "../../sipp_b200/csrc/pairing.cuh"
+#include "../../sipp_b200/csrc/fqdot.cuh"
 #include "../../sipp_b200/csrc/coop.cuh"
 
 using namespace sipp;
@@ -77,6 +78,6 @@ int hc_fold_g2(const uint8_t* p1, const uint8_t* p2, const uint8_t* k, uint8_t* 
     return 0;
 }
 
-#include "hostcheck_coop.inc"
-
 }  // extern "C"
+
+#include "hostcheck_coop.inc"

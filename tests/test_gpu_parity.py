@@ -78,7 +78,37 @@ def test_fq12_ops(lib, oracle, golden):
     assert _fq12_op(lib, 7, e) == oracle.field_op("FQ12_SQR", e)  # cyclotomic squaring on a GT element
 
 
-def test_pairing_golden_and_oracle(sipp, oracle, golden):
+def test_coop_fq12_ops(lib, oracle, golden):
+    """6-lane cooperative Fq12 arithmetic (lazy-reduction inner products + warp shuffles) vs the oracle"""
+    rng = random.Random(12)
+    n = 23  # not a multiple of the 5 groups per warp
+    a = b"".join(le(rng.randrange(P)) for _ in range(12 * n))
+    b = b"".join(le(rng.randrange(P)) for _ in range(12 * n))
+    assert _fq12_op(lib, 20, a, b) == oracle.field_op("FQ12_MUL", a, b)
+    assert _fq12_op(lib, 21, a) == oracle.field_op("FQ12_SQR", a)
+    assert _fq12_op(lib, 22, a) == oracle.field_op("FQ12_INV", a)
+    assert _fq12_op(lib, 23, a) == oracle.field_op("FQ12_FROB1", a)
+    assert _fq12_op(lib, 24, a) == oracle.field_op("FQ12_FROB2", a)
+    assert _fq12_op(lib, 25, a) == oracle.field_op("FQ12_FROB3", a)
+    assert _fq12_op(lib, 26, a) == oracle.field_op("FQ12_CONJ", a)
+    A, B = oracle.seeded_inputs(91, 7, threads=4)
+    gt = b"".join(oracle.pairing(A[64 * i:64 * i + 64], B[128 * i:128 * i + 128]) for i in range(7))
+    assert _fq12_op(lib, 27, gt) == oracle.field_op("FQ12_SQR", gt)          # Granger-Scott on GT elements
+    assert _fq12_op(lib, 28, gt) == _fq12_op(lib, 8, gt)                      # cooperative ^x == per-thread ^x
+    ml = b"".join(oracle.miller_loop(A[64 * i:64 * i + 64], B[128 * i:128 * i + 128]) for i in range(7))
+    assert _fq12_op(lib, 29, ml) == gt                                        # cooperative final exponentiation
+
+
+@pytest.fixture(params=[1, 0], ids=["split-coop", "per-thread"])
+def pipeline(request, sipp):
+    """both Miller pipelines must be bit-exact: 1 = line kernel + cooperative accumulation (default), 0 = one loop per thread"""
+    from sipp_b200 import _lib
+    sipp.set_option(_lib.OPT_PIPELINE, request.param)
+    yield request.param
+    sipp.set_option(_lib.OPT_PIPELINE, 1)
+
+
+def test_pairing_golden_and_oracle(sipp, oracle, golden, pipeline):
     pg = golden["pairing_gen"]
     got = sipp.pairing(H(pg["a"]), H(pg["b"]))
     assert got.hex() == pg["exact"]
@@ -107,8 +137,8 @@ def test_seeded_inputs(sipp, oracle):
         assert sipp.seeded_inputs(seed, n) == oracle.seeded_inputs(seed, n, threads=4)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 63, 64, 65, 200])
-def test_inner_product(sipp, oracle, n):
+@pytest.mark.parametrize("n", [1, 2, 3, 19, 20, 21, 63, 64, 65, 200, 1500])
+def test_inner_product(sipp, oracle, n, pipeline):
     """prover_native.rs:15-23, incl. ragged (non power of two, partial block) sizes"""
     A, B = oracle.seeded_inputs(1000 + n, n, threads=4)
     assert sipp.inner_product(A, B) == oracle.inner_product(A, B, threads=4)
@@ -120,7 +150,7 @@ def test_inner_product_empty_and_mismatch(sipp):
         sipp.inner_product(bytes(64), b"")  # assert_eq!(A.len(), B.len())
 
 
-def test_inner_product_with_identities(sipp, oracle):
+def test_inner_product_with_identities(sipp, oracle, pipeline):
     A, B = oracle.seeded_inputs(5, 8, threads=4)
     A = bytearray(A); B = bytearray(B)
     A[64:128] = bytes(64); B[128 * 5:128 * 6] = bytes(128)
@@ -154,7 +184,7 @@ def test_fold_round(sipp, oracle):
     ctx.close()
 
 
-def test_prove_golden(sipp, golden):
+def test_prove_golden(sipp, golden, pipeline):
     """whole proofs against the committed golden vectors (pure-Python model), incl. identity / doubling inputs"""
     for c in golden["prove"]:
         proof = sipp.sipp_prove_native(H(c["A"]), H(c["B"]))
@@ -277,6 +307,14 @@ def test_sharded_prove_single_rank(sipp, oracle):
     A, B = oracle.seeded_inputs(78, 16, threads=4)
     proof = sharded_prove(CudaEngine(), A, B, 16, A, B, rank=0, world=1)
     assert b"".join(proof) == oracle.sipp_prove(A, B, threads=4)
+
+
+def test_inner_product_many_pairs_per_group(sipp, oracle):
+    """enough pairs that every 6-lane group folds several pairs into one accumulator (shared squaring, kpg > 1)"""
+    n = 20000
+    A, B = sipp.seeded_inputs(6, 2048)
+    A, B = (A * 10)[:64 * n], (B * 10)[:128 * n]
+    assert sipp.inner_product(A, B) == oracle.inner_product(A, B, threads=16)
 
 
 def test_roundtrip_property_large(sipp):
