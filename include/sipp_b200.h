@@ -142,6 +142,10 @@ int sipp_test_fq_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, si
 /* op: 0 mul, 1 sqr, 2 inv, 3..5 frobenius^1..3, 6 conj, 7 cyclotomic sqr, 8 cyclotomic ^x; elements 384 B.
  * op + 20 runs the 6-lane cooperative version (29 = cooperative final exponentiation) */
 int sipp_test_fq12_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t count);
+/* host only (no GPU needed): the per-round recoding of the challenge handed to the fold kernel -- GLV (G1, x) and GLS
+ * (G2, x^-1) sub-scalars in non-adjacent form.  Writes the raw plan as 32-bit words: 6 components (2 for G1, then 4 for
+ * G2) of {plus[5], minus[5], neg}, then g1_bits, g2_bits; returns the number of words written or a negative status. */
+int sipp_test_fold_plan(const uint8_t x[32], const uint8_t x_inv[32], uint32_t *out_words, size_t out_cap);
 /* which: 0 mad.lo.u32 chains, 1 mad.wide.u32 chains, 2 lo/hi carry chains, 3 fq_mul PTX, 4 fq_mul portable.
  * returns operations per second (IMAD instructions for 0-2, Fq multiplications for 3-4) in *ops_per_s */
 int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);

@@ -109,7 +109,7 @@ __device__ __forceinline__ Fq2 select_fq2(bool c, const Fq2& a, const Fq2& b) {
     return r;
 }
 
-__device__ __noinline__ Fq2 coop_mul(const Lane6& L, const Fq2& a, const Fq2& b) {
+static __device__ __noinline__ Fq2 coop_mul(const Lane6& L, const Fq2& a, const Fq2& b) {
     const int k = L.k < 6 ? L.k : 0;
     Fq2 xb = fq2_mul_xi(b);
     Fq2 acc;
@@ -152,7 +152,7 @@ __device__ __forceinline__ void store_fq2_words(uint32_t* p, const Fq2& v) {
     q[2] = make_uint4(v.c1.l[0], v.c1.l[1], v.c1.l[2], v.c1.l[3]);
     q[3] = make_uint4(v.c1.l[4], v.c1.l[5], v.c1.l[6], v.c1.l[7]);
 }
-__device__ __noinline__ Fq2 coop_sparse(const Lane6& L, const Fq2& g, const uint32_t* line) {
+static __device__ __noinline__ Fq2 coop_sparse(const Lane6& L, const Fq2& g, const uint32_t* line) {
     const int k = L.k < 6 ? L.k : 0;
     Fq2 gm1 = shfl_fq2(g, L.base + (k + 5) % 6);
     Fq2 gm3 = shfl_fq2(g, L.base + (k + 3) % 6);
@@ -162,7 +162,7 @@ __device__ __noinline__ Fq2 coop_sparse(const Lane6& L, const Fq2& g, const uint
     return lane_sparse(g, gm1, gm3, l0, l1s, l3s);
 }
 
-__device__ __noinline__ Fq2 coop_cyc_sqr(const Lane6& L, const Fq2& g) {
+static __device__ __noinline__ Fq2 coop_cyc_sqr(const Lane6& L, const Fq2& g) {
     const int k = L.k < 6 ? L.k : 0;
     Fq2 partner = shfl_fq2(g, L.base + (k + 3) % 6);
     Fq2 a = (k < 3) ? g : partner;
@@ -174,10 +174,10 @@ __device__ __noinline__ Fq2 coop_cyc_sqr(const Lane6& L, const Fq2& g) {
     return lane_cyc_finish(k, t, g);
 }
 __device__ __forceinline__ Fq2 coop_conj(const Lane6& L, const Fq2& g) { return lane_conj(L.k, g); }
-__device__ __noinline__ Fq2 coop_frob(const Lane6& L, const Fq2& g, int power) { return lane_frob(L.k < 6 ? L.k : 0, g, power); }
+static __device__ __noinline__ Fq2 coop_frob(const Lane6& L, const Fq2& g, int power) { return lane_frob(L.k < 6 ? L.k : 0, g, power); }
 
 // a^x for the BN parameter x (a in the cyclotomic subgroup)
-__device__ __noinline__ Fq2 coop_cyc_exp_x(const Lane6& L, const Fq2& a) {
+static __device__ __noinline__ Fq2 coop_cyc_exp_x(const Lane6& L, const Fq2& a) {
     Fq2 acc = a;
     const unsigned long long x = SIPP_BN_X;
 #pragma unroll 1
@@ -190,7 +190,7 @@ __device__ __noinline__ Fq2 coop_cyc_exp_x(const Lane6& L, const Fq2& a) {
 
 // f^-1: n = f * conj(f) lies in Fq6 = span{w^0, w^2, w^4}; invert it with the cubic-extension adjugate (computed
 // redundantly on every lane) and multiply back
-__device__ __noinline__ Fq2 coop_inv(const Lane6& L, const Fq2& f) {
+static __device__ __noinline__ Fq2 coop_inv(const Lane6& L, const Fq2& f) {
     const int k = L.k < 6 ? L.k : 0;
     Fq2 cf = coop_conj(L, f);
     Fq2 n = coop_mul(L, f, cf);
@@ -207,7 +207,7 @@ __device__ __noinline__ Fq2 coop_inv(const Lane6& L, const Fq2& f) {
 }
 
 // final exponentiation f^((p^12-1)/r) (+ the arkworks multiple if ark_norm), all six lanes of a group cooperating
-__device__ __noinline__ Fq2 coop_final_exp(const Lane6& L, const Fq2& f, bool ark_norm) {
+static __device__ __noinline__ Fq2 coop_final_exp(const Lane6& L, const Fq2& f, bool ark_norm) {
     Fq2 t = coop_mul(L, coop_conj(L, f), coop_inv(L, f));
     Fq2 m = coop_mul(L, coop_frob(L, t, 2), t);
     Fq2 mx = coop_cyc_exp_x(L, m);

@@ -97,6 +97,30 @@ SIPP_HD Jac<F> jac_add_affine(const Jac<F>& p, const Affine<F>& q) {
     return r;
 }
 
+// P + Q, both Jacobian (add-2007-bl without the Z-sum trick: 12M + 4S); handles identities, P = Q and P = -Q.
+template <class F>
+SIPP_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
+    if (f_is_zero(p.z)) return q;
+    if (f_is_zero(q.z)) return p;
+    F z1z1 = f_sqr(p.z), z2z2 = f_sqr(q.z);
+    F u1 = f_mul(p.x, z2z2), u2 = f_mul(q.x, z1z1);
+    F s1 = f_mul(f_mul(p.y, q.z), z2z2), s2 = f_mul(f_mul(q.y, p.z), z1z1);
+    F h = f_sub(u2, u1);
+    F rr = f_sub(s2, s1);
+    if (f_is_zero(h)) {
+        if (f_is_zero(rr)) return jac_dbl(p);
+        return jac_identity<F>();
+    }
+    F hh = f_sqr(h);
+    F hhh = f_mul(hh, h);
+    F v = f_mul(u1, hh);
+    Jac<F> r;
+    r.x = f_sub(f_sub(f_sub(f_sqr(rr), hhh), v), v);
+    r.y = f_sub(f_mul(rr, f_sub(v, r.x)), f_mul(s1, hhh));
+    r.z = f_mul(f_mul(p.z, q.z), h);
+    return r;
+}
+
 template <class F>
 SIPP_HD Affine<F> jac_to_affine(const Jac<F>& p) {
     Affine<F> r;
@@ -130,6 +154,42 @@ template <class F>
 SIPP_HD Jac<F> fold_point_jac(const Affine<F>& p1, const Affine<F>& p2, const uint32_t* k) {
     Jac<F> t = jac_scalar_mul(p2, k);
     return jac_add_affine(t, p1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// endomorphisms used by the lane-split fold (fold_plan.h): component j of an element works on endo^j(P)
+//   G1: phi(x, y) = (beta x, y) = [L1] P            G2: psi(x, y) = (conj(x) g_{1,2}, conj(y) g_{1,3}) = [6x^2] P
+// psi^j(x, y) = (conj^j(x) gamma[j][2], conj^j(y) gamma[j][3])  (gamma[j][i] = xi^(i (p^j - 1) / 6), tower.cuh)
+SIPP_HD G1A endo_apply(const G1A& p, int j) {
+    if (j == 0) return p;
+    G1A r;
+    r.x = fq_mul(p.x, Fq SIPP_GLV_BETA_INIT);
+    r.y = p.y;
+    return r;
+}
+SIPP_HD G2A endo_apply(const G2A& p, int j) {
+    if (j == 0) return p;
+    G2A r;
+    r.x = f_mul((j & 1) ? fq2_conj(p.x) : p.x, frob_gamma(j, 2));
+    r.y = f_mul((j & 1) ? fq2_conj(p.y) : p.y, frob_gamma(j, 3));
+    return r;
+}
+
+// sum_i (plus_i - minus_i) 2^i * Q over `bits` NAF digits (masks shared by the whole warp: uniform branches)
+template <class F>
+SIPP_HD Jac<F> jac_scalar_mul_naf(const Affine<F>& q, const uint32_t* plus, const uint32_t* minus, int bits) {
+    Jac<F> acc = jac_identity<F>();
+    for (int i = bits - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        const uint32_t m = 1u << (i & 31);
+        const bool dp = (plus[i >> 5] & m) != 0, dm = (minus[i >> 5] & m) != 0;
+        if (dp || dm) {
+            Affine<F> t = q;
+            if (dm) t.y = f_neg(q.y);
+            acc = jac_add_affine(acc, t);
+        }
+    }
+    return acc;
 }
 
 }  // namespace sipp

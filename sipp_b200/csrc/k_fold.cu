@@ -1,22 +1,95 @@
 // k_fold.cu -- see kernels overview in device_common.cuh
+#include "coop.cuh"
 #include "device_common.cuh"
+#include "fold_plan.h"
 
 namespace sipp {
 
 // ------------------------------------------------------------------------------------------------ K4
-__global__ void __launch_bounds__(64) k_fold_g1(uint32_t* __restrict__ A, size_t h, Scalar256 k) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= h) return;
-    G1A p1 = load_g1(A, i), p2 = load_g1(A, i + h);
-    G1A r = jac_to_affine(fold_point_jac(p1, p2, k.w));
-    store_g1(A, i, r);
+// Fixed-scalar fold, lane-split over the endomorphism components (fold_plan.h).
+//   A_i <- A_i + x A_{i+h}       /root/reference/src/prover_native.rs:60-64
+//   B_i <- B_i + x^-1 B_{i+h}    /root/reference/src/prover_native.rs:65-69
+// One launch covers both groups.  Blocks [0, g2_blocks) fold 32 G2 elements each: warp j multiplies psi^j(B_{i+h}) by the
+// 66-bit sub-scalar k_j (NAF, Jacobian accumulator, mixed additions) -- the digit tests are warp-uniform because a whole
+// warp works on the same component; warps 1..3 hand their partial sums to warp 0 through shared memory, which adds them,
+// adds B_i and normalises to affine.  The remaining blocks fold 64 G1 elements each the same way with the two GLV
+// components (warps 0/1 and 2/3).  Against one thread per element this shortens the dependent chain from 254 doublings
+// to 66 (G2) / 128 (G1) at equal total work, which is what the latency-bound rounds (n <= 2^14 per GPU) need.
+#define SIPP_FOLD_THREADS 128
+
+template <class F>
+__device__ __forceinline__ void store_jac(uint32_t* dst, const Jac<F>& p);
+template <>
+__device__ __forceinline__ void store_jac<Fq2>(uint32_t* dst, const Jac<Fq2>& p) {
+    store_fq2_words(dst, p.x); store_fq2_words(dst + 16, p.y); store_fq2_words(dst + 32, p.z);
 }
-__global__ void __launch_bounds__(64) k_fold_g2(uint32_t* __restrict__ B, size_t h, Scalar256 k) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= h) return;
-    G2A p1 = load_g2(B, i), p2 = load_g2(B, i + h);
-    G2A r = jac_to_affine(fold_point_jac(p1, p2, k.w));
-    store_g2(B, i, r);
+__device__ __forceinline__ Jac<Fq2> load_jac2(const uint32_t* src) {
+    Jac<Fq2> p;
+    p.x = load_fq2_words(src); p.y = load_fq2_words(src + 16); p.z = load_fq2_words(src + 32);
+    return p;
+}
+__device__ __forceinline__ void store_fq_words(uint32_t* p, const Fq& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ Fq load_fq_words(const uint32_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    return Fq{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+template <>
+__device__ __forceinline__ void store_jac<Fq>(uint32_t* dst, const Jac<Fq>& p) {
+    store_fq_words(dst, p.x); store_fq_words(dst + 8, p.y); store_fq_words(dst + 16, p.z);
+}
+__device__ __forceinline__ Jac<Fq> load_jac1(const uint32_t* src) {
+    Jac<Fq> p;
+    p.x = load_fq_words(src); p.y = load_fq_words(src + 8); p.z = load_fq_words(src + 16);
+    return p;
+}
+
+// [k_j] (+-) endo^j(p2) for this warp's component
+template <class F>
+__device__ __forceinline__ Jac<F> fold_component(const Affine<F>& p2, const FoldComp& c, int j, int bits) {
+    Affine<F> q = endo_apply(p2, j);
+    if (c.neg) q.y = f_neg(q.y);
+    return jac_scalar_mul_naf(q, c.plus, c.minus, bits);
+}
+
+__global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_split(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, FoldPlan plan_arg,
+                                                                 unsigned g2_blocks) {
+    __shared__ FoldPlan plan;
+    __shared__ __align__(16) uint32_t xch[3 * 32 * 48];  // G2: [3 comps][32 lanes][48 words]; G1: [2 halves][32 lanes][24 words]
+    for (int i = threadIdx.x; i < (int)(sizeof(FoldPlan) / 4); i += blockDim.x) ((uint32_t*)&plan)[i] = ((const uint32_t*)&plan_arg)[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x < g2_blocks) {
+        size_t i = (size_t)blockIdx.x * 32 + lane;
+        const bool valid = i < h;
+        if (!valid) i = h - 1;
+        Jac<Fq2> acc = fold_component(load_g2(B, i + h), plan.g2[warp], warp, plan.g2_bits);
+        if (warp > 0) store_jac(xch + ((warp - 1) * 32 + lane) * 48, acc);
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll 1
+            for (int j = 0; j < 3; j++) acc = jac_add(acc, load_jac2(xch + (j * 32 + lane) * 48));
+            G2A r = jac_to_affine(jac_add_affine(acc, load_g2(B, i)));
+            if (valid) store_g2(B, i, r);
+        }
+    } else {
+        const int comp = warp & 1, half = warp >> 1;
+        size_t i = (size_t)(blockIdx.x - g2_blocks) * 64 + half * 32 + lane;
+        const bool valid = i < h;
+        if (!valid) i = h - 1;
+        Jac<Fq> acc = fold_component(load_g1(A, i + h), plan.g1[comp], comp, plan.g1_bits);
+        if (comp == 1) store_jac(xch + (half * 32 + lane) * 24, acc);
+        __syncthreads();
+        if (comp == 0) {
+            acc = jac_add(acc, load_jac1(xch + (half * 32 + lane) * 24));
+            G1A r = jac_to_affine(jac_add_affine(acc, load_g1(A, i)));
+            if (valid) store_g1(A, i, r);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ inputs
@@ -65,9 +138,11 @@ __global__ void __launch_bounds__(64) k_seeded_inputs(uint64_t seed, size_t n, u
 }
 
 
-int launch_fold(uint32_t* A, uint32_t* B, size_t h, const Scalar256& x, const Scalar256& xinv, cudaStream_t s) {
-    k_fold_g1<<<(unsigned)((h + 63) / 64), 64, 0, s>>>(A, h, x);
-    k_fold_g2<<<(unsigned)((h + 63) / 64), 64, 0, s>>>(B, h, xinv);
+int launch_fold(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s) {
+    // In-place: an element's partner i + h is only read by the block that owns i, and i < h <= i + h, so no block reads
+    // what another block writes.
+    unsigned g2_blocks = (unsigned)((h + 31) / 32), g1_blocks = (unsigned)((h + 63) / 64);
+    k_fold_split<<<g2_blocks + g1_blocks, SIPP_FOLD_THREADS, 0, s>>>(A, B, h, plan, g2_blocks);
     return (int)cudaGetLastError();
 }
 int launch_seeded_inputs(uint64_t seed, size_t n, uint32_t* dA, uint32_t* dB, cudaStream_t s) {

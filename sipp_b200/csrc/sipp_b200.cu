@@ -414,14 +414,15 @@ int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
     if (!c || !x || !x_inv) return fail(SIPP_ERR_ARG, "null argument");
     if (c->n < 2) return fail(SIPP_ERR_ARG, "fold needs n >= 2");
     size_t h = c->n / 2;
-    Scalar256 kx = scalar_from_bytes(x), ki = scalar_from_bytes(x_inv);
+    FoldPlan plan;
+    if (fold_plan_build(x, x_inv, &plan)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
     {
         Span sp(2, g_stream);
         // new_A = a1 + a2.mul(x)  prover_native.rs:60-64;  new_B = b1 + b2.mul(inv_x)  :65-69
-        int e = launch_fold(c->dA, c->dB, h, kx, ki, g_stream);
+        int e = launch_fold(c->dA, c->dB, h, plan, g_stream);
         if (e) return cuda_fail((cudaError_t)e, "k_fold");
     }
-    g_stats.launches += 2;
+    g_stats.launches += 1;
     g_stats.fold_points += h;
     c->n = h;                                                                       // n = n / 2   :74
     return SIPP_OK;
@@ -755,6 +756,14 @@ int sipp_test_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, 
     cudaFree(da); cudaFree(dout); if (db) cudaFree(db);
     if (e != cudaSuccess) return cuda_fail(e, "sipp_test_fq12_op");
     return SIPP_OK;
+}
+
+int sipp_test_fold_plan(const uint8_t x[32], const uint8_t x_inv[32], uint32_t* out_words, size_t out_cap) {
+    if (!x || !x_inv || !out_words || out_cap < sizeof(FoldPlan) / 4) return fail(SIPP_ERR_ARG, "bad argument");
+    FoldPlan plan;
+    if (fold_plan_build(x, x_inv, &plan)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
+    memcpy(out_words, &plan, sizeof plan);
+    return (int)(sizeof(FoldPlan) / 4);
 }
 
 int sipp_microbench(int which, int iters, double* ops_per_s, double* ms_out) {

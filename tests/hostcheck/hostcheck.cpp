@@ -81,3 +81,33 @@ int hc_fold_g2(const uint8_t* p1, const uint8_t* p2, const uint8_t* k, uint8_t* 
 }  // extern "C"
 
 #include "hostcheck_coop.inc"
+
+// lane-split fold (k_fold_split): the per-warp component products and the combine step, emulated sequentially with
+// the device code's own functions; the plan comes from the product's host recoder (glv.cc, linked into this harness)
+#include "../../sipp_b200/csrc/fold_plan.h"
+extern "C" int hc_fold_split_g1(const uint8_t* p1, const uint8_t* p2, const uint8_t* x, const uint8_t* xinv, uint8_t* out) {
+    FoldPlan plan;
+    if (fold_plan_build(x, xinv, &plan)) return -1;
+    G1A a1 = g1_decode(W(p1)), a2 = g1_decode(W(p2));
+    Jac<Fq> acc = jac_identity<Fq>();
+    for (int j = 0; j < 2; j++) {
+        G1A q = endo_apply(a2, j);
+        if (plan.g1[j].neg) q.y = f_neg(q.y);
+        acc = jac_add(acc, jac_scalar_mul_naf(q, plan.g1[j].plus, plan.g1[j].minus, plan.g1_bits));
+    }
+    g1_encode(W(out), jac_to_affine(jac_add_affine(acc, a1)));
+    return 0;
+}
+extern "C" int hc_fold_split_g2(const uint8_t* p1, const uint8_t* p2, const uint8_t* x, const uint8_t* xinv, uint8_t* out) {
+    FoldPlan plan;
+    if (fold_plan_build(x, xinv, &plan)) return -1;
+    G2A b1 = g2_decode(W(p1)), b2 = g2_decode(W(p2));
+    Jac<Fq2> acc = jac_identity<Fq2>();
+    for (int j = 0; j < 4; j++) {
+        G2A q = endo_apply(b2, j);
+        if (plan.g2[j].neg) q.y = f_neg(q.y);
+        acc = jac_add(acc, jac_scalar_mul_naf(q, plan.g2[j].plus, plan.g2[j].minus, plan.g2_bits));
+    }
+    g2_encode(W(out), jac_to_affine(jac_add_affine(acc, b1)));
+    return 0;
+}

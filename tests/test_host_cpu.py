@@ -110,3 +110,40 @@ def test_shard_indices():
         for i in range(m // 2):
             assert i % G == (i + m // 2) % G
         m //= 2
+
+
+def test_fold_plan_recoding():
+    """host recoding of the round challenge for the fold kernel (glv.cc): sum_j (+-NAF_j) L^j == k (mod r) for the GLV
+    (G1, x) and GLS (G2, x^-1) decompositions, sub-scalars short, NAF digits non-adjacent"""
+    import random
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    lib.sipp_test_fold_plan.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.c_size_t]
+    R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    X = 4965661367192848881
+    L2 = 6 * X * X
+    L1 = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    assert (L1 * L1 + L1 + 1) % R == 0 and (L2**4 - L2**2 + 1) % R == 0
+    rng = random.Random(8)
+
+    def naf_value(words):
+        plus = sum(words[i] << (32 * i) for i in range(5))
+        minus = sum(words[5 + i] << (32 * i) for i in range(5))
+        assert plus & minus == 0
+        nz = plus | minus
+        assert nz & (nz >> 1) == 0, "adjacent non-zero digits"
+        v = plus - minus
+        return -v if words[10] else v, nz.bit_length()
+
+    cases = [(1, 1), (2, pow(2, -1, R)), (R - 1, R - 1), (L1, L2), (L2 % R, L1)] + [(rng.randrange(1, R),) * 2 for _ in range(300)]
+    for kx, ki in cases:
+        buf = (ctypes.c_uint32 * 128)()
+        nw = lib.sipp_test_fold_plan(kx.to_bytes(32, "little"), ki.to_bytes(32, "little"), buf, 128)
+        assert nw == 6 * 11 + 2
+        w = list(buf[:nw])
+        comps = [naf_value(w[11 * j:11 * j + 11]) for j in range(6)]
+        g1_bits, g2_bits = w[66], w[67]
+        assert sum(v * pow(L1, j, R) for j, (v, _) in enumerate(comps[:2])) % R == kx
+        assert sum(v * pow(L2, j, R) for j, (v, _) in enumerate(comps[2:])) % R == ki
+        assert g1_bits == max(b for _, b in comps[:2]) and g1_bits <= 130
+        assert g2_bits == max(b for _, b in comps[2:]) and g2_bits <= 68

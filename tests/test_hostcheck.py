@@ -1,0 +1,105 @@
+"""The kernels' ALGORITHMS on the CPU: tests/hostcheck compiles the device headers (sipp_b200/csrc/*.cuh) for the host
+with g++ -- the PTX carry chains replaced by the plain-C++ emulation in fq.cuh, warp shuffles by array reads -- and every
+layer is compared with the oracle.  This is test infrastructure only (the product never computes on the host); it lets
+algorithm changes be checked without a GPU, the `-m gpu` tests then check the real kernels."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HC = os.path.join(ROOT, "tests", "hostcheck")
+P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+def le(v): return v.to_bytes(32, "little")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC, "hostcheck.so")
+    srcs = [os.path.join(HC, "hostcheck.cpp"), os.path.join(ROOT, "sipp_b200", "csrc", "glv.cc")]
+    deps = srcs + [os.path.join(HC, "hostcheck_coop.inc")] + [os.path.join(ROOT, "sipp_b200", "csrc", f)
+                                                               for f in os.listdir(os.path.join(ROOT, "sipp_b200", "csrc")) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", so] + srcs)
+    return ctypes.CDLL(so)
+
+
+def _buf(n): return ctypes.create_string_buffer(n)
+
+
+def test_fq_and_dot(hc, oracle):
+    rng = random.Random(1)
+    edge = [0, 1, 2, P - 1, P - 2, 2**256 % P, (P - 1) // 2, 2**32 - 1]
+    xs = edge + [rng.randrange(P) for _ in range(300)]
+    ys = list(reversed(edge)) + [rng.randrange(P) for _ in range(300)]
+    a, b = b"".join(map(le, xs)), b"".join(map(le, ys))
+    for op, name in ((0, "FQ_MUL"), (1, "FQ_MUL"), (2, "FQ_ADD"), (3, "FQ_SUB")):
+        out = _buf(len(a))
+        assert hc.hc_fq_op(op, a, b, out, len(xs)) == 0
+        assert out.raw == oracle.field_op(name, a, b)
+    out = _buf(32 * 20)
+    hc.hc_fq_op(4, a, None, out, 20)
+    assert out.raw == oracle.field_op("FQ_INV", a[:32 * 20])
+    for n in (1, 2, 3, 4, 5, 6, 8, 12):
+        for trial in range(6):
+            big = trial == 0  # all operands p - 1: the largest lazy sum
+            u = [P - 1 if big else rng.randrange(P) for _ in range(n)]
+            v = [P - 1 if big else rng.randrange(P) for _ in range(n)]
+            out = _buf(32)
+            assert hc.hc_fq_dot(n, b"".join(map(le, u)), b"".join(map(le, v)), out) == 0
+            assert int.from_bytes(out.raw, "little") == sum(x * y for x, y in zip(u, v)) % P
+
+
+def test_fq12_and_coop(hc, oracle):
+    rng = random.Random(2)
+    a = b"".join(le(rng.randrange(P)) for _ in range(12))
+    b = b"".join(le(rng.randrange(P)) for _ in range(12))
+    out = _buf(384)
+    for op, name in ((0, "FQ12_MUL"), (1, "FQ12_SQR"), (2, "FQ12_INV"), (3, "FQ12_FROB1"), (4, "FQ12_FROB2"), (5, "FQ12_FROB3"), (6, "FQ12_CONJ")):
+        assert hc.hc_fq12_op(op, a, b if op == 0 else None, out) == 0
+        assert out.raw == oracle.field_op(name, a, b if op == 0 else None), name
+    hc.hc_coop_op(0, a, b, out)
+    assert out.raw == oracle.field_op("FQ12_MUL", a, b)
+    for op, name in ((3, "FQ12_FROB1"), (4, "FQ12_FROB2"), (5, "FQ12_FROB3"), (6, "FQ12_CONJ")):
+        hc.hc_coop_op(op, a, None, out)
+        assert out.raw == oracle.field_op(name, a)
+    A, B = oracle.seeded_inputs(3, 1)
+    gt = oracle.pairing(A, B)
+    hc.hc_coop_op(1, gt, None, out)
+    assert out.raw == oracle.field_op("FQ12_SQR", gt)
+    hc.hc_fq12_op(7, gt, None, out)
+    assert out.raw == oracle.field_op("FQ12_SQR", gt)
+
+
+def test_pairing_and_inner_product(hc, oracle):
+    A, B = oracle.seeded_inputs(21, 3)
+    out = _buf(384)
+    hc.hc_pairing(A[:64], B[:128], out, 0)
+    assert out.raw == oracle.pairing(A[:64], B[:128])
+    hc.hc_inner_product(A, B, 3, out)
+    assert out.raw == oracle.inner_product(A, B)
+
+
+def test_fold_split(hc, oracle):
+    """the lane-split GLV / GLS fold == the oracle's plain double-and-add fold, incl. exceptional points and scalars"""
+    rng = random.Random(5)
+    A, B = oracle.seeded_inputs(33, 4)
+    a1, a2, b1, b2 = A[:64], A[64:128], B[:128], B[128:256]
+    scalars = [1, 2, 3, R - 1, R - 2, 6 * 4965661367192848881**2] + [rng.randrange(1, R) for _ in range(6)]
+    for k in scalars:
+        x = le(k)
+        cases1 = [(a1, a2), (bytes(64), a2), (a1, bytes(64)), (oracle.g1_mul(a2, x), a2), (oracle.g1_mul(a2, le(R - k)), a2)]
+        for p1, p2 in cases1:
+            out = _buf(64)
+            assert hc.hc_fold_split_g1(p1, p2, x, x, out) == 0
+            assert out.raw == oracle.fold_g1(p1 + p2, x)
+        cases2 = [(b1, b2), (bytes(128), b2), (b1, bytes(128)), (oracle.g2_mul(b2, x), b2), (oracle.g2_mul(b2, le(R - k)), b2)]
+        for p1, p2 in cases2:
+            out = _buf(128)
+            assert hc.hc_fold_split_g2(p1, p2, x, x, out) == 0
+            assert out.raw == oracle.fold_g2(p1 + p2, x)
