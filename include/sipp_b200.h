@@ -101,7 +101,9 @@ void sipp_transcript_append_g2(sipp_transcript *t, const uint8_t b[128]);       
 void sipp_transcript_get_challenge(const sipp_transcript *t, uint8_t x[32]);           /* :56-65 */
 /* absorb n (A_i, B_i) pairs in order: the loop at prover_native.rs:36-39 / verifier_native.rs:25-28 */
 void sipp_transcript_append_pairs(sipp_transcript *t, const uint8_t *A, const uint8_t *B, size_t n);
-void sipp_poseidon_permute(uint64_t state[12]);
+void sipp_poseidon_permute(uint64_t state[12]);          /* AVX-512 when the CPU has it, else portable */
+void sipp_poseidon_permute_portable(uint64_t state[12]);
+int sipp_poseidon_backend(void);                          /* 1 = AVX-512, 0 = portable */
 
 /* ---- whole protocol with the C++ host transcript inside (what the Python mirror and bench.py call) ------ */
 /* pub fn sipp_prove_native(A, B) -> Vec<Fq12>                  prover_native.rs:26-80

@@ -1,0 +1,23 @@
+// poseidon_fast.h -- tables shared by the portable (transcript.cc) and AVX-512 (poseidon_avx512.cc) Poseidon code.
+#pragma once
+#include <stdint.h>
+
+namespace sipp {
+
+// Sparse-form partial rounds (derivation in transcript.cc) plus vector-friendly copies of the round constants.
+struct PoseidonFastTables {
+    alignas(64) uint64_t rc_full[8][16];   // round constants of the 4 + 4 full rounds, lanes 12..15 = 0
+    alignas(64) uint64_t first[16];        // constants added before the first partial round
+    alignas(64) uint64_t w16[22][16];      // w16[r][i] = w_r[i - 1] for i = 1..11, 0 elsewhere
+    alignas(64) double mds_c0a[8];         // CIRC[0] + 8 in lane 0, CIRC[0] elsewhere
+    double mds_circ[12];
+    uint64_t post[22];
+    uint64_t init[11][11];
+    uint64_t vhat[22][11];
+    uint64_t m00;
+};
+
+void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T);
+bool poseidon_avx512_supported();
+
+}  // namespace sipp

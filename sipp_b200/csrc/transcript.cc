@@ -5,9 +5,11 @@
 // points / Fq12 elements, and `get_challenge` with num-bigint's zero-stripping `to_u32_digits`.
 // The transcript is a strictly sequential chain and stays on the host (north star: "transcript_native ... stay as
 // they are"); the prover overlaps the 8n-permutation absorb of A, B with the GPU's first products.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/sipp_b200.h"
+#include "poseidon_fast.h"
 #include "poseidon_rc.h"
 
 namespace {
@@ -182,8 +184,27 @@ void init_fast_partial() {
             for (int k = 0; k < 12; k++) cur[r][k] = nxt[r][k];
     }
 }
+sipp::PoseidonFastTables g_tab;
+bool g_use_avx512 = false;
 struct FastPartialInit {
-    FastPartialInit() { init_fast_partial(); }
+    FastPartialInit() {
+        init_fast_partial();
+        memset(&g_tab, 0, sizeof g_tab);
+        for (int k = 0; k < 8; k++)
+            for (int i = 0; i < 12; i++) g_tab.rc_full[k][i] = SIPP_POSEIDON_RC[12 * (k < 4 ? k : 22 + k) + i];
+        for (int i = 0; i < 12; i++) g_tab.first[i] = g_fp.first[i];
+        for (int r = 0; r < 22; r++) {
+            g_tab.post[r] = g_fp.post[r];
+            for (int i = 0; i < 11; i++) { g_tab.w16[r][i + 1] = g_fp.w[r][i]; g_tab.vhat[r][i] = g_fp.vhat[r][i]; }
+        }
+        for (int i = 0; i < 11; i++)
+            for (int j = 0; j < 11; j++) g_tab.init[i][j] = g_fp.init[i][j];
+        for (int i = 0; i < 12; i++) g_tab.mds_circ[i] = (double)MDS_CIRC[i];
+        for (int i = 0; i < 8; i++) g_tab.mds_c0a[i] = (double)(MDS_CIRC[0] + (i == 0 ? 8 : 0));
+        g_tab.m00 = g_fp.m00;
+        const char* force = getenv("SIPP_POSEIDON");  // "portable" forces the scalar path (tests compare both)
+        g_use_avx512 = sipp::poseidon_avx512_supported() && !(force && !strcmp(force, "portable"));
+    }
 } g_fp_init;
 
 // sum of 11 products of canonical-or-not u64 values, reduced once: accumulate the 128-bit products in three limbs
@@ -223,7 +244,8 @@ inline void partial_rounds(uint64_t* s) {
 
 extern "C" {
 
-void sipp_poseidon_permute(uint64_t s[12]) {
+// portable implementation (also the reference the AVX-512 path is tested against)
+void sipp_poseidon_permute_portable(uint64_t s[12]) {
     int rnd = 0;
     for (int k = 0; k < 4; k++, rnd++) {
         for (int i = 0; i < 12; i++) s[i] = gl_pow7(gl_add(s[i], SIPP_POSEIDON_RC[12 * rnd + i]));
@@ -237,6 +259,12 @@ void sipp_poseidon_permute(uint64_t s[12]) {
     }
     for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 }
+
+void sipp_poseidon_permute(uint64_t s[12]) {
+    if (g_use_avx512) sipp::poseidon_permute_avx512(s, g_tab);
+    else sipp_poseidon_permute_portable(s);
+}
+int sipp_poseidon_backend(void) { return g_use_avx512 ? 1 : 0; }
 
 void sipp_transcript_new(sipp_transcript* t) { memset(t, 0, sizeof *t); }
 

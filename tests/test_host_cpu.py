@@ -147,3 +147,26 @@ def test_fold_plan_recoding():
         assert sum(v * pow(L2, j, R) for j, (v, _) in enumerate(comps[2:])) % R == ki
         assert g1_bits == max(b for _, b in comps[:2]) and g1_bits <= 130
         assert g2_bits == max(b for _, b in comps[2:]) and g2_bits <= 68
+
+
+def test_poseidon_avx512_matches_portable():
+    """the AVX-512 permutation (used when the CPU has it) computes exactly the portable one, incl. non-canonical
+    and extreme lanes, over a long chain"""
+    import random
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    lib.sipp_poseidon_permute_portable.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+    lib.sipp_poseidon_permute_portable.restype = None
+    rng = random.Random(3)
+    PG = 2**64 - 2**32 + 1
+    special = [0, 1, PG - 1, 2**32 - 1, 2**32, 2**63, PG - 2**32]
+    st = [rng.randrange(PG) for _ in range(12)]
+    for it in range(3000):
+        if it % 5 == 0:
+            st[rng.randrange(12)] = rng.choice(special)
+        a = (ctypes.c_uint64 * 12)(*st)
+        b = (ctypes.c_uint64 * 12)(*st)
+        lib.sipp_poseidon_permute(a)
+        lib.sipp_poseidon_permute_portable(b)
+        assert list(a) == list(b), it
+        st = list(a)
