@@ -23,8 +23,15 @@ SIPP_HD void f_set_one(Fq& a) { a = fq_one(); }
 SIPP_HD void f_set_zero(Fq& a) { a = fq_zero(); }
 SIPP_HD Fq2 f_add(const Fq2& a, const Fq2& b) { return fq2_add(a, b); }
 SIPP_HD Fq2 f_sub(const Fq2& a, const Fq2& b) { return fq2_sub(a, b); }
+// Fq2 products of the group law: inlined by default; a translation unit whose kernels would otherwise outgrow the
+// instruction cache (k_lines: 47k SASS instructions when inlined) defines SIPP_CURVE_FQ2_CALLS to make them real calls
+#if defined(SIPP_CURVE_FQ2_CALLS)
+SIPP_HD Fq2 f_mul(const Fq2& a, const Fq2& b) { return fq2_mul(a, b); }
+SIPP_HD Fq2 f_sqr(const Fq2& a) { return fq2_sqr(a); }
+#else
 SIPP_HD Fq2 f_mul(const Fq2& a, const Fq2& b) { return fq2_mul_inl(a, b); }
 SIPP_HD Fq2 f_sqr(const Fq2& a) { return fq2_sqr_inl(a); }
+#endif
 SIPP_HD Fq2 f_dbl(const Fq2& a) { return fq2_dbl(a); }
 SIPP_HD Fq2 f_neg(const Fq2& a) { return fq2_neg(a); }
 SIPP_HD Fq2 f_inv(const Fq2& a) { return fq2_inv(a); }

@@ -12,6 +12,7 @@
 //   k_reduce_fe_coop  product of the partials and ONE cooperative final exponentiation per product.
 //
 // Replaces the per-pair `pairing` calls + serial product of /root/reference/src/prover_native.rs:17-22 (and :48-49).
+#define SIPP_CURVE_FQ2_CALLS 1
 #include "coop.cuh"
 #include "device_common.cuh"
 
@@ -25,7 +26,10 @@ namespace sipp {
 
 // ------------------------------------------------------------------------------------------------ L: line generation
 // A chunk covers pairs [c0, c0 + mc) of EVERY product of the job; lines layout [prod][mc][91][80 words].
-__global__ void __launch_bounds__(64) k_lines(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, MillerJob job, int nprod, size_t c0,
+#ifndef SIPP_LINES_MINBLOCKS
+#define SIPP_LINES_MINBLOCKS 4  // 230 registers; capping at 128 (8 blocks) spills and measured 8% slower (profiles/r01_ab_occupancy.txt)
+#endif
+__global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_lines(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, MillerJob job, int nprod, size_t c0,
                                               size_t mc, uint32_t* __restrict__ lines) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= mc * (size_t)nprod) return;
@@ -88,7 +92,10 @@ __device__ __noinline__ Fq2 block_product_coop(const Lane6& L, Fq2 f, uint32_t* 
 
 // grid = (blocks, nprod).  Group gid of product `prod` folds pairs [gid * kpg, (gid + 1) * kpg) of that product.
 // lines: chunk-local, pair index = prod_local_base + j.
-__global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_accum(const uint32_t* __restrict__ lines, size_t m_chunk, int nprod_in_chunk, int kpg,
+#ifndef SIPP_ACCUM_MINBLOCKS
+#define SIPP_ACCUM_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(SIPP_ACCUM_THREADS, SIPP_ACCUM_MINBLOCKS) k_accum(const uint32_t* __restrict__ lines, size_t m_chunk, int nprod_in_chunk, int kpg,
                                                             uint32_t* __restrict__ partials, int partial_stride_prod, int block_offset) {
     __shared__ __align__(16) uint32_t stage[SIPP_ACCUM_GROUPS][2][SIPP_LINE_WORDS];
     __shared__ __align__(16) uint32_t red[SIPP_ACCUM_GROUPS * 96];

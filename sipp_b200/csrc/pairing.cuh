@@ -20,8 +20,15 @@ struct G2H {
     Fq2 x, y, z;
 };
 
+#if defined(SIPP_CURVE_FQ2_CALLS)
+#define SIPP_LINE_FN SIPP_HD_NOINLINE  // one copy of each step in instruction-cache-bound kernels
+#else
+#define SIPP_LINE_FN SIPP_HD
+#endif
+SIPP_LINE_FN Fq2 fq2_scale_step(const Fq2& a, const Fq& k) { return fq2_scale(a, k); }
+
 // tangent at T, then T <- 2T.  l0 = -2YZ, l1 = 3X^2, l3 = 3b'Z^2 - Y^2.   (6 squarings + 3 products + 2 halvings)
-SIPP_HD void line_double(G2H& t, Fq2& l0, Fq2& l1, Fq2& l3) {
+SIPP_LINE_FN void line_double(G2H& t, Fq2& l0, Fq2& l1, Fq2& l3) {
     const Fq half = fq_two_inv();
     const Fq2 bt = fq2_b_twist();
     Fq2 a = fq2_scale(f_mul(t.x, t.y), half);
@@ -42,7 +49,7 @@ SIPP_HD void line_double(G2H& t, Fq2& l0, Fq2& l1, Fq2& l3) {
 }
 
 // chord through T and Q (affine), then T <- T + Q.  l0 = lambda, l1 = -theta, l3 = theta xQ - lambda yQ
-SIPP_HD void line_add(G2H& t, const G2A& q, Fq2& l0, Fq2& l1, Fq2& l3) {
+SIPP_LINE_FN void line_add(G2H& t, const G2A& q, Fq2& l0, Fq2& l1, Fq2& l3) {
     Fq2 theta = fq2_sub(t.y, f_mul(q.y, t.z));
     Fq2 lambda = fq2_sub(t.x, f_mul(q.x, t.z));
     Fq2 c = f_sqr(theta);
@@ -84,22 +91,22 @@ SIPP_HD void miller_lines(const G1A& p, const G2A& q, Sq sq, Emit emit) {
     for (int i = 63; i >= 0; i--) {
         if (i != 63) sq(step);
         line_double(t, l0, l1, l3);
-        emit(step++, fq2_scale(l0, p.y), fq2_scale(l1, p.x), l3);
-        if ((plus >> i) & 1ull) {
-            line_add(t, q, l0, l1, l3);
-            emit(step++, fq2_scale(l0, p.y), fq2_scale(l1, p.x), l3);
-        } else if ((minus >> i) & 1ull) {
-            line_add(t, nq, l0, l1, l3);
-            emit(step++, fq2_scale(l0, p.y), fq2_scale(l1, p.x), l3);
+        emit(step++, fq2_scale_step(l0, p.y), fq2_scale_step(l1, p.x), l3);
+        const bool dp = (plus >> i) & 1ull, dm = (minus >> i) & 1ull;
+        if (dp || dm) {  // one chord site for both signs: the negated point differs only in y
+            G2A qs = q;
+            if (dm) qs.y = nq.y;
+            line_add(t, qs, l0, l1, l3);
+            emit(step++, fq2_scale_step(l0, p.y), fq2_scale_step(l1, p.x), l3);
         }
     }
     G2A q1 = g2_frobenius(q);
     G2A q2 = g2_frobenius(q1);
     q2.y = fq2_neg(q2.y);
     line_add(t, q1, l0, l1, l3);
-    emit(step++, fq2_scale(l0, p.y), fq2_scale(l1, p.x), l3);
+    emit(step++, fq2_scale_step(l0, p.y), fq2_scale_step(l1, p.x), l3);
     line_add(t, q2, l0, l1, l3);
-    emit(step++, fq2_scale(l0, p.y), fq2_scale(l1, p.x), l3);
+    emit(step++, fq2_scale_step(l0, p.y), fq2_scale_step(l1, p.x), l3);
 }
 
 // One full Miller loop in one thread (baseline / small-n path).  Identity inputs contribute 1 (ark convention).

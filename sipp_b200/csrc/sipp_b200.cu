@@ -98,6 +98,45 @@ Scalar256 scalar_from_bytes(const uint8_t* b) {
     return s;
 }
 
+// Device memory pool: contexts and staging buffers are created per prove call; cudaMalloc / cudaFree cost hundreds of
+// microseconds each and cudaFree synchronises the device, so freed blocks are kept and reused (grow-only, released in
+// sipp_shutdown).  One host thread per process by contract, so no locking.
+struct PoolBlock {
+    void* ptr;
+    size_t size;
+    bool used;
+};
+std::vector<PoolBlock> g_pool;
+cudaError_t pool_alloc(void** out, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (size_t i = 0; i < g_pool.size(); i++) {
+        const PoolBlock& b = g_pool[i];
+        if (!b.used && b.size >= bytes && b.size <= 2 * bytes && (best < 0 || b.size < g_pool[best].size)) best = (int)i;
+    }
+    if (best >= 0) {
+        g_pool[best].used = true;
+        *out = g_pool[best].ptr;
+        return cudaSuccess;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    g_pool.push_back({p, bytes, true});
+    *out = p;
+    return cudaSuccess;
+}
+void pool_free(void* p) {
+    if (!p) return;
+    for (auto& b : g_pool)
+        if (b.ptr == p) { b.used = false; return; }
+    cudaFree(p);  // not from the pool
+}
+void pool_release_all() {
+    for (auto& b : g_pool) cudaFree(b.ptr);
+    g_pool.clear();
+}
+
 // device scratch shared by all contexts of this process (one host thread per process by contract)
 struct Scratch {
     uint32_t* partials = nullptr;  // [blocks][2][96]
@@ -264,10 +303,10 @@ cudaError_t order_after(cudaStream_t later, cudaStream_t earlier) {
 int ctx_alloc(size_t n, sipp_ctx** out) {
     sipp_ctx* c = new sipp_ctx();
     c->n = c->cap = n;
-    cudaError_t e = cudaMalloc(&c->dA, n * 16 * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&c->dB, n * 32 * sizeof(uint32_t));
+    cudaError_t e = pool_alloc((void**)&c->dA, n * 16 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = pool_alloc((void**)&c->dB, n * 32 * sizeof(uint32_t));
     if (e != cudaSuccess) {
-        if (c->dA) cudaFree(c->dA);
+        pool_free(c->dA);
         delete c;
         return cuda_fail(e, "cudaMalloc(ctx)");
     }
@@ -296,6 +335,7 @@ int sipp_init(int device) {
         if (g_stream) cudaStreamDestroy(g_stream);
         g_stream = nullptr;
         g_scr = Scratch();
+        pool_release_all();
     }
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
@@ -314,6 +354,7 @@ int sipp_shutdown(void) {
     if (g_scr.flag) cudaFree(g_scr.flag);
     if (g_scr.lines) cudaFree(g_scr.lines);
     g_scr = Scratch();
+    pool_release_all();
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
     g_device = -1;
@@ -378,22 +419,24 @@ int sipp_ctx_create(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out
     if (rc) return rc;
     if (!A || !B || !out || n == 0) return fail(SIPP_ERR_ARG, "sipp_ctx_create: null pointer or n == 0");
     uint8_t *tA = nullptr, *tB = nullptr;
-    CK(cudaMalloc(&tA, n * 64));
-    cudaError_t e = cudaMalloc(&tB, n * 128);
-    if (e != cudaSuccess) { cudaFree(tA); return cuda_fail(e, "cudaMalloc"); }
+    CK(pool_alloc((void**)&tA, n * 64));
+    cudaError_t e = pool_alloc((void**)&tB, n * 128);
+    if (e != cudaSuccess) { pool_free(tA); return cuda_fail(e, "cudaMalloc"); }
     e = cudaMemcpyAsync(tA, A, n * 64, cudaMemcpyHostToDevice, g_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(tB, B, n * 128, cudaMemcpyHostToDevice, g_stream);
-    if (e != cudaSuccess) { cudaFree(tA); cudaFree(tB); return cuda_fail(e, "H2D"); }
-    rc = sipp_ctx_create_from_device(tA, tB, n, out);
-    cudaFree(tA);
-    cudaFree(tB);
+    if (e != cudaSuccess) { pool_free(tA); pool_free(tB); return cuda_fail(e, "H2D"); }
+    rc = sipp_ctx_create_from_device(tA, tB, n, out);  // synchronises the stream: the staging blocks are idle on return
+    pool_free(tA);
+    pool_free(tB);
     return rc;
 }
 
 int sipp_ctx_destroy(sipp_ctx* c) {
     if (!c) return SIPP_OK;
-    if (c->dA) cudaFree(c->dA);
-    if (c->dB) cudaFree(c->dB);
+    // every entry point that enqueues work on a context synchronises before returning results, and a block handed
+    // out again is only touched by later work on the same stream, so recycling without a device sync is safe
+    pool_free(c->dA);
+    pool_free(c->dB);
     delete c;
     return SIPP_OK;
 }
@@ -432,7 +475,7 @@ int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
     if (!c) return fail(SIPP_ERR_ARG, "null ctx");
     size_t n = c->n;
     uint32_t* tmp;
-    CK(cudaMalloc(&tmp, n * 32 * sizeof(uint32_t)));
+    CK(pool_alloc((void**)&tmp, n * 32 * sizeof(uint32_t)));
     cudaError_t e = cudaSuccess;
     if (A_out) {
         launch_codec_encode(c->dA, tmp, n * 2, g_stream);
@@ -446,7 +489,7 @@ int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
         e = cudaMemcpyAsync(B_out, tmp, n * 128, cudaMemcpyDeviceToHost, g_stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
     }
-    cudaFree(tmp);
+    pool_free(tmp);
     if (e != cudaSuccess) return cuda_fail(e, "sipp_ctx_read");
     return SIPP_OK;
 }
