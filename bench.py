@@ -272,6 +272,9 @@ def main():
         return 0
 
     assert b"".join(proof_res) == (proof_e2e if isinstance(proof_e2e, bytes) else b"".join(proof_e2e)), "resident and e2e proofs differ"
+    if world > 1:
+        # the sharded proof must be byte-identical to the single-GPU proof of the same inputs (BASELINE config 3)
+        assert b"".join(proof_res) == b"".join(sipp_b200.sipp_prove_native(A, B)), "sharded proof differs from the single-GPU proof"
     value = n * K / t_res
     e2e = n * K / t_e2e
     mill_ach = st["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / max(st["miller_ms"] * 1e-3, 1e-12)

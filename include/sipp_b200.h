@@ -72,7 +72,8 @@ int sipp_ctx_read(sipp_ctx *ctx, uint8_t *A_out, uint8_t *B_out);
 
 /* ---- multi-GPU: strided shards exchange 384-byte partial Miller products ------------------------------- */
 /* Writes this shard's un-exponentiated partial products (device format, SIPP_PARTIAL_BYTES each) to DEVICE memory
- * `d_out`, on `stream` (a cudaStream_t, may be NULL): 1 partial for `which` = 0 (Z), 2 for `which` = 1 (Z_L, Z_R).
+ * `d_out`, on `stream` (a cudaStream_t; NULL = the legacy default stream, the library orders its own non-blocking
+ * stream against it with events): 1 partial for `which` = 0 (Z), 2 for `which` = 1 (Z_L, Z_R).
  * The host all-gathers them (NCCL) and every rank, or rank 0, calls sipp_combine_partials. */
 #define SIPP_PARTIAL_BYTES 384
 int sipp_ctx_partial_products(sipp_ctx *ctx, int which, void *d_out, void *stream);

@@ -497,7 +497,9 @@ int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
 // ------------------------------------------------------------------------------------------------ multi-GPU pieces
 int sipp_ctx_partial_products(sipp_ctx* c, int which, void* d_out, void* stream) {
     if (!c || !d_out) return fail(SIPP_ERR_ARG, "null argument");
-    cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+    // NULL is the legacy default stream (what torch.cuda.current_stream().cuda_stream is unless the caller switched
+    // streams) -- NOT the library stream: g_stream is non-blocking and does not synchronise with it implicitly.
+    cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
     // the caller's stream (e.g. torch's current stream, which NCCL orders against) must see the folds issued on the
     // library stream, and later library work must see these launches
     if (s != g_stream) CK(order_after(s, g_stream));
@@ -517,7 +519,7 @@ int sipp_combine_partials(const void* d_partials, int count, int nprod, uint8_t*
     if (!d_partials || !out || count < 1 || nprod < 1 || nprod > 2) return fail(SIPP_ERR_ARG, "bad argument");
     rc = scratch_reserve(1);
     if (rc) return rc;
-    cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+    cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;  // NULL = legacy default stream (see above)
     if (s != g_stream) CK(order_after(s, g_stream));
     rc = launch_reduce((const uint32_t*)d_partials, count, nprod, g_scr.out, true, s);
     if (rc) return rc;

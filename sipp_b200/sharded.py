@@ -100,12 +100,17 @@ def sharded_prove(engine, A_local: bytes, B_local: bytes, n: int, A_full: Option
     dev = engine.tensor_device()
     ctx = engine.create(A_local, B_local) if device_ptrs is None else engine.create_from_device(device_ptrs, n // world)
     tr = None
+    absorb = None
     if rank == 0:
         assert A_full is not None and B_full is not None
         tr = api.Transcript()
         import ctypes
+        import threading
         from . import _lib
-        _lib.load().sipp_transcript_append_pairs(ctypes.byref(tr._t), A_full, B_full, n)  # register A and B  :36-39
+        # register A and B (:36-39): a strictly serial 8n-permutation hash chain that needs nothing from the GPUs, so it
+        # runs on a host thread (ctypes releases the GIL) while every rank computes Z and the first Z_L, Z_R
+        absorb = threading.Thread(target=_lib.load().sipp_transcript_append_pairs, args=(ctypes.byref(tr._t), A_full, B_full, n))
+        absorb.start()
     proof: List[bytes] = []
 
     def product_round(which: int) -> Optional[List[bytes]]:
@@ -117,12 +122,15 @@ def sharded_prove(engine, A_local: bytes, B_local: bytes, n: int, A_full: Option
         return None
 
     z = product_round(0)                                                    # let Z = inner_product(A, B)   :29
-    if rank == 0:
-        proof.append(z[0]); tr.append_fq12(z[0])                            # :42-43
     cur = n
+    first = True
     while cur > 1 and cur // world >= 2:                                    # folds stay local while n >= 2G
         zs = product_round(1)                                               # Z_L, Z_R   :48-49
         xb = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if rank == 0 and first:
+            absorb.join()
+            proof.append(z[0]); tr.append_fq12(z[0])                        # :42-43
+        first = False
         if rank == 0:
             proof.append(zs[0]); tr.append_fq12(zs[0])                      # :52-53
             proof.append(zs[1]); tr.append_fq12(zs[1])                      # :54-55
@@ -134,6 +142,9 @@ def sharded_prove(engine, A_local: bytes, B_local: bytes, n: int, A_full: Option
         xs = bytes(xb.cpu().numpy().tobytes())
         ctx.fold(xs[:32], xs[32:])                                          # :60-74 on the local shard
         cur //= 2
+    if rank == 0 and first:                                                 # no local round ran (n == world)
+        absorb.join()
+        proof.append(z[0]); tr.append_fq12(z[0])
     if cur > 1:
         # every rank holds exactly one pair: collapse the tail onto rank 0
         a1, b1 = ctx.read()
