@@ -247,7 +247,8 @@ def main():
         ops, ms = ctypes.c_double(), ctypes.c_double()
         _lib.check(lib.sipp_microbench(which, 2000 if which < 3 else 400, ctypes.byref(ops), ctypes.byref(ms)))
         peaks[name] = ops.value
-    # peak of the integer-multiply pipe in 32x32 product-halves per second (an IMAD.WIDE retires two)
+    # peak of the integer-multiply pipe in 32x32 product-halves per second: a 32-bit IMAD retires one half, an
+    # IMAD.WIDE (with or without carry) retires two but issues at half the rate, so all three legs agree (18.5 T/s)
     imad_peak = max(peaks["mad_lo"], 2 * peaks["mad_wide"], peaks["mad_lo_hi_carry"])
     sat = None
     if rank == 0 and args.saturated_pairs:
@@ -281,8 +282,8 @@ def main():
     roofline = {"bound": "imad", "kernel": "k_miller (optimal-ate Miller loops + block product)", "achieved": mill_ach / 1e12,
                 "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak, "traffic": None,
                 "launches": int(st["miller_launches"]), "avg_launch_ms": st["miller_ms"] / max(1, st["miller_launches"]),
-                "peak_source": "measured in this run (sipp_microbench: max of mad.lo, 2 x mad.wide, lo/hi carry chain); "
-                               "MEASURED_PEAKS.json has no integer peak",
+                "peak_source": "measured in this run (sipp_microbench: max of IMAD, 2 x IMAD.WIDE, lo/hi carry chain, all in "
+                               "32x32 product halves/s); MEASURED_PEAKS.json has no integer peak",
                 "kernel_time_share": {"miller_ms": st["miller_ms"] / K, "reduce_final_exp_ms": st["reduce_fe_ms"] / K, "fold_ms": st["fold_ms"] / K,
                                       "other_ms": st["other_ms"] / K, "host_transcript_exposed_ms": st["transcript_ms"] / K,
                                       "step_ms": t_res / K * 1e3},

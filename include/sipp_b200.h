@@ -51,6 +51,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
 #define SIPP_OPT_PROFILE 3            /* 1 = record per-kernel CUDA-event timings (sipp_get_stats) */
 #define SIPP_OPT_PIPELINE 4           /* 1 = split Miller loop: line kernel + 6-lane cooperative accumulation and final
                                          exponentiation [default]; 0 = one Miller loop per thread (first-round baseline) */
+#define SIPP_OPT_WIDE_LINES_MAX 5     /* products of at most this many pairs (summed over the products of a launch) use the
+                                         16-lanes-per-pair line kernel (k_lines_wide, latency-bound rounds); 0 = never */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

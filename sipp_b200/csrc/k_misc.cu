@@ -80,19 +80,29 @@ __global__ void __launch_bounds__(256) k_bench_mad_lo(uint32_t* out, int iters, 
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
 }
+// 8 x 8 schoolbook column accumulation with plain (carry-less) 32x32->64 multiply-adds whose operands change every
+// round -- ptxas cannot hoist the products (an earlier version with loop-invariant operands was strength-reduced to
+// IADD3 / IADD3.X pairs and reported an "IMAD.WIDE" rate that was really the 64-bit add rate).  64 IMAD.WIDE.U32 + 16
+// ALU instructions per round; verified in SASS (tools/sass_mix.py).
 __global__ void __launch_bounds__(256) k_bench_mad_wide(uint64_t* out, int iters, uint32_t seed) {
-    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-    uint64_t r0 = a, r1 = a + 1, r2 = a + 2, r3 = a + 3, r4 = a + 4, r5 = a + 5, r6 = a + 6, r7 = a + 7;
-    for (int i = 0; i < iters; i++) {
+    uint32_t x[8], y[8];
+    uint64_t t[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-                         "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\tmad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                         : "+l"(r0), "+l"(r1), "+l"(r2), "+l"(r3), "+l"(r4), "+l"(r5), "+l"(r6), "+l"(r7)
-                         : "r"(b), "r"(a));
+    for (int i = 0; i < 8; i++) { x[i] = seed * (i + 3) + threadIdx.x; y[i] = seed * (i + 11) + blockIdx.x * 7 + threadIdx.x * 13; t[i] = i; }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) t[(i + j) & 7] += (uint64_t)x[i] * y[j];
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { x[i] ^= (uint32_t)t[i]; y[i] += (uint32_t)(t[i] >> 32); }
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= t[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 __global__ void __launch_bounds__(256) k_bench_mad_carry(uint32_t* out, int iters, uint32_t seed) {
     // the row primitive of fq_mul: 8-limb lo/hi carry chains, two independent accumulators

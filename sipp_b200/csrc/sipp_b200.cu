@@ -23,6 +23,7 @@ thread_local std::string g_err;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
 int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0, g_opt_pipeline = 1;
+int g_opt_wide_max = 16384;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
 int g_sm_count = 148;
 
 struct TimedSpan {
@@ -262,7 +263,8 @@ int ctx_products_to_device(sipp_ctx* c, int which, size_t* blocks_out, int* npro
     for (size_t c0 = 0; c0 < job.m; c0 += mc) {
         size_t cur = job.m - c0 < mc ? job.m - c0 : mc;
         Span sp(0, s);
-        int e = launch_lines(c->dA, c->dB, job, nprod, c0, cur, g_scr.lines, s);
+        const bool wide = cur * (size_t)nprod <= (size_t)g_opt_wide_max;
+        int e = wide ? launch_lines_wide(c->dA, c->dB, job, nprod, c0, cur, g_scr.lines, s) : launch_lines(c->dA, c->dB, job, nprod, c0, cur, g_scr.lines, s);
         if (e) return cuda_fail((cudaError_t)e, "k_lines");
         e = launch_accum(g_scr.lines, cur, nprod, kpg, g_scr.partials, (int)block_off, s);
         if (e) return cuda_fail((cudaError_t)e, "k_accum");
@@ -367,6 +369,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_FQ12_ORDER: g_opt_fq12_order = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_PROFILE: g_opt_profile = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_PIPELINE: g_opt_pipeline = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_WIDE_LINES_MAX: g_opt_wide_max = value < 0 ? 0 : value; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -376,6 +379,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_FQ12_ORDER: return g_opt_fq12_order;
         case SIPP_OPT_PROFILE: return g_opt_profile;
         case SIPP_OPT_PIPELINE: return g_opt_pipeline;
+        case SIPP_OPT_WIDE_LINES_MAX: return g_opt_wide_max;
         default: return -1;
     }
 }

@@ -42,9 +42,10 @@ def test_fq_and_dot(hc, oracle):
         out = _buf(len(a))
         assert hc.hc_fq_op(op, a, b, out, len(xs)) == 0
         assert out.raw == oracle.field_op(name, a, b)
-    out = _buf(32 * 20)
-    hc.hc_fq_op(4, a, None, out, 20)
-    assert out.raw == oracle.field_op("FQ_INV", a[:32 * 20])
+    out = _buf(len(a))
+    hc.hc_fq_op(4, a, None, out, len(xs))  # binary (Kaliski) inversion, all iteration counts incl. the edge values
+    assert out.raw[:32 * 20] == oracle.field_op("FQ_INV", a[:32 * 20])
+    assert out.raw == b"".join(le(pow(x, P - 2, P)) for x in xs)
     for n in (1, 2, 3, 4, 5, 6, 8, 12):
         for trial in range(6):
             big = trial == 0  # all operands p - 1: the largest lazy sum
@@ -103,3 +104,33 @@ def test_fold_split(hc, oracle):
             out = _buf(128)
             assert hc.hc_fold_split_g2(p1, p2, x, x, out) == 0
             assert out.raw == oracle.fold_g2(p1 + p2, x)
+
+
+def test_line_engine(hc, oracle):
+    """lane-parallel line programs (engine.cuh + line_programs.h, the code k_lines_wide runs): fq_lincomb4 against plain
+    integers, and the whole Miller loop through the 16-lane schedule == the oracle's pairing"""
+    rng = random.Random(9)
+    for trial in range(200):
+        if trial < 4:
+            s = [P - 1] * 4
+            c = [[2047, 0, 0, 0], [-2047, 0, 0, 0], [512, 512, 512, 511], [-512, -512, -512, -511]][trial]
+        else:
+            s = [rng.choice([0, 1, P - 1, rng.randrange(P)]) for _ in range(4)]
+            c = [rng.randrange(-511, 512) for _ in range(4)]
+        out = _buf(32)
+        hc.hc_lincomb4(b"".join(map(le, s)), (ctypes.c_int * 4)(*c), out)
+        assert int.from_bytes(out.raw, "little") == sum(x * y for x, y in zip(s, c)) % P, (s, c)
+    A, B = oracle.seeded_inputs(77, 3)
+    for i in range(3):
+        out = _buf(384)
+        assert hc.hc_pairing_wide(A[64 * i:64 * i + 64], B[128 * i:128 * i + 128], out) == 0
+        assert out.raw == oracle.pairing(A[64 * i:64 * i + 64], B[128 * i:128 * i + 128])
+
+
+def test_line_programs_generator_is_current():
+    """line_programs.h is what tools/gen_line_programs.py emits, and its self-check against the pure-Python model passes"""
+    path = os.path.join(ROOT, "sipp_b200", "csrc", "line_programs.h")
+    before = open(path).read()
+    subprocess.check_call([os.environ.get("PYTHON", "python"), os.path.join(ROOT, "tools", "gen_line_programs.py"), "--check"],
+                          stdout=subprocess.DEVNULL)
+    assert open(path).read() == before
