@@ -53,6 +53,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          exponentiation [default]; 0 = one Miller loop per thread (first-round baseline) */
 #define SIPP_OPT_WIDE_LINES_MAX 5     /* products of at most this many pairs (summed over the products of a launch) use the
                                          16-lanes-per-pair line kernel (k_lines_wide, latency-bound rounds); 0 = never */
+#define SIPP_OPT_FE_ENGINE 6          /* 1 = final exponentiation on the 32-lane Fq12 machine (k_reduce_fe_eng) [default];
+                                         0 = 6-lane cooperative version (k_reduce_fe_coop) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

@@ -23,7 +23,8 @@ thread_local std::string g_err;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
 int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0, g_opt_pipeline = 1;
-int g_opt_wide_max = 16384;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
+int g_opt_fe_engine = 1;
+int g_opt_wide_max = 8192;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
 int g_sm_count = 148;
 
 struct TimedSpan {
@@ -212,8 +213,9 @@ int launch_miller(const sipp_ctx* c, int nprod, const MillerJob& job, uint32_t* 
 
 int launch_reduce(const uint32_t* d_partials, int count, int nprod, uint32_t* d_out, bool final_exp, cudaStream_t s) {
     Span sp(1, s);
-    int e = g_opt_pipeline ? launch_reduce_fe_coop(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s)
-                           : launch_reduce_fe(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s);
+    int e = !g_opt_pipeline ? launch_reduce_fe(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s)
+            : g_opt_fe_engine ? launch_reduce_fe_eng(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s)
+                              : launch_reduce_fe_coop(d_partials, count, nprod, d_out, final_exp ? 1 : 0, g_opt_fe_norm, s);
     if (e) return cuda_fail((cudaError_t)e, "k_reduce_fe");
     g_stats.launches++;
     return SIPP_OK;
@@ -370,6 +372,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_PROFILE: g_opt_profile = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_PIPELINE: g_opt_pipeline = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_WIDE_LINES_MAX: g_opt_wide_max = value < 0 ? 0 : value; return SIPP_OK;
+        case SIPP_OPT_FE_ENGINE: g_opt_fe_engine = value ? 1 : 0; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -380,6 +383,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_PROFILE: return g_opt_profile;
         case SIPP_OPT_PIPELINE: return g_opt_pipeline;
         case SIPP_OPT_WIDE_LINES_MAX: return g_opt_wide_max;
+        case SIPP_OPT_FE_ENGINE: return g_opt_fe_engine;
         default: return -1;
     }
 }

@@ -99,17 +99,20 @@ def test_coop_fq12_ops(lib, oracle, golden):
     assert _fq12_op(lib, 29, ml) == gt                                        # cooperative final exponentiation
 
 
-@pytest.fixture(params=[(1, 16384), (1, 0), (0, 0)], ids=["split-wide-lines", "split-thread-lines", "per-thread"])
+@pytest.fixture(params=[(1, 8192, 1), (1, 0, 0), (0, 0, 0)], ids=["split-engines", "split-thread-lines-coop-fe", "per-thread"])
 def pipeline(request, sipp):
     """all Miller pipelines must be bit-exact: split = line kernel + cooperative accumulation (default) with the lines made by
-    16 lanes per pair (k_lines_wide, the latency-bound rounds) or by one thread per pair (k_lines); per-thread = one whole
-    loop per thread (first-round baseline)"""
+    16 lanes per pair (k_lines_wide, the latency-bound rounds) or by one thread per pair (k_lines), and the final
+    exponentiation on the 32-lane Fq12 machine or the 6-lane cooperative code; per-thread = one whole loop per thread
+    (first-round baseline)"""
     from sipp_b200 import _lib
     sipp.set_option(_lib.OPT_PIPELINE, request.param[0])
     sipp.set_option(_lib.OPT_WIDE_LINES_MAX, request.param[1])
+    sipp.set_option(_lib.OPT_FE_ENGINE, request.param[2])
     yield request.param
     sipp.set_option(_lib.OPT_PIPELINE, 1)
-    sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 16384)
+    sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
+    sipp.set_option(_lib.OPT_FE_ENGINE, 1)
 
 
 def test_pairing_golden_and_oracle(sipp, oracle, golden, pipeline):

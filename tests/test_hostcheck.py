@@ -47,7 +47,7 @@ def test_fq_and_dot(hc, oracle):
     assert out.raw[:32 * 20] == oracle.field_op("FQ_INV", a[:32 * 20])
     assert out.raw == b"".join(le(pow(x, P - 2, P)) for x in xs)
     for n in (1, 2, 3, 4, 5, 6, 8, 12):
-        for trial in range(6):
+        for trial in range(40):
             big = trial == 0  # all operands p - 1: the largest lazy sum
             u = [P - 1 if big else rng.randrange(P) for _ in range(n)]
             v = [P - 1 if big else rng.randrange(P) for _ in range(n)]
@@ -134,3 +134,18 @@ def test_line_programs_generator_is_current():
     subprocess.check_call([os.environ.get("PYTHON", "python"), os.path.join(ROOT, "tools", "gen_line_programs.py"), "--check"],
                           stdout=subprocess.DEVNULL)
     assert open(path).read() == before
+
+
+def test_fq12_machine_final_exp(hc, oracle):
+    """final exponentiation through the generated 32-lane programs (the code k_reduce_fe_eng runs) == the generic device
+    code == the oracle's pairing value, for both normalisations"""
+    hc.hc_final_exp.restype = ctypes.c_long
+    rng = random.Random(11)
+    for trial in range(3):
+        f = b"".join(le(rng.randrange(P)) for _ in range(12))
+        for ark in (0, 1):
+            a, b = _buf(384), _buf(384)
+            hc.hc_final_exp(0, f, a, ark)
+            levels = hc.hc_final_exp(1, f, b, ark)
+            assert a.raw == b.raw and levels > 500
+    subprocess.check_call([os.environ.get("PYTHON", "python"), os.path.join(ROOT, "tools", "gen_fq12_programs.py"), "--check"], stdout=subprocess.DEVNULL)

@@ -6,8 +6,9 @@ from sipp_b200 import _lib
 for n in (4096, 128):
     A, B = sipp_b200.seeded_inputs(2, n)
     ref = None
-    for wide in (0, 16384):
+    for wide in (0, 8192):
         sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, wide)
+        sipp_b200.set_option(_lib.OPT_FE_ENGINE, 1 if wide else 0)
         for rep in range(3):
             sipp_b200.set_option(_lib.OPT_PROFILE, 1)
             sipp_b200.stats(reset=True)
@@ -31,4 +32,4 @@ for m in (256, 1024, 2048, 4096, 8192, 16384):
             st = sipp_b200.stats(reset=True)
         print("m=%6d wide=%d  miller %.3f ms  reduce+fe %.3f ms" % (m, 1 if wide else 0, st["miller_ms"], st["reduce_fe_ms"]))
     ctx.close()
-sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, 16384)
+sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
