@@ -14,6 +14,7 @@
 #include "fqdot.cuh"
 #include "tower.cuh"
 #include "line_programs.h"
+#include "fold_plan.h"
 
 namespace sipp {
 
@@ -83,7 +84,7 @@ inline void lp_store(uint32_t* slots, int s, const Fq& v) {
 
 SIPP_HD int lp_dst(const LpIns& ins) { return (int)(ins.w0 & 255u); }
 
-// one instruction on one lane; `type` is uniform over the level (0 = MUL, 1 = LIN)
+// one instruction on one lane; `type` is uniform over the level (0 = MUL, 1 = LIN, 2 = MUL1)
 SIPP_HD Fq lp_eval(int type, const LpIns& ins, const uint32_t* slots) {
     const Fq a = lp_load(slots, (ins.w0 >> 8) & 255u), b = lp_load(slots, (ins.w0 >> 16) & 255u);
     const Fq c = lp_load(slots, ins.w0 >> 24);
@@ -96,6 +97,7 @@ SIPP_HD Fq lp_eval(int type, const LpIns& ins, const uint32_t* slots) {
         const Fq x[2] = {a, c}, y[2] = {b, d};
         return fq_dot<2>(x, y);
     }
+    if (type == 2) return fq_mul(a, b);
     return fq_lincomb4(a, b, c, d, (int)(int16_t)(ins.w2 & 0xffffu), (int)(int16_t)(ins.w2 >> 16), (int)(int16_t)(ins.w3 & 0xffffu),
                        (int)(int16_t)(ins.w3 >> 16));
 }
@@ -124,6 +126,46 @@ SIPP_HD void lp_miller(M& mach) {
     mach.emit(step++);
 }
 
+// [k]Q for the fold kernels: k given as signed binary digits (bit i of plus / minus set = digit +1 / -1), most significant
+// digit at `top` (must be +1: the caller negates Q and swaps the masks otherwise).  T starts as Q; G2 uses the line
+// programs' point arithmetic (their line outputs are simply not consumed), G1 the Fq programs.
+template <class M>
+SIPP_HD void lp_scalar_mul(M& mach, bool g2, const uint32_t* plus, const uint32_t* minus, int top) {
+    for (int i = top - 1; i >= 0; i--) {
+        const uint32_t bit = 1u << (i & 31);
+        const bool dp = (plus[i >> 5] & bit) != 0, dm = (minus[i >> 5] & bit) != 0;
+        if (g2) {
+            mach.run(SIPP_LP_DBL_FIRST, SIPP_LP_DBL_LEVELS);
+            if (dp) mach.run(SIPP_LP_ADD_P_FIRST, SIPP_LP_ADD_P_LEVELS);
+            else if (dm) mach.run(SIPP_LP_ADD_M_FIRST, SIPP_LP_ADD_M_LEVELS);
+        } else {
+            mach.run(SIPP_LP_DBL1_FIRST, SIPP_LP_DBL1_LEVELS);
+            if (dp) mach.run(SIPP_LP_ADD1_P_FIRST, SIPP_LP_ADD1_P_LEVELS);
+            else if (dm) mach.run(SIPP_LP_ADD1_M_FIRST, SIPP_LP_ADD1_M_LEVELS);
+        }
+    }
+}
+
+// digits of one fold component as lp_scalar_mul wants them
+struct FoldDigits {
+    uint32_t plus[SIPP_FOLD_MASK_WORDS], minus[SIPP_FOLD_MASK_WORDS];
+    int top;    // index of the most significant non-zero digit, -1 if the sub-scalar is zero
+    bool flip;  // that digit is -1: work with -Q and negated digits
+};
+SIPP_HD FoldDigits fold_digits(const FoldComp& c, int bits) {
+    FoldDigits d;
+    d.top = -1;
+    for (int i = bits - 1; i >= 0; i--) {
+        const uint32_t bit = 1u << (i & 31);
+        if ((c.plus[i >> 5] | c.minus[i >> 5]) & bit) { d.top = i; break; }
+    }
+    d.flip = d.top >= 0 && (c.minus[d.top >> 5] >> (d.top & 31)) & 1u;
+    for (int w = 0; w < SIPP_FOLD_MASK_WORDS; w++) {
+        d.plus[w] = d.flip ? c.minus[w] : c.plus[w];
+        d.minus[w] = d.flip ? c.plus[w] : c.minus[w];
+    }
+    return d;
+}
 // the fixed slots every group starts from (P, Q in Montgomery limbs)
 SIPP_HD void lp_fill_fixed(uint32_t* slots, const Fq& xp, const Fq& yp, const Fq2& qx, const Fq2& qy) {
     const Fq2 xi_inv = Fq2 SIPP_XI_INV_INIT;

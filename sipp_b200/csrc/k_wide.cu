@@ -78,3 +78,131 @@ int launch_lines_wide(const uint32_t* A, const uint32_t* B, const MillerJob& job
 }
 
 }  // namespace sipp
+
+// ------------------------------------------------------------------------------------------------ K4 on the line engine
+// k_fold_wide: the fixed-scalar fold of the latency-bound rounds.  As in k_fold_split the challenge is recoded on the host
+// (fold_plan.h: GLS components for G2, GLV for G1, NAF digits) and one component = one scalar multiplication; here every
+// component of every element gets a GROUP of 16 lanes that runs the generated point programs (DBL / ADD_P / ADD_M, the same
+// tables as the Miller-loop lines; DBL1 / ADD1_* over Fq for G1), so a doubling is 2 MUL levels instead of ~16 dependent Fq
+// products.  The two groups of a warp work on the SAME component of two elements: the digit schedule is warp-uniform.
+//   A_i <- A_i + x A_{i+h}       /root/reference/src/prover_native.rs:60-64
+//   B_i <- B_i + x^-1 B_{i+h}    /root/reference/src/prover_native.rs:65-69
+// The component sums, the addition of the base point (all exceptional cases: identity, doubling, inverse) and the affine
+// normalisation are the complete Jacobian formulas of curve.cuh, one thread per element.
+namespace sipp {
+
+__device__ __forceinline__ void store_words(uint32_t* dst, const Fq& v) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = v.l[i];
+}
+__device__ __forceinline__ Fq load_words(const uint32_t* src) {
+    Fq v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.l[i] = src[i];
+    return v;
+}
+
+__global__ void __launch_bounds__(SIPP_WIDE_THREADS) k_fold_wide(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, FoldPlan plan_arg, unsigned g2_blocks) {
+    __shared__ __align__(16) uint32_t smem[SIPP_WIDE_GROUPS * SIPP_LP_SLOTS * 8];
+    __shared__ FoldPlan plan;
+    __shared__ __align__(16) uint32_t xch[SIPP_WIDE_GROUPS * 48];  // one Jacobian point per group (G2: 48 words, G1: 24)
+    for (int i = threadIdx.x; i < (int)(sizeof(FoldPlan) / 4); i += blockDim.x) ((uint32_t*)&plan)[i] = ((const uint32_t*)&plan_arg)[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, group = threadIdx.x / SIPP_LP_LANES, lane = threadIdx.x % SIPP_LP_LANES, gi = group & 1;
+    uint32_t* slots = smem + group * (SIPP_LP_SLOTS * 8);
+    DevMachine mach;
+    mach.slots = slots; mach.out = nullptr; mach.lane = lane; mach.store = false; mach.ident = false;
+    if (blockIdx.x < g2_blocks) {
+        const int comp = warp;                       // 4 warps = 4 GLS components, 2 elements per block
+        size_t e = (size_t)blockIdx.x * 2 + gi;
+        const bool valid = e < h;
+        if (!valid) e = h - 1;
+        const FoldDigits d = fold_digits(plan.g2[comp], plan.g2_bits);
+        bool ident = false;
+        if (lane == 0) {
+            G2A q = load_g2(B, e + h);
+            ident = affine_is_identity(q);
+            q = endo_apply(q, comp);
+            if ((plan.g2[comp].neg != 0) != d.flip) q.y = fq2_neg(q.y);
+            lp_fill_fixed(slots, fq_zero(), fq_zero(), q.x, q.y);
+        }
+        __syncwarp();
+        if (d.top >= 0) {
+            mach.run(SIPP_LP_SETUP_FIRST, SIPP_LP_SETUP_LEVELS);
+            lp_scalar_mul(mach, true, d.plus, d.minus, d.top);
+        }
+        if (lane == 0) {
+            Jac<Fq2> r = jac_identity<Fq2>();
+            if (!ident && d.top >= 0) {
+                const Fq2 X{lp_load(slots, SIPP_LP_SLOT_X0), lp_load(slots, SIPP_LP_SLOT_X1)}, Y{lp_load(slots, SIPP_LP_SLOT_Y0), lp_load(slots, SIPP_LP_SLOT_Y1)};
+                const Fq2 Z = fq2_mul_xi(Fq2{lp_load(slots, SIPP_LP_SLOT_ZH0), lp_load(slots, SIPP_LP_SLOT_ZH1)});
+                r.x = fq2_mul(X, Z);                 // homogeneous (X : Y : Z)  ->  Jacobian (X Z, Y Z^2, Z)
+                r.y = fq2_mul(Y, fq2_sqr(Z));
+                r.z = Z;
+            }
+            uint32_t* o = xch + group * 48;
+            store_words(o, r.x.c0); store_words(o + 8, r.x.c1); store_words(o + 16, r.y.c0); store_words(o + 24, r.y.c1);
+            store_words(o + 32, r.z.c0); store_words(o + 40, r.z.c1);
+        }
+        __syncthreads();
+        if (warp == 0 && lane == 0) {
+            Jac<Fq2> acc;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t* o = xch + ((j * 2 + gi) * 48);   // group of component j, element gi
+                Jac<Fq2> t;
+                t.x = Fq2{load_words(o), load_words(o + 8)}; t.y = Fq2{load_words(o + 16), load_words(o + 24)}; t.z = Fq2{load_words(o + 32), load_words(o + 40)};
+                acc = j ? jac_add(acc, t) : t;
+            }
+            const G2A r = jac_to_affine(jac_add_affine(acc, load_g2(B, e)));
+            if (valid) store_g2(B, e, r);
+        }
+    } else {
+        const int comp = warp & 1, pair = warp >> 1;  // warps (0,1) and (2,3): the two GLV components of 2 x 2 elements
+        size_t e = (size_t)(blockIdx.x - g2_blocks) * 4 + pair * 2 + gi;
+        const bool valid = e < h;
+        if (!valid) e = h - 1;
+        const FoldDigits d = fold_digits(plan.g1[comp], plan.g1_bits);
+        bool ident = false;
+        if (lane == 0) {
+            G1A q = load_g1(A, e + h);
+            ident = affine_is_identity(q);
+            q = endo_apply(q, comp);
+            if ((plan.g1[comp].neg != 0) != d.flip) q.y = fq_neg(q.y);
+            lp_store(slots, SIPP_LP_SLOT_ZERO, fq_zero());
+            lp_store(slots, SIPP_LP_SLOT_QX0, q.x); lp_store(slots, SIPP_LP_SLOT_QY0, q.y);
+            lp_store(slots, SIPP_LP_SLOT_X1, q.x); lp_store(slots, SIPP_LP_SLOT_Y1, q.y); lp_store(slots, SIPP_LP_SLOT_Z1, fq_one());
+        }
+        __syncwarp();
+        if (d.top >= 0) lp_scalar_mul(mach, false, d.plus, d.minus, d.top);
+        if (lane == 0) {
+            Jac<Fq> r = jac_identity<Fq>();
+            if (!ident && d.top >= 0) {
+                const Fq X = lp_load(slots, SIPP_LP_SLOT_X1), Y = lp_load(slots, SIPP_LP_SLOT_Y1), Z = lp_load(slots, SIPP_LP_SLOT_Z1);
+                r.x = fq_mul(X, Z);
+                r.y = fq_mul(Y, fq_sqr(Z));
+                r.z = Z;
+            }
+            uint32_t* o = xch + group * 48;
+            store_words(o, r.x); store_words(o + 8, r.y); store_words(o + 16, r.z);
+        }
+        __syncthreads();
+        if (comp == 0 && lane == 0) {
+            Jac<Fq> acc, t;
+            const uint32_t* o0 = xch + group * 48;              // component 0 of this element
+            const uint32_t* o1 = xch + (group + 2) * 48;        // component 1: next warp, same group-in-warp
+            acc.x = load_words(o0); acc.y = load_words(o0 + 8); acc.z = load_words(o0 + 16);
+            t.x = load_words(o1); t.y = load_words(o1 + 8); t.z = load_words(o1 + 16);
+            acc = jac_add(acc, t);
+            const G1A r = jac_to_affine(jac_add_affine(acc, load_g1(A, e)));
+            if (valid) store_g1(A, e, r);
+        }
+    }
+}
+
+int launch_fold_wide(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s) {
+    const unsigned g2_blocks = (unsigned)((h + 1) / 2), g1_blocks = (unsigned)((h + 3) / 4);
+    k_fold_wide<<<g2_blocks + g1_blocks, SIPP_WIDE_THREADS, 0, s>>>(A, B, h, plan, g2_blocks);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sipp

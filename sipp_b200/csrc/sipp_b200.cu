@@ -24,6 +24,7 @@ int g_device = -1;
 cudaStream_t g_stream = nullptr;
 int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0, g_opt_pipeline = 1;
 int g_opt_fe_engine = 1;
+int g_opt_wide_fold_max = 512;
 int g_opt_wide_max = 8192;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
 int g_sm_count = 148;
 
@@ -373,6 +374,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_PIPELINE: g_opt_pipeline = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_WIDE_LINES_MAX: g_opt_wide_max = value < 0 ? 0 : value; return SIPP_OK;
         case SIPP_OPT_FE_ENGINE: g_opt_fe_engine = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_WIDE_FOLD_MAX: g_opt_wide_fold_max = value < 0 ? 0 : value; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -384,6 +386,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_PIPELINE: return g_opt_pipeline;
         case SIPP_OPT_WIDE_LINES_MAX: return g_opt_wide_max;
         case SIPP_OPT_FE_ENGINE: return g_opt_fe_engine;
+        case SIPP_OPT_WIDE_FOLD_MAX: return g_opt_wide_fold_max;
         default: return -1;
     }
 }
@@ -470,7 +473,7 @@ int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
     {
         Span sp(2, g_stream);
         // new_A = a1 + a2.mul(x)  prover_native.rs:60-64;  new_B = b1 + b2.mul(inv_x)  :65-69
-        int e = launch_fold(c->dA, c->dB, h, plan, g_stream);
+        int e = h <= (size_t)g_opt_wide_fold_max ? launch_fold_wide(c->dA, c->dB, h, plan, g_stream) : launch_fold(c->dA, c->dB, h, plan, g_stream);
         if (e) return cuda_fail((cudaError_t)e, "k_fold");
     }
     g_stats.launches += 1;

@@ -109,10 +109,12 @@ def pipeline(request, sipp):
     sipp.set_option(_lib.OPT_PIPELINE, request.param[0])
     sipp.set_option(_lib.OPT_WIDE_LINES_MAX, request.param[1])
     sipp.set_option(_lib.OPT_FE_ENGINE, request.param[2])
+    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 1 << 20 if request.param[2] else 0)  # every fold on the engine / none
     yield request.param
     sipp.set_option(_lib.OPT_PIPELINE, 1)
     sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
     sipp.set_option(_lib.OPT_FE_ENGINE, 1)
+    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
 
 
 def test_pairing_golden_and_oracle(sipp, oracle, golden, pipeline):
@@ -164,8 +166,11 @@ def test_inner_product_with_identities(sipp, oracle, pipeline):
     assert sipp.inner_product(bytes(A), bytes(B)) == oracle.inner_product(bytes(A), bytes(B))
 
 
-def test_fold_round(sipp, oracle):
-    """prover_native.rs:60-74 via the round-granular context API, incl. exceptional points"""
+@pytest.mark.parametrize("wide_fold", [1 << 20, 0], ids=["lane-engine", "per-thread-components"])
+def test_fold_round(sipp, oracle, wide_fold):
+    """prover_native.rs:60-74 via the round-granular context API, incl. exceptional points; both fold kernels"""
+    from sipp_b200 import _lib
+    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, wide_fold)
     rng = random.Random(3)
     A, B = oracle.seeded_inputs(31, 16, threads=4)
     A = bytearray(A); B = bytearray(B)
@@ -189,6 +194,15 @@ def test_fold_round(sipp, oracle):
     assert a2 == wa and b2 == wb
     assert wa[64 * 3:64 * 4] == bytes(64) and wb[128 * 3:128 * 4] == bytes(128)
     ctx.close()
+    # ragged sizes (partial blocks of the 2- and 4-element layouts) and edge scalars
+    A, B = oracle.seeded_inputs(32, 14, threads=4)
+    for k in (1, 2, R - 1, rng.randrange(1, R)):
+        x = le(k); xinv = oracle.fr_inverse(x)
+        ctx = sipp.ProverContext(A, B)
+        ctx.fold(x, xinv)
+        assert ctx.read() == (oracle.fold_g1(A, x), oracle.fold_g2(B, xinv))
+        ctx.close()
+    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
 
 
 def test_prove_golden(sipp, golden, pipeline):

@@ -59,6 +59,11 @@ class Program:
         assert len(ops) <= LANES, (self.name, len(ops))
         self.levels.append(("MUL", ops))
 
+    def mul1(self, ops):
+        """ops: (dst, s0, s1): dst = s0 * s1 (plain Fq product; the G1 programs)"""
+        assert len(ops) <= LANES, (self.name, len(ops))
+        self.levels.append(("MUL1", ops))
+
     def lin(self, ops):
         """ops: (dst, [(coef, src), ...]) with at most 4 terms"""
         assert len(ops) <= LANES, (self.name, len(ops))
@@ -152,6 +157,30 @@ def build_add(name, q, sign):
     return p
 
 
+def build_dbl1():
+    """G1 (y^2 = x^3 + 3 over Fq), T <- 2T (x4) in homogeneous projective coordinates (X1, Y1, Z1):
+         b = Y^2, c = Z^2, e = 3 b Z^2 = 9c, f = 3e ; X' = 2 XY (b - f), Y' = (b + f)^2 - 12 e^2, Z' = 8 b (YZ)"""
+    p = Program("DBL1")
+    p.mul1([("XY1", "X1", "Y1"), ("B1", "Y1", "Y1"), ("C1", "Z1", "Z1"), ("YZ1", "Y1", "Z1")])
+    p.lin([("E1", [(9, "C1")]), ("BMF1", [(1, "B1"), (-27, "C1")]), ("BPF1", [(1, "B1"), (27, "C1")])])
+    p.mul1([("E21", "E1", "E1"), ("G21", "BPF1", "BPF1"), ("XN1", "XY1", "BMF1"), ("ZN1", "B1", "YZ1")])
+    p.lin([("X1", [(2, "XN1")]), ("Y1", [(1, "G21"), (-12, "E21")]), ("Z1", [(8, "ZN1")])])
+    return p
+
+
+def build_add1(name, sign):
+    """G1, T <- T + sign * Q with Q = (QX0, QY0) affine (same formulas as build_add, over Fq)"""
+    p = Program(name)
+    p.mul1([("A1", "QY0", "Z1"), ("BQ1", "QX0", "Z1")])
+    p.lin([("TH1", [(1, "Y1"), (-sign, "A1")]), ("LA1", [(1, "X1"), (-1, "BQ1")])])
+    p.mul1([("CC1", "TH1", "TH1"), ("DD1", "LA1", "LA1")])
+    p.mul1([("EV1", "LA1", "DD1"), ("FH1", "Z1", "CC1"), ("GV1", "X1", "DD1")])
+    p.lin([("H1", [(1, "EV1"), (1, "FH1"), (-2, "GV1")]), ("GMH1", [(3, "GV1"), (-1, "EV1"), (-1, "FH1")])])
+    p.mul1([("X1", "LA1", "H1"), ("YA1", "TH1", "GMH1"), ("YB1", "EV1", "Y1"), ("Z1", "Z1", "EV1")])
+    p.lin([("Y1", [(1, "YA1"), (-1, "YB1")])])
+    return p
+
+
 def build_setup():
     """Q1 = pi(Q), Q2 = pi(Q1) (used negated), hats, and T = Q (Z = 1  =>  Zh = xi^-1)"""
     p = Program("SETUP")
@@ -173,6 +202,9 @@ def run(prog, slots):
             if kind == "MUL":
                 dst, s0, s1, s2, s3, neg = op
                 v = slots[s0] * slots[s1] + (-1 if neg else 1) * slots[s2] * slots[s3]
+            elif kind == "MUL1":
+                dst, s0, s1 = op
+                v = slots[s0] * slots[s1]
             else:
                 dst, terms = op
                 v = sum(c * slots[s] for c, s in terms)
@@ -210,20 +242,66 @@ def model_lines_check(programs, seed=5, pairs=2):
     return True
 
 
+def model_scalar_mul_check(programs, seed=9):
+    """the fold kernels' use of the programs: [k]Q by signed digits through DBL / ADD_P / ADD_M (G2) and DBL1 / ADD1_* (G1)"""
+    import random
+    rng = random.Random(seed)
+    A, B = m.seeded_inputs(seed, 1)
+    for trial in range(4):
+        k = rng.randrange(2, 1 << 66)
+        digits = []  # NAF, little endian
+        kk = k
+        while kk:
+            d = 0
+            if kk & 1:
+                d = 2 - (kk & 3)
+                kk -= d
+            digits.append(d)
+            kk >>= 1
+        assert digits[-1] == 1
+        # G2
+        q = B[0]
+        xiinv = m.f2_inv(m.XI)
+        slots = {"ZERO": 0, "XP": 0, "YP": 0, "QX0": q[0][0], "QX1": q[0][1], "QY0": q[1][0], "QY1": q[1][1], "XIINV0": xiinv[0], "XIINV1": xiinv[1],
+                 "G12_0": m.GAMMA[1][2][0], "G12_1": m.GAMMA[1][2][1], "G13_0": m.GAMMA[1][3][0], "G13_1": m.GAMMA[1][3][1]}
+        run(programs["SETUP"], slots)
+        for d in reversed(digits[:-1]):
+            run(programs["DBL"], slots)
+            if d:
+                run(programs["ADD_P" if d == 1 else "ADD_M"], slots)
+        z = m.f2_mul(m.XI, (slots["ZH0"], slots["ZH1"]))
+        zi = m.f2_inv(z)
+        got = (m.f2_mul((slots["X0"], slots["X1"]), zi), m.f2_mul((slots["Y0"], slots["Y1"]), zi))
+        assert got == m.g2_mul(q, k), "G2 scalar multiplication through the programs"
+        # G1
+        p1 = A[0]
+        slots = {"ZERO": 0, "QX0": p1[0], "QY0": p1[1], "X1": p1[0], "Y1": p1[1], "Z1": 1}
+        for d in reversed(digits[:-1]):
+            run(programs["DBL1"], slots)
+            if d:
+                run(programs["ADD1_P" if d == 1 else "ADD1_M"], slots)
+        zi = pow(slots["Z1"], P - 2, P)
+        assert (slots["X1"] * zi % P, slots["Y1"] * zi % P) == m.g1_mul(p1, k), "G1 scalar multiplication through the programs"
+    return True
+
+
 def emit(programs, path):
-    order = ["SETUP", "DBL", "ADD_P", "ADD_M", "ADD_Q1", "ADD_Q2"]
+    order = ["SETUP", "DBL", "ADD_P", "ADD_M", "ADD_Q1", "ADD_Q2", "DBL1", "ADD1_P", "ADD1_M"]
     code, types, index = [], [], {}
     for name in order:
         prog = programs[name]
         index[name] = (len(types), len(prog.levels))
         for kind, ops in prog.levels:
-            types.append(0 if kind == "MUL" else 1)
+            types.append({"MUL": 0, "LIN": 1, "MUL1": 2}[kind])
             for lane in range(LANES):
                 if lane < len(ops):
                     if kind == "MUL":
                         dst, s0, s1, s2, s3, neg = ops[lane]
                         srcs, coefs, flags = [S[s0], S[s1], S[s2], S[s3]], [0, 0, 0, 0], (1 if neg else 0)
                         dsti = S[dst]
+                    elif kind == "MUL1":
+                        dst, s0, s1 = ops[lane]
+                        srcs, coefs, flags, dsti = [S[s0], S[s1], S["ZERO"], S["ZERO"]], [0, 0, 0, 0], 0, S[dst]
                     else:
                         dst, terms = ops[lane]
                         terms = terms + [(0, "ZERO")] * (4 - len(terms))
@@ -241,12 +319,12 @@ def emit(programs, path):
            "#define SIPP_LP_LANES %d" % LANES,
            "#define SIPP_LP_SLOTS %d" % len(S.idx),
            "#define SIPP_LP_LEVELS %d" % len(types)]
-    for name in FIXED + OUT[:1] + ["X0", "Y0", "ZH0"]:
+    for name in FIXED + OUT[:1] + ["X0", "X1", "Y0", "Y1", "ZH0", "ZH1", "Z1"]:
         out.append("#define SIPP_LP_SLOT_%s %d" % (name, S[name]))
     for name in order:
         out.append("#define SIPP_LP_%s_FIRST %d" % (name, index[name][0]))
         out.append("#define SIPP_LP_%s_LEVELS %d" % (name, index[name][1]))
-    out.append("// level type: 0 = MUL (dst = s0 s1 +- s2 s3), 1 = LIN (dst = sum c_k s_k)")
+    out.append("// level type: 0 = MUL (dst = s0 s1 +- s2 s3), 1 = LIN (dst = sum c_k s_k), 2 = MUL1 (dst = s0 s1)")
     out.append("#define SIPP_LP_TYPES_INIT { " + ", ".join(str(t) for t in types) + " }")
     out.append("// one 128-bit instruction per (level, lane): w0 = dst | s0<<8 | s1<<16 | s2<<24, w1 = s3 | flags<<8, w2 = c0 | c1<<16, w3 = c2 | c3<<16")
     out.append("#define SIPP_LP_CODE_INIT { \\")
@@ -260,9 +338,11 @@ def emit(programs, path):
 
 def main():
     programs = {"SETUP": build_setup(), "DBL": build_dbl(), "ADD_P": build_add("ADD_P", "Q", 1), "ADD_M": build_add("ADD_M", "Q", -1),
-                "ADD_Q1": build_add("ADD_Q1", "Q1", 1), "ADD_Q2": build_add("ADD_Q2", "Q2", -1)}
+                "ADD_Q1": build_add("ADD_Q1", "Q1", 1), "ADD_Q2": build_add("ADD_Q2", "Q2", -1),
+                "DBL1": build_dbl1(), "ADD1_P": build_add1("ADD1_P", 1), "ADD1_M": build_add1("ADD1_M", -1)}
     if "--check" in sys.argv:
         model_lines_check(programs)
+        model_scalar_mul_check(programs)
         print("self-check against the affine model: ok")
     path = os.path.join(ROOT, "sipp_b200", "csrc", "line_programs.h")
     nlev, nslots = emit(programs, path)

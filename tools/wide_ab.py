@@ -9,6 +9,7 @@ for n in (4096, 128):
     for wide in (0, 8192):
         sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, wide)
         sipp_b200.set_option(_lib.OPT_FE_ENGINE, 1 if wide else 0)
+        sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 512 if wide else 0)
         for rep in range(3):
             sipp_b200.set_option(_lib.OPT_PROFILE, 1)
             sipp_b200.stats(reset=True)
@@ -33,3 +34,23 @@ for m in (256, 1024, 2048, 4096, 8192, 16384):
         print("m=%6d wide=%d  miller %.3f ms  reduce+fe %.3f ms" % (m, 1 if wide else 0, st["miller_ms"], st["reduce_fe_ms"]))
     ctx.close()
 sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
+
+# fold alone: time per fold of h elements for both kernels
+import random
+rng = random.Random(1)
+for h in (64, 256, 512, 1024, 2048):
+    A, B = sipp_b200.seeded_inputs(5, 2 * h)
+    for wide in (0, 1 << 20):
+        sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, wide)
+        outs = []
+        for rep in range(2):
+            ctx = sipp_b200.ProverContext(A, B)
+            x = rng.randrange(1, 1 << 250).to_bytes(32, "little") if rep == 0 else x
+            sipp_b200.set_option(_lib.OPT_PROFILE, 1)
+            sipp_b200.stats(reset=True)
+            ctx.fold(x, sipp_b200.fr_inverse(x))
+            outs.append(ctx.read())
+            st = sipp_b200.stats(reset=True)
+            ctx.close()
+        print("fold h=%5d wide=%d  %.3f ms" % (h, 1 if wide else 0, st["fold_ms"]))
+sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
