@@ -37,6 +37,53 @@ class SIPPStatement:
     final_B: bytes
     final_Z: bytes
 
+    def to_vec(self) -> List[int]:
+        """the u32 public-input vector `SIPPStatement::from_vec` parses (statements.rs:133-170)"""
+        import struct
+        raw = b"".join(self.A) + b"".join(self.B) + fq12_to_myfq12_bytes(self.Z) + self.final_A + self.final_B + fq12_to_myfq12_bytes(self.final_Z)
+        return list(struct.unpack("<%dI" % (len(raw) // 4), raw))
+
+    @staticmethod
+    def from_vec(n: int, vec: Sequence[int]) -> "SIPPStatement":
+        """statements.rs:133-170, same length assertion"""
+        import struct
+        total = 16 * n + 32 * n + 96 + 16 + 32 + 96
+        assert len(vec) == total, "assert!(input.len() == total_len)"
+        raw = struct.pack("<%dI" % total, *vec)
+        o = 0
+        A = [raw[o + G1_BYTES * i:o + G1_BYTES * (i + 1)] for i in range(n)]; o += G1_BYTES * n
+        B = [raw[o + G2_BYTES * i:o + G2_BYTES * (i + 1)] for i in range(n)]; o += G2_BYTES * n
+        Z = myfq12_bytes_to_fq12(raw[o:o + FQ12_BYTES]); o += FQ12_BYTES
+        fa = raw[o:o + G1_BYTES]; o += G1_BYTES
+        fb = raw[o:o + G2_BYTES]; o += G2_BYTES
+        fz = myfq12_bytes_to_fq12(raw[o:o + FQ12_BYTES])
+        return SIPPStatement(A=A, B=B, Z=Z, final_A=fa, final_B=fb, final_Z=fz)
+
+
+# ---- hand-off to the circuit side: statements.rs:90-170 (`SIPPStatement::from_vec`) ---------------------------------------
+# The plonky2 verifier circuit takes the statement as one vector of 32-bit limbs (8 little-endian limbs per Fq):
+#   A (n x 16) | B (n x 32) | Z (96) | final_A (16) | final_B (32) | final_Z (96)
+# G1 / G2 limbs are x | y resp. x.c0 | x.c1 | y.c0 | y.c1 -- byte-identical to the canonical little-endian boundary format.
+# An Fq12 is `MyFq12.coeffs` (SURVEY A.2, hypothesis H2 = w-power basis): coeffs[i] = g_i.c0, coeffs[i + 6] = g_i.c1 with
+# g_0..g_5 = c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2 of the arkworks nested form.
+_W_TO_ARK_SLOT = (0, 3, 1, 4, 2, 5)
+
+
+def fq12_to_myfq12_bytes(f: bytes) -> bytes:
+    """ark-serialized Fq12 (384 B) -> the 12 MyFq12 coefficients, 32 little-endian bytes each"""
+    assert len(f) == FQ12_BYTES
+    fq = [f[32 * i:32 * i + 32] for i in range(12)]
+    return b"".join(fq[2 * _W_TO_ARK_SLOT[i]] for i in range(6)) + b"".join(fq[2 * _W_TO_ARK_SLOT[i] + 1] for i in range(6))
+
+
+def myfq12_bytes_to_fq12(c: bytes) -> bytes:
+    assert len(c) == FQ12_BYTES
+    co = [c[32 * i:32 * i + 32] for i in range(12)]
+    out = [b""] * 12
+    for i in range(6):
+        out[2 * _W_TO_ARK_SLOT[i]], out[2 * _W_TO_ARK_SLOT[i] + 1] = co[i], co[i + 6]
+    return b"".join(out)
+
 
 def _flat(points: Points, size: int) -> bytes:
     if isinstance(points, (bytes, bytearray, memoryview)):

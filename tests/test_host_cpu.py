@@ -170,3 +170,30 @@ def test_poseidon_avx512_matches_portable():
         lib.sipp_poseidon_permute_portable(b)
         assert list(a) == list(b), it
         st = list(a)
+
+
+def test_statement_public_input_vector(golden):
+    """SIPPStatement <-> the u32 vector of statements.rs:133-170 (what the untouched plonky2 circuit consumes): layout, the
+    MyFq12 coefficient order (against the independent pure-Python model) and the round trip"""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import sipp_model as m
+    from sipp_b200 import api
+    rng = random.Random(4)
+    f = [(rng.randrange(m.P), rng.randrange(m.P)) for _ in range(6)]          # w-basis coefficients g_0..g_5
+    ark = m.f12_bytes(f)
+    my = api.fq12_to_myfq12_bytes(ark)
+    assert [int.from_bytes(my[32 * i:32 * i + 32], "little") for i in range(12)] == m.f12_myfq12_coeffs(f)
+    assert api.myfq12_bytes_to_fq12(my) == ark
+    n = 4
+    A = [bytes(rng.randrange(256) for _ in range(64)) for _ in range(n)]
+    B = [bytes(rng.randrange(256) for _ in range(128)) for _ in range(n)]
+    st = api.SIPPStatement(A=A, B=B, Z=ark, final_A=A[1], final_B=B[2], final_Z=m.f12_bytes(list(reversed(f))))
+    vec = st.to_vec()
+    assert len(vec) == 16 * n + 32 * n + 96 + 16 + 32 + 96 and all(0 <= v < 2**32 for v in vec)
+    assert vec[:8] == [int.from_bytes(A[0][4 * i:4 * i + 4], "little") for i in range(8)]            # x of A_0, 8 LE limbs
+    assert vec[48 * n:48 * n + 8] == [(m.f12_myfq12_coeffs(f)[0] >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    assert api.SIPPStatement.from_vec(n, vec) == st
+    with pytest.raises(AssertionError):
+        api.SIPPStatement.from_vec(n, vec[:-1])
