@@ -57,6 +57,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          0 = 6-lane cooperative version (k_reduce_fe_coop) */
 #define SIPP_OPT_WIDE_FOLD_MAX 7      /* folds of at most this many elements per group use the point programs on the lane
                                          engine (k_fold_wide, latency-bound rounds); 0 = never */
+#define SIPP_OPT_WIDE_ACCUM_MAX 8     /* launches of at most this many pairs accumulate the lines on the 32-lane Fq12 machine
+                                         (k_accum_eng) instead of the 6-lane groups of k_accum; 0 = never */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

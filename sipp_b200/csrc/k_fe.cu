@@ -87,6 +87,96 @@ __global__ void __launch_bounds__(SIPP_RFE_THREADS) k_reduce_fe_eng(const uint32
     }
 }
 
+// ------------------------------------------------------------------------------------------------ accumulation on the machine
+// k_accum_eng: the Fq12 side of the Miller loop for the latency-bound rounds.  One warp = one machine holds the
+// accumulator f of a group of `kpg` pairs (register 0) and folds their lines into it: per tangent step ONE shared
+// squaring (MUL12: a DOT6 level on 24 lanes), then per pair one sparse product (SPARSE: a DOT6 level on 12 lanes).
+// Lines are staged global -> shared with cp.async one line ahead into two line registers.  4 machines per block, tree
+// product through shared memory -> one 384-byte partial per block, same layout as k_accum's.
+// grid = (blocks, nprod); group g of product `prod` folds pairs [g kpg, (g + 1) kpg).
+#define SIPP_ACC_MACHINES 4
+#define SIPP_ACC_REGS 4  // 0 accumulator, 1 / 2 line buffers, 3 exchange
+#define SIPP_ACC_SLOTS (SIPP_F12_GLOBAL_SLOTS + SIPP_F12_REG_SLOTS * SIPP_ACC_REGS)
+__device__ __forceinline__ void acc_cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__global__ void __launch_bounds__(SIPP_ACC_MACHINES * 32) k_accum_eng(const uint32_t* __restrict__ lines, size_t m_chunk, int kpg, uint32_t* __restrict__ partials,
+                                                                     int partial_stride_prod, int block_offset) {
+    __shared__ __align__(16) uint32_t smem[SIPP_ACC_MACHINES * SIPP_ACC_SLOTS * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int prod = blockIdx.y;
+    uint32_t* slots = smem + warp * (SIPP_ACC_SLOTS * 8);
+    const size_t gid = (size_t)blockIdx.x * SIPP_ACC_MACHINES + warp;
+    const size_t j0 = gid * (size_t)kpg;
+    size_t j1 = j0 + (size_t)kpg;
+    if (j1 > m_chunk) j1 = m_chunk;
+    const int npairs = j0 < m_chunk ? (int)(j1 - j0) : 0;
+    const uint32_t* base = lines + ((size_t)prod * m_chunk + j0) * (size_t)(SIPP_LINES_PER_PAIR * 80);
+    DevMachine12 mc;
+    mc.slots = slots;
+    mc.lane = lane;
+    // f = 1, slot 0 of the globals = 0
+    if (lane < 12) lp_store(slots, f12_reg_base(0) + lane, lane == 0 ? fq_one() : fq_zero());
+    if (lane == 12) lp_store(slots, 0, fq_zero());
+    const int total = SIPP_LINES_PER_PAIR * npairs;  // fetch order: step-major (step s, pair q)
+    auto prefetch = [&](int idx, int buf) {
+        if (idx < total && lane < 20) {
+            const int s = idx / npairs, q = idx - s * npairs;
+            const uint32_t* src = base + (size_t)q * (SIPP_LINES_PER_PAIR * 80) + s * 80;
+            acc_cp_async16(slots + (size_t)f12_reg_base(1 + buf) * 8 + lane * 4, src + lane * 4);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    int fetch = 0;
+    prefetch(0, 0);
+    auto fold_lines = [&]() {
+        for (int q = 0; q < npairs; q++) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int buf = fetch & 1;
+            prefetch(fetch + 1, buf ^ 1);
+            F12_OP3(mc, SPARSE, 0, 0, 1 + buf);
+            fetch++;
+        }
+    };
+    const unsigned long long plus = SIPP_ATE_PLUS_MASK, minus = SIPP_ATE_MINUS_MASK;
+    if (npairs > 0) {
+        for (int i = 63; i >= 0; i--) {
+            if (i != 63) F12_OP3(mc, MUL12, 0, 0, 0);
+            fold_lines();
+            if (((plus | minus) >> i) & 1ull) fold_lines();
+        }
+        fold_lines();
+        fold_lines();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // tree product over the machines of the block: 2 <- 3 and 0 <- 1 are independent, then 0 <- 2
+#pragma unroll 1
+    for (int half = SIPP_ACC_MACHINES / 2; half >= 1; half >>= 1) {
+        __syncthreads();
+        if (warp < half) {
+            const uint32_t* other = smem + (warp + half) * (SIPP_ACC_SLOTS * 8) + f12_reg_base(0) * 8;
+            for (int w = lane; w < 96; w += 32) slots[f12_reg_base(3) * 8 + w] = other[w];
+            __syncwarp();
+            F12_OP3(mc, MUL12, 0, 0, 3);
+        }
+    }
+    if (warp == 0) {
+        uint32_t* o = partials + ((size_t)(blockIdx.x + block_offset) * partial_stride_prod + prod) * 96;
+        for (int w = lane; w < 96; w += 32) o[w] = slots[f12_reg_base(0) * 8 + w];
+    }
+}
+int accum_eng_blocks(size_t m_chunk, int kpg) {
+    const size_t groups = (m_chunk + (size_t)kpg - 1) / (size_t)kpg;
+    return (int)((groups + SIPP_ACC_MACHINES - 1) / SIPP_ACC_MACHINES);
+}
+int launch_accum_eng(const uint32_t* lines, size_t m_chunk, int nprod, int kpg, uint32_t* partials, int block_offset, cudaStream_t s) {
+    dim3 grid((unsigned)accum_eng_blocks(m_chunk, kpg), (unsigned)nprod);
+    k_accum_eng<<<grid, SIPP_ACC_MACHINES * 32, 0, s>>>(lines, m_chunk, kpg, partials, nprod, block_offset);
+    return (int)cudaGetLastError();
+}
+
 int launch_reduce_fe_eng(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s) {
     k_reduce_fe_eng<<<nprod, SIPP_RFE_THREADS, 0, s>>>(partials, count, nprod, out, final_exp, ark_norm);
     return (int)cudaGetLastError();

@@ -25,6 +25,7 @@ cudaStream_t g_stream = nullptr;
 int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0, g_opt_pipeline = 1;
 int g_opt_fe_engine = 1;
 int g_opt_wide_fold_max = 512;
+int g_opt_wide_accum_max = 1536;
 int g_opt_wide_max = 8192;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
 int g_sm_count = 148;
 
@@ -250,13 +251,17 @@ int ctx_products_to_device(sipp_ctx* c, int which, size_t* blocks_out, int* npro
     const size_t cap_bytes = (size_t)6 << 30;
     size_t mc = job.m;
     if (mc * (size_t)nprod * per_pair > cap_bytes) mc = cap_bytes / ((size_t)nprod * per_pair);
-    const size_t groups_target = (size_t)g_sm_count * 2 * 20;
-    int kpg = (int)((mc + groups_target - 1) / groups_target);
+    // accumulation: 6-lane groups (k_accum, 20 per block) or, for the small launches of the latency-bound rounds, one
+    // 32-lane machine per group (k_accum_eng, 4 per block); kpg pairs share one accumulator (and its squarings)
+    const bool eng = mc * (size_t)nprod <= (size_t)g_opt_wide_accum_max;
+    const size_t groups_target = eng ? (size_t)g_sm_count * 8 : (size_t)g_sm_count * 2 * 20;
+    int kpg = (int)(((eng ? mc * (size_t)nprod : mc) + groups_target - 1) / groups_target);
     if (kpg < 1) kpg = 1;
+    auto blocks_of = [&](size_t cur) { return (size_t)(eng ? accum_eng_blocks(cur, kpg) : accum_blocks(cur, kpg)); };
     size_t total_blocks = 0;
     for (size_t c0 = 0; c0 < job.m; c0 += mc) {
         size_t cur = job.m - c0 < mc ? job.m - c0 : mc;
-        total_blocks += (size_t)accum_blocks(cur, kpg);
+        total_blocks += blocks_of(cur);
     }
     int rc = scratch_reserve(total_blocks);
     if (rc) return rc;
@@ -269,9 +274,10 @@ int ctx_products_to_device(sipp_ctx* c, int which, size_t* blocks_out, int* npro
         const bool wide = cur * (size_t)nprod <= (size_t)g_opt_wide_max;
         int e = wide ? launch_lines_wide(c->dA, c->dB, job, nprod, c0, cur, g_scr.lines, s) : launch_lines(c->dA, c->dB, job, nprod, c0, cur, g_scr.lines, s);
         if (e) return cuda_fail((cudaError_t)e, "k_lines");
-        e = launch_accum(g_scr.lines, cur, nprod, kpg, g_scr.partials, (int)block_off, s);
+        e = eng ? launch_accum_eng(g_scr.lines, cur, nprod, kpg, g_scr.partials, (int)block_off, s)
+                : launch_accum(g_scr.lines, cur, nprod, kpg, g_scr.partials, (int)block_off, s);
         if (e) return cuda_fail((cudaError_t)e, "k_accum");
-        block_off += (size_t)accum_blocks(cur, kpg);
+        block_off += blocks_of(cur);
         g_stats.launches += 2;
         g_stats.miller_launches++;
     }
@@ -375,6 +381,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_WIDE_LINES_MAX: g_opt_wide_max = value < 0 ? 0 : value; return SIPP_OK;
         case SIPP_OPT_FE_ENGINE: g_opt_fe_engine = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_WIDE_FOLD_MAX: g_opt_wide_fold_max = value < 0 ? 0 : value; return SIPP_OK;
+        case SIPP_OPT_WIDE_ACCUM_MAX: g_opt_wide_accum_max = value < 0 ? 0 : value; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -387,6 +394,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_WIDE_LINES_MAX: return g_opt_wide_max;
         case SIPP_OPT_FE_ENGINE: return g_opt_fe_engine;
         case SIPP_OPT_WIDE_FOLD_MAX: return g_opt_wide_fold_max;
+        case SIPP_OPT_WIDE_ACCUM_MAX: return g_opt_wide_accum_max;
         default: return -1;
     }
 }

@@ -3,6 +3,7 @@
 // checked against the oracle on a machine without a GPU.  The PTX carry chains are replaced by the plain-C++
 // emulation in fq.cuh; everything above them is the exact code the GPU runs.  Never linked into the product.
 #include <cstring>
+#include <vector>
 
 #include "../../sipp_b200/csrc/codec.cuh"
 #include "../../sipp_b200/csrc/pairing.cuh"

@@ -110,11 +110,13 @@ def pipeline(request, sipp):
     sipp.set_option(_lib.OPT_WIDE_LINES_MAX, request.param[1])
     sipp.set_option(_lib.OPT_FE_ENGINE, request.param[2])
     sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 1 << 20 if request.param[2] else 0)  # every fold on the engine / none
+    sipp.set_option(_lib.OPT_WIDE_ACCUM_MAX, 8192 if request.param[2] else 0)
     yield request.param
     sipp.set_option(_lib.OPT_PIPELINE, 1)
     sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
     sipp.set_option(_lib.OPT_FE_ENGINE, 1)
     sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
+    sipp.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1536)
 
 
 def test_pairing_golden_and_oracle(sipp, oracle, golden, pipeline):

@@ -84,6 +84,9 @@ def test_pairing_and_inner_product(hc, oracle):
     assert out.raw == oracle.pairing(A[:64], B[:128])
     hc.hc_inner_product(A, B, 3, out)
     assert out.raw == oracle.inner_product(A, B)
+    out2 = _buf(384)
+    assert hc.hc_inner_product_machine(A, B, 3, out2) == 0  # lines -> 32-lane accumulate (shared squarings) -> machine FE
+    assert out2.raw == out.raw
 
 
 def test_fold_split(hc, oracle):

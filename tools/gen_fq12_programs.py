@@ -137,6 +137,22 @@ def build_csqr():
     return p
 
 
+def build_sparse():
+    """D = A * (l0 + l1 w + l3 w^3) with the line in register B as the line kernels store it (10 slots):
+       l0 | l1 | xi l1 | l3 | xi l3.   c_k = g_k l0 + g_{k-1} l1 [xi l1 if k < 1] + g_{k-3} l3 [xi l3 if k < 3]"""
+    p = Program("SPARSE")
+    line = lambda j: (("B", 2 * j), ("B", 2 * j + 1))
+    ops = []
+    for k in range(6):
+        for c in range(2):
+            terms = fq2_mul_terms(reg2("A", k), line(0), c)
+            terms += fq2_mul_terms(reg2("A", (k + 5) % 6), line(2 if k < 1 else 1), c)
+            terms += fq2_mul_terms(reg2("A", (k + 3) % 6), line(4 if k < 3 else 3), c)
+            ops.append((val("D", k, c), terms))
+    p.dot(6, ops)
+    return p
+
+
 def build_frob(kf):
     p = Program("FROB%d" % kf)
     ops = []
@@ -261,6 +277,13 @@ def self_check(progs):
     mc.run(progs["COPY"], "R3", "R1"); assert mc.get12("R3") == a
     mc.run(progs["INV12"], "R0", "R1", "R4"); assert mc.get12("R0") == m.f12_inv(a)
     mc.set12("R5", a); mc.run(progs["INV12"], "R5", "R5", "R4"); assert mc.get12("R5") == m.f12_inv(a)   # in place
+    l0, l1, l3 = (rng.randrange(P), rng.randrange(P)), (rng.randrange(P), rng.randrange(P)), (rng.randrange(P), rng.randrange(P))
+    line = mc.reg("R6")
+    for j, v in enumerate((l0, l1, m.f2_mul(m.XI, l1), l3, m.f2_mul(m.XI, l3))):
+        line[2 * j], line[2 * j + 1] = v
+    mc.set12("R1", a)
+    mc.run(progs["SPARSE"], "R1", "R1", "R6")                      # in place
+    assert mc.get12("R1") == m.f12_mul(a, [l0, l1, m.F2_ZERO, l3, m.F2_ZERO, m.F2_ZERO])
     # cyclotomic element: easy part of the final exponentiation of a random element
     t = m.f12_mul(m.f12_conj(a), m.f12_inv(a))
     cyc = m.f12_mul(m.f12_frob(t, 2), t)
@@ -280,7 +303,7 @@ def enc_slot(s):
 
 
 def emit(progs, path):
-    order = ["MUL12", "CSQR", "FROB1", "FROB2", "FROB3", "CONJ", "COPY", "INV12"]
+    order = ["MUL12", "CSQR", "FROB1", "FROB2", "FROB3", "CONJ", "COPY", "INV12", "SPARSE"]
     code, types, index = [], [], {}
     dump = ("G", 63)  # idle lanes write X(2), which no program reads
     for name in order:
@@ -339,7 +362,7 @@ def emit(progs, path):
 
 def main():
     progs = {"MUL12": build_mul12(), "CSQR": build_csqr(), "FROB1": build_frob(1), "FROB2": build_frob(2), "FROB3": build_frob(3),
-             "CONJ": build_conj(), "COPY": build_copy(), "INV12": build_inv12()}
+             "CONJ": build_conj(), "COPY": build_copy(), "INV12": build_inv12(), "SPARSE": build_sparse()}
     if "--check" in sys.argv:
         self_check(progs)
         print("self-check against the model: ok")

@@ -10,6 +10,7 @@ for n in (4096, 128):
         sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, wide)
         sipp_b200.set_option(_lib.OPT_FE_ENGINE, 1 if wide else 0)
         sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 512 if wide else 0)
+        sipp_b200.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1536 if wide else 0)
         for rep in range(3):
             sipp_b200.set_option(_lib.OPT_PROFILE, 1)
             sipp_b200.stats(reset=True)
@@ -24,16 +25,18 @@ for m in (256, 1024, 2048, 4096, 8192, 16384):
     A, B = sipp_b200.seeded_inputs(3, min(m, 4096))
     k = max(1, m // 4096)
     ctx = sipp_b200.ProverContext(A * k, B * k)
-    for wide in (0, 1 << 20):
+    for wide in (0, 1 << 20, 2 << 20):
         sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, wide)
+        sipp_b200.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1 << 20 if wide == 2 << 20 else 0)
         for rep in range(2):
             sipp_b200.set_option(_lib.OPT_PROFILE, 1)
             sipp_b200.stats(reset=True)
             z = ctx.inner_product()
             st = sipp_b200.stats(reset=True)
-        print("m=%6d wide=%d  miller %.3f ms  reduce+fe %.3f ms" % (m, 1 if wide else 0, st["miller_ms"], st["reduce_fe_ms"]))
+        print("m=%6d lines %s accum %s  miller %.3f ms  reduce+fe %.3f ms" % (m, "wide" if wide else "thread", "machine" if wide == 2 << 20 else "6-lane", st["miller_ms"], st["reduce_fe_ms"]))
     ctx.close()
 sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
+sipp_b200.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1536)
 
 # fold alone: time per fold of h elements for both kernels
 import random
