@@ -59,6 +59,7 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          engine (k_fold_wide, latency-bound rounds); 0 = never */
 #define SIPP_OPT_WIDE_ACCUM_MAX 8     /* launches of at most this many pairs accumulate the lines on the 32-lane Fq12 machine
                                          (k_accum_eng) instead of the 6-lane groups of k_accum; 0 = never */
+#define SIPP_OPT_BATCH_KPG_MAX 9      /* batched instances: at most this many pairs of one product share an accumulator group */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 
@@ -127,6 +128,16 @@ int sipp_ctx_prove(sipp_ctx *ctx, const uint8_t *A, const uint8_t *B, uint8_t *p
 int sipp_verify_native(const uint8_t *A, size_t a_len, const uint8_t *B, size_t b_len, const uint8_t *proof, size_t proof_len,
                        uint8_t *final_A, uint8_t *final_B, uint8_t *final_Z);
 
+/* ---- batched instances: `count` independent proofs in lock-step (BASELINE config "4096 independent n=128 instances") ---- */
+/* Equivalent to `count` calls of sipp_prove_native (prover_native.rs:26-80) on A[j*n .. (j+1)*n), B[j*n .. (j+1)*n):
+ * proofs = count x sipp_proof_len(n) x 384 B, instance j's proof at proofs + j * sipp_proof_len(n) * 384 in the returned
+ * (reversed) order.  Round k of every instance runs in the same launches; each instance keeps its own Fiat-Shamir chain
+ * (transcript_native.rs:14-66) ON THE DEVICE, so nothing crosses PCIe between the upload and the proofs.  Instances are
+ * independent: a multi-GPU host gives each rank its own slice of instances, no collective. */
+int sipp_prove_native_batch(const uint8_t *A, const uint8_t *B, size_t n, size_t count, uint8_t *proofs);
+/* same with DEVICE buffers in boundary format (inputs resident in HBM, proofs left in HBM) */
+int sipp_prove_native_batch_device(const void *dA, const void *dB, size_t n, size_t count, void *d_proofs);
+
 /* ---- synthetic inputs and instrumentation --------------------------------------------------------------- */
 /* A_i = [a_i]G1, B_i = [b_i]G2 with the documented SplitMix64 scalar stream (same as oracle_seeded_inputs);
  * generated on the GPU into DEVICE buffers dA (n x 64 B), dB (n x 128 B) in boundary format */
@@ -159,6 +170,12 @@ int sipp_test_fq12_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out, 
 int sipp_test_fold_plan(const uint8_t x[32], const uint8_t x_inv[32], uint32_t *out_words, size_t out_cap);
 /* which: 0 mad.lo.u32 chains, 1 mad.wide.u32 chains, 2 lo/hi carry chains, 3 fq_mul PTX, 4 fq_mul portable.
  * returns operations per second (IMAD instructions for 0-2, Fq multiplications for 3-4) in *ops_per_s */
+/* device transcript (k_transcript.cu): `count` independent Poseidon permutations, 12 x u64 each, in place */
+int sipp_test_poseidon_device(uint64_t *states, size_t count);
+/* one transcript round for `count` instances: states in/out (4 x u64 each); fq12s = count x nf x 384 B with nf = 2 (Z_L, Z_R)
+ * or 3 (Z, Z_L, Z_R: first round); x_out = count x 64 B (challenge x || x^-1); plans_out = count x raw fold plan
+ * (same words as sipp_test_fold_plan) or NULL */
+int sipp_test_transcript_round_device(uint64_t *states, const uint8_t *fq12s, int nf, size_t count, uint8_t *x_out, uint32_t *plans_out);
 int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);
 
 #ifdef __cplusplus

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("SIPP_LIB") or os.path.join(_HERE, "libsipp_b200.so") 
 
 OK, ERR_CUDA, ERR_ARG, ERR_LENGTH, ERR_ZERO_CHALLENGE, ERR_SHORT_PROOF, ERR_ENCODING, ERR_VERIFY = 0, -1, -2, -3, -4, -5, -6, -7
 OPT_FE_NORMALISATION, OPT_FQ12_ORDER, OPT_PROFILE, OPT_PIPELINE, OPT_WIDE_LINES_MAX, OPT_FE_ENGINE, OPT_WIDE_FOLD_MAX, OPT_WIDE_ACCUM_MAX = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_BATCH_KPG_MAX = 9
 
 
 class SippError(RuntimeError):
@@ -81,6 +82,11 @@ def load():
     lib.sipp_get_stats.argtypes = [ctypes.POINTER(Stats)]
     lib.sipp_test_fq_op.argtypes = [i, u8p, u8p, u8p, sz]
     lib.sipp_test_fq12_op.argtypes = [i, u8p, u8p, u8p, sz]
+    lib.sipp_prove_native_batch.argtypes = [u8p, u8p, sz, sz, u8p]
+    lib.sipp_prove_native_batch_device.argtypes = [vp, vp, sz, sz, vp]
+    lib.sipp_test_poseidon_device.argtypes = [ctypes.POINTER(ctypes.c_uint64), sz]
+    lib.sipp_test_transcript_round_device.argtypes = [ctypes.POINTER(ctypes.c_uint64), u8p, i, sz, u8p, ctypes.POINTER(ctypes.c_uint32)]
+    lib.sipp_test_fold_plan.argtypes = [u8p, u8p, ctypes.POINTER(ctypes.c_uint32), sz]
     lib.sipp_microbench.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib

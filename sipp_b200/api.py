@@ -132,6 +132,26 @@ def sipp_prove_native(A: Points, B: Points) -> List[bytes]:
     return _split(proof.raw, FQ12_BYTES)
 
 
+def sipp_prove_native_batch(A: Points, B: Points, n: int) -> List[List[bytes]]:
+    """`count` independent instances of `n` pairs each, proved in lock-step on the device (one Fiat-Shamir chain per instance
+    on the GPU): proofs[j] == sipp_prove_native(A[j*n:(j+1)*n], B[j*n:(j+1)*n])  (prover_native.rs:26-80 per instance)."""
+    a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+    na, nb = len(a) // G1_BYTES, len(b) // G2_BYTES
+    assert na == nb, "assert_eq!(A.len(), B.len())"  # prover_native.rs:27
+    if n <= 0 or na % n:
+        raise ValueError("the number of pairs (%d) is not a multiple of the instance size %d" % (na, n))
+    count = na // n
+    _lib.require_gpu_once()
+    lib = _lib.load()
+    plen = lib.sipp_proof_len(n)
+    if plen == 0:
+        raise SippError(_lib.ERR_ARG, "n must be a non-zero power of two")
+    proofs = ctypes.create_string_buffer(FQ12_BYTES * plen * count)
+    _lib.check(lib.sipp_prove_native_batch(a, b, n, count, proofs))
+    raw = proofs.raw
+    return [_split(raw[j * plen * FQ12_BYTES:(j + 1) * plen * FQ12_BYTES], FQ12_BYTES) for j in range(count)]
+
+
 def sipp_verify_native(A: Points, B: Points, proof: Sequence[bytes]) -> SIPPStatement:
     """verifier_native.rs:14-85; returns the SIPPStatement or raises VerificationError."""
     a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)

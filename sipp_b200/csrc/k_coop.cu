@@ -26,18 +26,7 @@ namespace sipp {
 
 // ------------------------------------------------------------------------------------------------ L: line generation
 // A chunk covers pairs [c0, c0 + mc) of EVERY product of the job; lines layout [prod][mc][91][80 words].
-#ifndef SIPP_LINES_MINBLOCKS
-#define SIPP_LINES_MINBLOCKS 4  // 230 registers; capping at 128 (8 blocks) spills and measured 8% slower (profiles/r01_ab_occupancy.txt)
-#endif
-__global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_lines(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, MillerJob job, int nprod, size_t c0,
-                                              size_t mc, uint32_t* __restrict__ lines) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= mc * (size_t)nprod) return;
-    int prod = (int)(t / mc);
-    size_t j = c0 + (t - (size_t)prod * mc);
-    G1A p = load_g1(A, job.a_off[prod] + j);
-    G2A q = load_g2(B, job.b_off[prod] + j);
-    uint32_t* out = lines + t * SIPP_PAIR_LINE_WORDS;
+__device__ __forceinline__ void lines_of_pair(const G1A& p, const G2A& q, uint32_t* __restrict__ out) {
     if (affine_is_identity(p) || affine_is_identity(q)) {
         // contributes the factor 1: every line is the constant 1
         Fq2 one = fq2_one(), zero = fq2_zero();
@@ -61,6 +50,31 @@ __global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_lines(const uint32
             store_fq2_words(o + 48, l3);
             store_fq2_words(o + 64, fq2_mul_xi(l3));
         });
+}
+#ifndef SIPP_LINES_MINBLOCKS
+#define SIPP_LINES_MINBLOCKS 4  // 230 registers; capping at 128 (8 blocks) spills and measured 8% slower (profiles/r01_ab_occupancy.txt)
+#endif
+__global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_lines(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, MillerJob job, int nprod, size_t c0,
+                                              size_t mc, uint32_t* __restrict__ lines) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= mc * (size_t)nprod) return;
+    int prod = (int)(t / mc);
+    size_t j = c0 + (t - (size_t)prod * mc);
+    lines_of_pair(load_g1(A, job.a_off[prod] + j), load_g2(B, job.b_off[prod] + j), lines + t * SIPP_PAIR_LINE_WORDS);
+}
+
+// Batched instances (lock-step rounds over `count` independent SIPP instances, launch.h BatchJob): product P = inst * nprod + y
+// pairs A[inst * stride + a_off[y] + i] with B[inst * stride + b_off[y] + i], i < h.  A chunk covers whole products
+// [p0, p0 + np); lines layout [product][h][91][80 words], so one accumulator group owns consecutive pairs of ONE product.
+__global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_lines_batch(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, BatchJob job, size_t p0,
+                                                                         size_t np, uint32_t* __restrict__ lines) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np * job.h) return;
+    size_t P = p0 + t / job.h, i = t % job.h;
+    size_t inst = P / (size_t)job.nprod;
+    int y = (int)(P % (size_t)job.nprod);
+    size_t base = inst * job.stride + i;
+    lines_of_pair(load_g1(A, base + job.a_off[y]), load_g2(B, base + job.b_off[y]), lines + t * SIPP_PAIR_LINE_WORDS);
 }
 
 // ------------------------------------------------------------------------------------------------ A: accumulation
@@ -96,7 +110,7 @@ __device__ __noinline__ Fq2 block_product_coop(const Lane6& L, Fq2 f, uint32_t* 
 #define SIPP_ACCUM_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(SIPP_ACCUM_THREADS, SIPP_ACCUM_MINBLOCKS) k_accum(const uint32_t* __restrict__ lines, size_t m_chunk, int nprod_in_chunk, int kpg,
-                                                            uint32_t* __restrict__ partials, int partial_stride_prod, int block_offset) {
+                                                            uint32_t* __restrict__ partials, int partial_stride_prod, int block_offset, int segmented) {
     __shared__ __align__(16) uint32_t stage[SIPP_ACCUM_GROUPS][2][SIPP_LINE_WORDS];
     __shared__ __align__(16) uint32_t red[SIPP_ACCUM_GROUPS * 96];
     const Lane6 L = lane6_of_thread();
@@ -153,6 +167,12 @@ __global__ void __launch_bounds__(SIPP_ACCUM_THREADS, SIPP_ACCUM_MINBLOCKS) k_ac
     fold_lines();
     if (npairs == 0) f = lane_one(k);
 
+    if (segmented) {
+        // batched instances: a group's pairs all belong to one product; the per-product reduction (k_fe_batch) multiplies the
+        // h / kpg consecutive group results.  block_offset counts groups here.
+        if (active_lane && npairs > 0) store_fq2_words(partials + ((size_t)block_offset + gid) * 96 + k * 16, f);
+        return;
+    }
     f = block_product_coop(L, f, red, active_lane ? group : SIPP_ACCUM_GROUPS, SIPP_ACCUM_GROUPS);
     if (active_lane && group == 0) store_fq2_words(partials + ((size_t)(blockIdx.x + block_offset) * partial_stride_prod + prod) * 96 + k * 16, f);
 }
@@ -189,6 +209,32 @@ __global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_reduce_fe_coop(const uin
                 store_fq2_words(out + prod * 96 + k * 16, f);
             }
         }
+    }
+}
+
+
+// Batched instances: product P multiplies its `gpp` consecutive group results and takes ONE final exponentiation; 20 products
+// per block (6 lanes each).  out: instance `P / nprod` at out + inst * out_stride words, Fq12 slot slot0 (y = 0) / slot1 (y = 1),
+// boundary bytes -- the instance's proof vector, written in its final (reversed) order (prover_native.rs:78).
+__global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_fe_batch(const uint32_t* __restrict__ partials, size_t nproducts, int gpp, int nprod,
+                                                               uint32_t* __restrict__ out, size_t out_stride, int slot0, int slot1, int ark_norm) {
+    const Lane6 L = lane6_of_thread();
+    const int warp = threadIdx.x >> 5;
+    const bool active_lane = L.k < 6;
+    const int group = warp * SIPP_GROUPS_PER_WARP + (active_lane ? L.base / 6 : 0);
+    const int k = active_lane ? L.k : 0;
+    size_t P = (size_t)blockIdx.x * SIPP_ACCUM_GROUPS + group;
+    const bool have = active_lane && P < nproducts;
+    if (P >= nproducts) P = nproducts - 1;
+    const uint32_t* src = partials + P * (size_t)gpp * 96 + k * 16;
+    Fq2 f = load_fq2_words(src);
+    for (int g = 1; g < gpp; g++) f = coop_mul(L, f, load_fq2_words(src + (size_t)g * 96));
+    f = coop_final_exp(L, f, ark_norm != 0);
+    if (have) {
+        size_t inst = P / (size_t)nprod;
+        int y = (int)(P % (size_t)nprod);
+        int slot = (k & 1) * 3 + (k >> 1);
+        fq2_encode(out + inst * out_stride + (size_t)(y ? slot1 : slot0) * 96 + slot * 16, f);
     }
 }
 
@@ -233,7 +279,7 @@ int accum_blocks(size_t m_chunk, int kpg) {
 }
 int launch_accum(const uint32_t* lines, size_t m_chunk, int nprod, int kpg, uint32_t* partials, int block_offset, cudaStream_t s) {
     dim3 grid((unsigned)accum_blocks(m_chunk, kpg), (unsigned)nprod);
-    k_accum<<<grid, SIPP_ACCUM_THREADS, 0, s>>>(lines, m_chunk, nprod, kpg, partials, nprod, block_offset);
+    k_accum<<<grid, SIPP_ACCUM_THREADS, 0, s>>>(lines, m_chunk, nprod, kpg, partials, nprod, block_offset, 0);
     return (int)cudaGetLastError();
 }
 int launch_reduce_fe_coop(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s) {
@@ -242,6 +288,23 @@ int launch_reduce_fe_coop(const uint32_t* partials, int count, int nprod, uint32
 }
 int launch_test_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s) {
     k_test_coop_op<<<(unsigned)((count + SIPP_GROUPS_PER_WARP - 1) / SIPP_GROUPS_PER_WARP), 32, 0, s>>>(op, a, b, out, count);
+    return (int)cudaGetLastError();
+}
+int launch_lines_batch(const uint32_t* A, const uint32_t* B, const BatchJob& job, size_t p0, size_t np, uint32_t* lines, cudaStream_t s) {
+    size_t threads = np * job.h;
+    k_lines_batch<<<(unsigned)((threads + 63) / 64), 64, 0, s>>>(A, B, job, p0, np, lines);
+    return (int)cudaGetLastError();
+}
+// segmented accumulation of a chunk of `pairs` = products * h pairs, kpg | h; group results to partials[group_offset + gid]
+int launch_accum_batch(const uint32_t* lines, size_t pairs, int kpg, uint32_t* partials, size_t group_offset, cudaStream_t s) {
+    dim3 grid((unsigned)accum_blocks(pairs, kpg), 1);
+    k_accum<<<grid, SIPP_ACCUM_THREADS, 0, s>>>(lines, pairs, 1, kpg, partials, 1, (int)group_offset, 1);
+    return (int)cudaGetLastError();
+}
+int launch_fe_batch(const uint32_t* partials, size_t nproducts, int gpp, int nprod, uint32_t* out, size_t out_stride, int slot0, int slot1, int ark_norm,
+                    cudaStream_t s) {
+    k_fe_batch<<<(unsigned)((nproducts + SIPP_ACCUM_GROUPS - 1) / SIPP_ACCUM_GROUPS), SIPP_ACCUM_THREADS, 0, s>>>(partials, nproducts, gpp, nprod, out, out_stride,
+                                                                                                                slot0, slot1, ark_norm);
     return (int)cudaGetLastError();
 }
 size_t lines_bytes_per_pair() { return (size_t)SIPP_PAIR_LINE_WORDS * sizeof(uint32_t); }

@@ -92,6 +92,48 @@ __global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_split(uint32_t* __re
     }
 }
 
+
+// Batched instances: the same lane split, but every instance has its own challenge, so the plan is read per element
+// (plans[inst]).  A warp's 32 elements belong to one instance while h >= 32 (uniform digit tests); in the last rounds a warp
+// spans several instances and the digit branches diverge -- those rounds hold 31/127 of an instance's fold work.
+__global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_batch(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, size_t stride, size_t count,
+                                                                 const FoldPlan* __restrict__ plans, unsigned g2_blocks) {
+    __shared__ __align__(16) uint32_t xch[3 * 32 * 48];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t total = count * h;
+    if (blockIdx.x < g2_blocks) {
+        size_t e = (size_t)blockIdx.x * 32 + lane;
+        const bool valid = e < total;
+        if (!valid) e = total - 1;
+        const size_t inst = e / h, i = inst * stride + e % h;
+        const FoldPlan* pl = plans + inst;
+        Jac<Fq2> acc = fold_component(load_g2(B, i + h), pl->g2[warp], warp, pl->g2_bits);
+        if (warp > 0) store_jac(xch + ((warp - 1) * 32 + lane) * 48, acc);
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll 1
+            for (int j = 0; j < 3; j++) acc = jac_add(acc, load_jac2(xch + (j * 32 + lane) * 48));
+            G2A r = jac_to_affine(jac_add_affine(acc, load_g2(B, i)));
+            if (valid) store_g2(B, i, r);
+        }
+    } else {
+        const int comp = warp & 1, half = warp >> 1;
+        size_t e = (size_t)(blockIdx.x - g2_blocks) * 64 + half * 32 + lane;
+        const bool valid = e < total;
+        if (!valid) e = total - 1;
+        const size_t inst = e / h, i = inst * stride + e % h;
+        const FoldPlan* pl = plans + inst;
+        Jac<Fq> acc = fold_component(load_g1(A, i + h), pl->g1[comp], comp, pl->g1_bits);
+        if (comp == 1) store_jac(xch + (half * 32 + lane) * 24, acc);
+        __syncthreads();
+        if (comp == 0) {
+            acc = jac_add(acc, load_jac1(xch + (half * 32 + lane) * 24));
+            G1A r = jac_to_affine(jac_add_affine(acc, load_g1(A, i)));
+            if (valid) store_g1(A, i, r);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ inputs
 __device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t step) {  // value of the step-th output (1-based)
     uint64_t z = seed + step * 0x9E3779B97F4A7C15ull;
@@ -143,6 +185,12 @@ int launch_fold(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaSt
     // what another block writes.
     unsigned g2_blocks = (unsigned)((h + 31) / 32), g1_blocks = (unsigned)((h + 63) / 64);
     k_fold_split<<<g2_blocks + g1_blocks, SIPP_FOLD_THREADS, 0, s>>>(A, B, h, plan, g2_blocks);
+    return (int)cudaGetLastError();
+}
+int launch_fold_batch(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t count, const FoldPlan* plans, cudaStream_t s) {
+    size_t total = count * h;
+    unsigned g2_blocks = (unsigned)((total + 31) / 32), g1_blocks = (unsigned)((total + 63) / 64);
+    k_fold_batch<<<g2_blocks + g1_blocks, SIPP_FOLD_THREADS, 0, s>>>(A, B, h, stride, count, plans, g2_blocks);
     return (int)cudaGetLastError();
 }
 int launch_seeded_inputs(uint64_t seed, size_t n, uint32_t* dA, uint32_t* dB, cudaStream_t s) {

@@ -15,6 +15,15 @@ struct MillerJob {
     size_t b_off[2];
     size_t m;
 };
+// Lock-step batch of independent instances: instance `inst` owns points [inst * stride, inst * stride + current n) of A and B;
+// product P = inst * nprod + y pairs A[inst * stride + a_off[y] + i] with B[inst * stride + b_off[y] + i], i < h.
+struct BatchJob {
+    size_t stride;
+    size_t a_off[2];
+    size_t b_off[2];
+    size_t h;
+    int nprod;
+};
 struct Scalar256 {
     uint32_t w[8];
 };
@@ -44,5 +53,16 @@ int accum_eng_blocks(size_t m_chunk, int kpg);
 int launch_accum_eng(const uint32_t* lines, size_t m_chunk, int nprod, int kpg, uint32_t* partials, int block_offset, cudaStream_t s);
 int launch_test_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s);
 size_t lines_bytes_per_pair();
+
+// batched instances (k_coop.cu, k_fold.cu, k_transcript.cu)
+int launch_lines_batch(const uint32_t* A, const uint32_t* B, const BatchJob& job, size_t p0, size_t np, uint32_t* lines, cudaStream_t s);
+int launch_accum_batch(const uint32_t* lines, size_t pairs, int kpg, uint32_t* partials, size_t group_offset, cudaStream_t s);
+int launch_fe_batch(const uint32_t* partials, size_t nproducts, int gpp, int nprod, uint32_t* out, size_t out_stride, int slot0, int slot1, int ark_norm,
+                    cudaStream_t s);
+int launch_fold_batch(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t count, const FoldPlan* plans, cudaStream_t s);
+int launch_tr_absorb_pairs(const uint32_t* bytesA, const uint32_t* bytesB, size_t n, size_t count, uint64_t* states, cudaStream_t s);
+int launch_tr_round(uint64_t* states, const uint32_t* proofs, size_t np, int slot_z, int slot_l, int slot_r, int order, size_t count, FoldPlan* plans,
+                    uint64_t* challenges, int* flags, cudaStream_t s);
+int launch_test_poseidon(uint64_t* states, size_t count, cudaStream_t s);
 
 }  // namespace sipp
