@@ -60,6 +60,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
 #define SIPP_OPT_WIDE_ACCUM_MAX 8     /* launches of at most this many pairs accumulate the lines on the 32-lane Fq12 machine
                                          (k_accum_eng) instead of the 6-lane groups of k_accum; 0 = never */
 #define SIPP_OPT_BATCH_KPG_MAX 9      /* batched instances: at most this many pairs of one product share an accumulator group */
+#define SIPP_OPT_FOLD_STRAUS 10       /* throughput folds: 1 = one thread per element with shared doublings (k_fold_straus) [default];
+                                         0 = lane-split components (k_fold_batch / k_fold_split) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

@@ -1,4 +1,7 @@
 // k_fold.cu -- see kernels overview in device_common.cuh
+// Fq2 products are real calls: fully inlined the scalar-multiplication loops are 45-65k SASS instructions, several times the
+// instruction cache.
+#define SIPP_CURVE_FQ2_CALLS 1
 #include "coop.cuh"
 #include "device_common.cuh"
 #include "fold_plan.h"
@@ -134,6 +137,66 @@ __global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_batch(uint32_t* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K4, throughput form
+// One thread per element, all endomorphism components on ONE accumulator (Straus / Shamir): the 66 (G2) or 128 (G1)
+// doublings are shared by the 4 (2) sub-scalars instead of being repeated per component as in the lane-split kernels --
+// G2: 66 dbl + ~88 mixed adds (~3.7k Fq-mul) against 4 x (66 dbl + 22 adds) (~6.9k); G1: ~1.8k against ~2.7k.  The lane
+// split buys latency (k_fold_split / k_fold_wide, small rounds of one proof); this one buys work, for launches that fill
+// the GPU: batched instances and the first rounds of a large proof.  plans[inst] as in k_fold_batch (count = 1: one proof).
+#define SIPP_STRAUS_THREADS 64
+
+template <class F, int NC>
+__device__ __forceinline__ Jac<F> straus_naf(const Affine<F>* tbl, const FoldComp* comps, int bits) {
+    Jac<F> acc = jac_identity<F>();
+#pragma unroll 1
+    for (int i = bits - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        const uint32_t m = 1u << (i & 31);
+        const int w = i >> 5;
+#pragma unroll 1
+        for (int c = 0; c < NC; c++) {
+            const bool dp = (comps[c].plus[w] & m) != 0, dm = (comps[c].minus[w] & m) != 0;
+            if (dp || dm) {
+                Affine<F> t = tbl[c];
+                if (dm) t.y = f_neg(t.y);
+                acc = jac_add_affine(acc, t);
+            }
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(SIPP_STRAUS_THREADS) k_fold_straus(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, size_t stride, size_t count,
+                                                                   const FoldPlan* __restrict__ plans, unsigned g2_blocks) {
+    const size_t total = count * h;
+    const bool is_g2 = blockIdx.x < g2_blocks;
+    size_t e = (size_t)(is_g2 ? blockIdx.x : blockIdx.x - g2_blocks) * SIPP_STRAUS_THREADS + threadIdx.x;
+    if (e >= total) return;
+    const size_t inst = e / h, i = inst * stride + e % h;
+    const FoldPlan* pl = plans + inst;
+    if (is_g2) {
+        G2A tbl[4];
+        const G2A p2 = load_g2(B, i + h);
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            tbl[c] = endo_apply(p2, c);
+            if (pl->g2[c].neg) tbl[c].y = f_neg(tbl[c].y);
+        }
+        Jac<Fq2> acc = straus_naf<Fq2, 4>(tbl, pl->g2, pl->g2_bits);
+        store_g2(B, i, jac_to_affine(jac_add_affine(acc, load_g2(B, i))));
+    } else {
+        G1A tbl[2];
+        const G1A p2 = load_g1(A, i + h);
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+            tbl[c] = endo_apply(p2, c);
+            if (pl->g1[c].neg) tbl[c].y = f_neg(tbl[c].y);
+        }
+        Jac<Fq> acc = straus_naf<Fq, 2>(tbl, pl->g1, pl->g1_bits);
+        store_g1(A, i, jac_to_affine(jac_add_affine(acc, load_g1(A, i))));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ inputs
 __device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t step) {  // value of the step-th output (1-based)
     uint64_t z = seed + step * 0x9E3779B97F4A7C15ull;
@@ -191,6 +254,12 @@ int launch_fold_batch(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t 
     size_t total = count * h;
     unsigned g2_blocks = (unsigned)((total + 31) / 32), g1_blocks = (unsigned)((total + 63) / 64);
     k_fold_batch<<<g2_blocks + g1_blocks, SIPP_FOLD_THREADS, 0, s>>>(A, B, h, stride, count, plans, g2_blocks);
+    return (int)cudaGetLastError();
+}
+int launch_fold_straus(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t count, const FoldPlan* plans, cudaStream_t s) {
+    size_t total = count * h;
+    unsigned blocks = (unsigned)((total + SIPP_STRAUS_THREADS - 1) / SIPP_STRAUS_THREADS);
+    k_fold_straus<<<2 * blocks, SIPP_STRAUS_THREADS, 0, s>>>(A, B, h, stride, count, plans, blocks);
     return (int)cudaGetLastError();
 }
 int launch_seeded_inputs(uint64_t seed, size_t n, uint32_t* dA, uint32_t* dB, cudaStream_t s) {
