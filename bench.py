@@ -92,8 +92,33 @@ def run_reference(args):
     if rank != 0:
         return 0
     from oracle import pyoracle as o
-    n = args.n or PAIRS_PER_GPU * args.gpus
     cores = os.cpu_count() or 1
+    if args.workload == "batch":
+        # config 5 on the host cores: instances are independent, so a step proves ONE instance with every core working on it
+        # (the oracle parallelises the pairings of a product); work per instance is identical, instances/s = 1 / step
+        n = args.instance_n
+        A, B = o.seeded_inputs(5, n, threads=cores)
+        for _ in range(args.warmup):
+            o.sipp_prove(A[:64 * 32], B[:128 * 32], o.FAITHFUL, cores)
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            o.sipp_prove(A, B, o.FAITHFUL, cores)
+            times.append(time.perf_counter() - t0)
+        per_step = sum(times) / len(times)
+        value = 1.0 / per_step
+        print(json.dumps({"impl": "reference", "metric": "SIPP native prove throughput, batched independent instances (instances per second)",
+                          "value": value, "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "u32 limbs (254-bit modular integer)", "data": "synthetic",
+                          "config": {"workload": "batched throughput: %d independent n=%d SIPP instances (CPU restatement of the reference)"
+                                                 % (args.instances, n), "instances": args.instances, "n": n},
+                          "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port",
+                                           "sample": "one faithful n=%d prove per step with all %d host threads; the %d instances are identical "
+                                                     "work" % (n, cores, args.instances)},
+                          "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    n = args.n or PAIRS_PER_GPU * args.gpus
     A, B = o.seeded_inputs(2, n, threads=cores)
     # bounded sample: one step = one faithful prove of the first `sample_n` pairs (work is linear in n)
     sample_n = min(n, 512)
@@ -120,6 +145,148 @@ def run_reference(args):
     return 0
 
 
+def measure_batch(count_total, n, world, rank, local_rank, W, K, barrier, all_max, flush):
+    """BASELINE config 5: `count_total` independent n-pair instances proved in lock-step, each with its own Fiat-Shamir chain on
+    the device; rank g owns a contiguous slice of the instances (no collective).  Returns a dict of measurements."""
+    import ctypes
+    import torch
+    import sipp_b200
+    from sipp_b200 import _lib
+    from sipp_b200.sharded import shard_instances
+    lib = _lib.load()
+    lo, hi = shard_instances(count_total, rank, world)
+    count = hi - lo
+    plen = lib.sipp_proof_len(n)
+    total = n * count
+    # instance j is seeded_inputs(seed = 5)[j * n : (j + 1) * n]: generate the global stream, keep this rank's slice
+    gA = torch.empty(count_total * n * 64, dtype=torch.uint8, device="cuda")
+    gB = torch.empty(count_total * n * 128, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.sipp_seeded_inputs_device(5, count_total * n, gA.data_ptr(), gB.data_ptr()))
+    dA = gA[lo * n * 64:hi * n * 64].clone()
+    dB = gB[lo * n * 128:hi * n * 128].clone()
+    del gA, gB
+    dP = torch.empty(count * plen * 384, dtype=torch.uint8, device="cuda")
+    A_pin, B_pin = dA.cpu().pin_memory(), dB.cpu().pin_memory()
+    P_pin = torch.empty(count * plen * 384, dtype=torch.uint8).pin_memory()
+
+    def step_resident():
+        _lib.check(lib.sipp_prove_native_batch_device(dA.data_ptr(), dB.data_ptr(), n, count, dP.data_ptr()))
+
+    def step_e2e():
+        _lib.check(lib.sipp_prove_native_batch(ctypes.c_char_p(A_pin.data_ptr()), ctypes.c_char_p(B_pin.data_ptr()), n, count,
+                                               ctypes.c_char_p(P_pin.data_ptr())))
+
+    def timed(fn, steps):
+        tot = 0.0
+        for _ in range(steps):
+            flush()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t0 = time.perf_counter()
+            fn()
+            e1.record()
+            barrier()
+            tot += all_max(max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3))
+        return tot
+
+    for _ in range(W):
+        step_resident()
+    sipp_b200.set_option(_lib.OPT_PROFILE, 1)
+    sipp_b200.stats(reset=True)
+    t_res = timed(step_resident, K)
+    st = sipp_b200.stats(reset=True)
+    sipp_b200.set_option(_lib.OPT_PROFILE, 0)
+    for _ in range(W):
+        step_e2e()
+    t_e2e = timed(step_e2e, K)
+    proofs = dP.cpu().numpy().tobytes()
+    assert proofs == P_pin.numpy().tobytes(), "resident and e2e batch proofs differ"
+    # parity inside the run: a sample of this rank's instances against the single-instance prover (itself pinned to the oracle)
+    A, B = A_pin.numpy().tobytes(), B_pin.numpy().tobytes()
+    for j in sorted({0, count // 2, count - 1}):
+        a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
+        assert proofs[j * plen * 384:(j + 1) * plen * 384] == b"".join(sipp_b200.sipp_prove_native(a, b)), "batch instance %d differs" % j
+    return {"count": count, "t_res": t_res, "t_e2e": t_e2e, "stats": st, "h2d": total * 192, "d2h": count * plen * 384,
+            "sample": (A[:64 * n], B[:128 * n], proofs[:plen * 384])}
+
+
+def run_batch(args, world, rank, local_rank, W, K):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import sipp_b200
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    n, count_total = args.instance_n, args.instances
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_max(dt):
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return dt
+
+    with ClockSampler(local_rank) as clocks:
+        m = measure_batch(count_total, n, world, rank, local_rank, W, K, barrier, all_max, flush)
+    clk = clocks.summary()
+    peaks = {}
+    for which, name in ((0, "mad_lo"), (1, "mad_wide"), (2, "mad_lo_hi_carry"), (3, "fq_mul_ptx")):
+        ops, ms = ctypes.c_double(), ctypes.c_double()
+        _lib.check(lib.sipp_microbench(which, 2000 if which < 3 else 400, ctypes.byref(ops), ctypes.byref(ms)))
+        peaks[name] = ops.value
+    imad_peak = max(peaks["mad_lo"], 2 * peaks["mad_wide"], peaks["mad_lo_hi_carry"])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    st = m["stats"]
+    mill_ach = st["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / max(st["miller_ms"] * 1e-3, 1e-12)
+    line = {"metric": "SIPP native prove throughput, batched independent instances (instances per second)", "value": count_total * K / m["t_res"],
+            "unit": "instances/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": m["t_res"] / K * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integer)", "data": "synthetic",
+            "config": {"workload": "batched throughput: %d independent n=%d SIPP instances, %dxB200 (instances sharded by rank, no collective)"
+                                   % (count_total, n, world), "instances": count_total, "n": n, "seed": 5,
+                       "miller_loops_per_step": count_total * miller_loops_per_prove(n), "l2": "flushed between steps (256 MB write)",
+                       "transcript": "on the device, one Poseidon chain per instance"},
+            "pairs_per_s": count_total * n * K / m["t_res"],
+            "e2e": {"value": count_total * K / m["t_e2e"], "unit": "instances/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "ms_per_step": m["t_e2e"] / K * 1e3},
+            "gpu_launches": int(st["launches"]), "clocks": clk,
+            "roofline": {"bound": "imad", "kernel": "k_lines_batch + k_accum (Miller loops of all instances of a round)", "achieved": mill_ach / 1e12,
+                         "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak, "traffic": None,
+                         "launches": int(st["miller_launches"]), "avg_launch_ms": st["miller_ms"] / max(1, st["miller_launches"]),
+                         "peak_source": "measured in this run (sipp_microbench)",
+                         "kernel_time_share": {"miller_ms": st["miller_ms"] / K, "final_exp_ms": st["reduce_fe_ms"] / K, "fold_ms": st["fold_ms"] / K,
+                                               "decode_transcript_ms(side stream, overlapped)": st["other_ms"] / K, "step_ms": m["t_res"] / K * 1e3},
+                         "microbench": peaks}}
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as o
+        a, b, gpu = m["sample"]
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        ref = o.sipp_prove(a, b, o.FAITHFUL, 1)
+        dt = time.perf_counter() - t0
+        assert ref == gpu, "batch instance 0 differs from the oracle"
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "instances/s", "cores": 1, "kind": "port",
+                                "sample": "single-thread faithful restatement proving instance 0 (n=%d), %.2f s; byte-identical to the GPU's "
+                                          "proof of that instance; %d host cores would run %d such instances side by side" % (n, dt, cores, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -129,6 +296,12 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--saturated-pairs", type=int, default=1 << 17)
+    ap.add_argument("--workload", default="prove", choices=["prove", "batch"],
+                    help="prove: one n-pair proof (BASELINE configs[1], the default); batch: BASELINE config 5, independent "
+                         "n=128 instances in lock-step, sharded by instance over the GPUs")
+    ap.add_argument("--instances", type=int, default=4096)
+    ap.add_argument("--instance-n", type=int, default=128)
+    ap.add_argument("--batch-instances", type=int, default=4096, help="config-5 summary added to the default line at N=1 (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -153,6 +326,8 @@ def main():
     lib = _lib.load()
     _lib.require_gpu_once()
     W, K = max(args.warmup, 3), args.steps
+    if args.workload == "batch":
+        return run_batch(args, world, rank, local_rank, W, K)
 
     # ---- synthetic inputs (seeded, generated on the GPU; same stream as the oracle's generator) ----
     A, B = sipp_b200.seeded_inputs(2, n)
@@ -316,6 +491,16 @@ def main():
                                           "%.1f s; GPU proof of the same sample is byte-identical" % (sample_n, n, dt),
                                 "all_cores_fast_variant": {"value": sample_n / dt_fast, "cores": os.cpu_count() or 1,
                                                            "note": "product of Miller loops + one final exponentiation, pthreads"}}
+    if world == 1 and args.batch_instances:
+        # BASELINE config 5 beside the headline (one timed step; `--workload batch` is the full bench of that config)
+        bm = measure_batch(args.batch_instances, 128, 1, 0, local_rank, 1, 1, barrier, lambda dt: dt, l2_flush)
+        bst = bm["stats"]
+        line["batched_instances"] = {"workload": "%d independent n=128 instances, lock-step, transcripts on the device" % args.batch_instances,
+                                     "instances_per_s": args.batch_instances / bm["t_res"], "e2e_instances_per_s": args.batch_instances / bm["t_e2e"],
+                                     "pairs_per_s": args.batch_instances * 128 / bm["t_res"], "ms": bm["t_res"] * 1e3,
+                                     "miller_ms": bst["miller_ms"], "final_exp_ms": bst["reduce_fe_ms"], "fold_ms": bst["fold_ms"],
+                                     "miller_frac_of_imad_peak": bst["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL
+                                     / max(bst["miller_ms"] * 1e-3, 1e-12) / imad_peak}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

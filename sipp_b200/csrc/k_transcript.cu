@@ -11,7 +11,8 @@
 //   get_challenge                                              :56-65  (zero-stripped u32 digits of the digest, mod r)
 // followed by what the prover does with the challenge: x^-1 (prover_native.rs:58) and the GLV / GLS recoding the fold
 // kernel consumes (glv_core.h).  The permutation is the textbook Poseidon (30 rounds of constants, S-box, MDS): the same
-// function as the host's sparse-matrix formulation (tests compare the two).
+// function as the host's sparse-matrix formulation (tests compare the two), computed by 16 lanes per instance, one lane per
+// state element.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -56,73 +57,59 @@ __device__ __forceinline__ uint64_t gl_pow7(uint64_t x) {
 }
 __device__ __forceinline__ uint64_t gl_canon(uint64_t a) { return a >= GL_P ? a - GL_P : a; }
 
-// out[r] = sum_i s[(i + r) mod 12] * CIRC[i] + 8 s[0] [r == 0]; 32-bit halves keep the dot products inside u64
-__device__ __forceinline__ void mds_layer(uint64_t* s) {
+// ---- one permutation on a group of 16 lanes: lane l < 12 holds state element l (lanes 12..15 shadow lanes 0..3 and are
+// ignored).  Per round every lane adds its constant, raises to the 7th power (all lanes in a full round, lane 0 in a partial
+// round) and gathers its MDS row with 24 shuffles: the dependent chain of a permutation is ~30 x (S-box + 24 multiply-adds)
+// instead of 30 x 12 x that on one thread, which is what the strictly sequential absorb chain of an instance needs.
+// rc: the 360 round constants in shared memory.
+__device__ __forceinline__ uint64_t poseidon_lanes(uint64_t s, int l, const uint64_t* rc) {
     const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) { lo[i] = (uint32_t)s[i]; hi[i] = (uint32_t)(s[i] >> 32); }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        uint64_t al = 0, ah = 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al += (uint64_t)lo[(i + r) % 12] * C[i];
-            ah += (uint64_t)hi[(i + r) % 12] * C[i];
-        }
-        if (r == 0) { al += (uint64_t)lo[0] * 8; ah += (uint64_t)hi[0] * 8; }
-        // value = al + ah 2^32 < 2^75
-        uint64_t l = al + (ah << 32);
-        uint64_t h = (ah >> 32) + (l < al ? 1 : 0);  // < 2^11
-        uint64_t m = h * GL_EPS;
-        uint64_t x = l + m;
-        if (x < m) x += GL_EPS;
-        s[r] = x;
-    }
-}
-
-__device__ __noinline__ void poseidon_permute(uint64_t* s) {
+    const int lc = l < 12 ? l : l - 12;
 #pragma unroll 1
     for (int rnd = 0; rnd < 30; rnd++) {
+        s = gl_add(s, rc[12 * rnd + lc]);
+        if (rnd < 4 || rnd >= 26 || lc == 0) s = gl_pow7(s);
+        const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+        uint64_t al = 0, ah = 0;
+        int src = lc;
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], c_rc[12 * rnd + i]);
-        if (rnd < 4 || rnd >= 26) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
-        } else {
-            s[0] = gl_pow7(s[0]);
+        for (int i = 0; i < 12; i++) {
+            const uint32_t vlo = __shfl_sync(0xffffffffu, lo, src, 16), vhi = __shfl_sync(0xffffffffu, hi, src, 16);
+            al += (uint64_t)vlo * C[i];
+            ah += (uint64_t)vhi * C[i];
+            src = src == 11 ? 0 : src + 1;
         }
-        mds_layer(s);
+        if (lc == 0) { al += (uint64_t)lo * 8; ah += (uint64_t)hi * 8; }
+        // value = al + ah 2^32 < 2^75
+        const uint64_t lw = al + (ah << 32);
+        const uint64_t hw = (ah >> 32) + (lw < al ? 1 : 0);  // < 2^11
+        const uint64_t m = hw * GL_EPS;
+        uint64_t x = lw + m;
+        if (x < m) x += GL_EPS;
+        s = x;
     }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+    return gl_canon(s);
 }
 
-// state <- hash_n_to_hash_no_pad(state || msg); msg = n u32-valued field elements read through `get(i)`
+// state <- hash_n_to_hash_no_pad(state || msg) on a lane group: lanes 0..3 hold the state in `s` on entry and on return;
+// msg = n u32-valued field elements read through get(i) (every lane calls it with its own index)
 template <class Get>
-__device__ __forceinline__ void tr_append(uint64_t st[4], int n, Get get) {
-    uint64_t s[12];
-#pragma unroll
-    for (int i = 0; i < 4; i++) s[i] = st[i];
-#pragma unroll
-    for (int i = 4; i < 12; i++) s[i] = 0;
-    int first = n < 4 ? n : 4;
-    for (int i = 0; i < first; i++) s[4 + i] = get(i);
-    poseidon_permute(s);
+__device__ __forceinline__ uint64_t tr_append_lanes(uint64_t s, int l, const uint64_t* rc, int n, Get get) {
+    const int lc = l < 12 ? l : l - 12;
+    const int first = n < 4 ? n : 4;
+    if (lc >= 4) s = (lc < 4 + first) ? get(lc - 4) : 0;
+    s = poseidon_lanes(s, l, rc);
     for (int off = first; off < n; off += 8) {
-        int len = n - off < 8 ? n - off : 8;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (i < len) s[i] = get(off + i);
-        poseidon_permute(s);
+        const int len = n - off < 8 ? n - off : 8;
+        if (lc < len) s = get(off + lc);
+        s = poseidon_lanes(s, l, rc);
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++) st[i] = s[i];
+    return s;
 }
 
 // f: 96 canonical u32 words in the boundary (ark nested) order; order 0 = MyFq12 w-basis, 1 = nested
-__device__ __forceinline__ void tr_append_fq12(uint64_t st[4], const uint32_t* f, int order) {
-    tr_append(st, 96, [&](int i) -> uint64_t {
+__device__ __forceinline__ uint64_t tr_append_fq12_lanes(uint64_t s, int l, const uint64_t* rc, const uint32_t* f, int order) {
+    return tr_append_lanes(s, l, rc, 96, [&](int i) -> uint64_t {
         if (order == 1) return f[i];
         int c = i >> 3, w = i & 7;          // coefficient c of MyFq12.coeffs, limb w
         int g = c < 6 ? c : c - 6;          // Fq2 coefficient of w^g; c >= 6 selects its c1
@@ -131,56 +118,68 @@ __device__ __forceinline__ void tr_append_fq12(uint64_t st[4], const uint32_t* f
     });
 }
 
+__device__ __forceinline__ void load_rc_shared(uint64_t* rc) {
+    for (int i = threadIdx.x; i < 360; i += blockDim.x) rc[i] = c_rc[i];
+    __syncthreads();
+}
+
 }  // namespace
 
-// one thread per instance: register A and B (prover_native.rs:36-39), 8 permutations per pair
-__global__ void __launch_bounds__(32) k_tr_absorb_pairs(const uint32_t* __restrict__ bytesA, const uint32_t* __restrict__ bytesB, size_t n, size_t count,
-                                                         uint64_t* __restrict__ states) {
-    size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst >= count) return;
-    uint64_t st[4] = {0, 0, 0, 0};  // Transcript::new  transcript_native.rs:19-23
+#define SIPP_TR_THREADS 32  // two instances per block: the chains are latency-bound, spread them over the SMs
+
+// 16 lanes per instance: register A and B (prover_native.rs:36-39), 8 permutations per pair
+__global__ void __launch_bounds__(SIPP_TR_THREADS) k_tr_absorb_pairs(const uint32_t* __restrict__ bytesA, const uint32_t* __restrict__ bytesB, size_t n, size_t count,
+                                                                     uint64_t* __restrict__ states) {
+    __shared__ uint64_t rc[360];
+    load_rc_shared(rc);
+    const int l = threadIdx.x & 15;
+    size_t inst = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool have = inst < count;
+    if (!have) inst = count - 1;  // shadow: the shuffles need every lane of the warp
+    uint64_t s = 0;  // Transcript::new  transcript_native.rs:19-23
     const uint32_t* a = bytesA + inst * n * 16;
     const uint32_t* b = bytesB + inst * n * 32;
     for (size_t i = 0; i < n; i++) {
         const uint32_t* pa = a + 16 * i;
         const uint32_t* pb = b + 32 * i;
-        tr_append(st, 16, [&](int k) -> uint64_t { return pa[k]; });  // append_g1  :42-46
-        tr_append(st, 32, [&](int k) -> uint64_t { return pb[k]; });  // append_g2  :48-54
+        s = tr_append_lanes(s, l, rc, 16, [&](int k) -> uint64_t { return pa[k]; });  // append_g1  :42-46
+        s = tr_append_lanes(s, l, rc, 32, [&](int k) -> uint64_t { return pb[k]; });  // append_g2  :48-54
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++) states[4 * inst + i] = st[i];
+    if (have && l < 4) states[4 * inst + l] = s;
 }
 
-// one thread per instance: absorb Z (first round only), Z_L, Z_R, derive the challenge, invert it, recode it.
-// proofs: [count][np][96 words] boundary bytes; slots index the Fq12 inside an instance's proof (slot_z < 0: skip).
-// flags[0] |= 1 on a zero challenge (x.inverse().unwrap() panics in the reference), |= 2 on a recoding failure.
-__global__ void __launch_bounds__(32) k_tr_round(uint64_t* __restrict__ states, const uint32_t* __restrict__ proofs, size_t np, int slot_z, int slot_l, int slot_r,
-                                                  int order, size_t count, FoldPlan* __restrict__ plans, uint64_t* __restrict__ challenges, int* __restrict__ flags) {
-    size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst >= count) return;
-    uint64_t st[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) st[i] = states[4 * inst + i];
+// 16 lanes per instance absorb Z (first round only), Z_L, Z_R and derive the digest; lane 0 then turns it into the challenge,
+// inverts it and recodes it.  proofs: [count][np][96 words] boundary bytes; slots index the Fq12 inside an instance's proof
+// (slot_z < 0: skip).  flags[0] |= 1 on a zero challenge (x.inverse().unwrap() panics in the reference), |= 2 on a recoding
+// failure.
+__global__ void __launch_bounds__(SIPP_TR_THREADS) k_tr_round(uint64_t* __restrict__ states, const uint32_t* __restrict__ proofs, size_t np, int slot_z, int slot_l,
+                                                              int slot_r, int order, size_t count, FoldPlan* __restrict__ plans, uint64_t* __restrict__ challenges,
+                                                              int* __restrict__ flags) {
+    __shared__ uint64_t rc[360];
+    load_rc_shared(rc);
+    const int l = threadIdx.x & 15;
+    size_t inst = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool have = inst < count;
+    if (!have) inst = count - 1;
+    uint64_t s = states[4 * inst + (l & 3)];
     const uint32_t* pf = proofs + inst * np * 96;
-    if (slot_z >= 0) tr_append_fq12(st, pf + (size_t)slot_z * 96, order);  // prover_native.rs:42-43
-    tr_append_fq12(st, pf + (size_t)slot_l * 96, order);                    // :52-53
-    tr_append_fq12(st, pf + (size_t)slot_r * 96, order);                    // :54-55
-#pragma unroll
-    for (int i = 0; i < 4; i++) states[4 * inst + i] = st[i];
+    if (slot_z >= 0) s = tr_append_fq12_lanes(s, l, rc, pf + (size_t)slot_z * 96, order);  // prover_native.rs:42-43
+    s = tr_append_fq12_lanes(s, l, rc, pf + (size_t)slot_l * 96, order);                    // :52-53
+    s = tr_append_fq12_lanes(s, l, rc, pf + (size_t)slot_r * 96, order);                    // :54-55
+    if (have && l < 4) states[4 * inst + l] = s;
     // get_challenge (&self: the state is not advanced)  transcript_native.rs:56-65
-    uint64_t s[12];
+    uint64_t d = poseidon_lanes(l < 4 ? s : 0, l, rc);
+    uint64_t dg[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) s[i] = st[i];
-#pragma unroll
-    for (int i = 4; i < 12; i++) s[i] = 0;
-    poseidon_permute(s);
+    for (int k = 0; k < 4; k++) dg[k] = __shfl_sync(0xffffffffu, d, k, 16);
+    if (!have || l != 0) return;
     uint32_t digits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int nd = 0;
     for (int k = 0; k < 4; k++) {  // to_u32_digits strips high zero digits (0 -> no digit at all)
-        uint64_t d = s[k];
-        while (d) {
-            digits[nd++] = (uint32_t)d;
-            d >>= 32;
+        uint64_t t = dg[k];
+        while (t) {
+            digits[nd++] = (uint32_t)t;
+            t >>= 32;
         }
     }
     uint64_t v[4];
@@ -189,19 +188,19 @@ __global__ void __launch_bounds__(32) k_tr_round(uint64_t* __restrict__ states, 
     for (int it = 0; it < 6 && glv::fr_geq(v, RM); it++) {  // v < 2^256 < 6r
         uint64_t borrow = 0;
         for (int i = 0; i < 4; i++) {
-            unsigned __int128 d = (unsigned __int128)v[i] - RM[i] - borrow;
-            v[i] = (uint64_t)d;
-            borrow = (uint64_t)(d >> 64) & 1;
+            unsigned __int128 t = (unsigned __int128)v[i] - RM[i] - borrow;
+            v[i] = (uint64_t)t;
+            borrow = (uint64_t)(t >> 64) & 1;
         }
     }
     uint64_t vi[4] = {0, 0, 0, 0};
-    int rc = glv::fr_inverse(v, vi);                                        // prover_native.rs:58
+    int rc_inv = glv::fr_inverse(v, vi);                                    // prover_native.rs:58
     if (challenges) {
         for (int i = 0; i < 4; i++) { challenges[8 * inst + i] = v[i]; challenges[8 * inst + 4 + i] = vi[i]; }
     }
     FoldPlan plan;
     for (int i = 0; i < (int)(sizeof(FoldPlan) / 4); i++) ((uint32_t*)&plan)[i] = 0;
-    if (rc) {
+    if (rc_inv) {
         atomicOr(flags, 1);
     } else {
         const glv::Tables t = {&SIPP_GLV_G1_BASIS[0][0][0], &SIPP_GLV_G1_RECIP[0][0], SIPP_GLV_G1_RECIP_SIGN,
@@ -211,14 +210,16 @@ __global__ void __launch_bounds__(32) k_tr_round(uint64_t* __restrict__ states, 
     plans[inst] = plan;
 }
 
-// test hook: `count` independent permutations
-__global__ void __launch_bounds__(32) k_test_poseidon(uint64_t* __restrict__ states, size_t count) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    uint64_t s[12];
-    for (int k = 0; k < 12; k++) s[k] = states[12 * i + k];
-    poseidon_permute(s);
-    for (int k = 0; k < 12; k++) states[12 * i + k] = s[k];
+// test hook: `count` independent permutations, 16 lanes each
+__global__ void __launch_bounds__(SIPP_TR_THREADS) k_test_poseidon(uint64_t* __restrict__ states, size_t count) {
+    __shared__ uint64_t rc[360];
+    load_rc_shared(rc);
+    const int l = threadIdx.x & 15;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool have = i < count;
+    if (!have) i = count - 1;
+    uint64_t s = poseidon_lanes(states[12 * i + (l < 12 ? l : l - 12)], l, rc);
+    if (have && l < 12) states[12 * i + l] = s;
 }
 
 static int load_rc() {
@@ -235,20 +236,20 @@ static int load_rc() {
 int launch_tr_absorb_pairs(const uint32_t* bytesA, const uint32_t* bytesB, size_t n, size_t count, uint64_t* states, cudaStream_t s) {
     int e = load_rc();
     if (e) return e;
-    k_tr_absorb_pairs<<<(unsigned)((count + 31) / 32), 32, 0, s>>>(bytesA, bytesB, n, count, states);
+    k_tr_absorb_pairs<<<(unsigned)((count * 16 + SIPP_TR_THREADS - 1) / SIPP_TR_THREADS), SIPP_TR_THREADS, 0, s>>>(bytesA, bytesB, n, count, states);
     return (int)cudaGetLastError();
 }
 int launch_tr_round(uint64_t* states, const uint32_t* proofs, size_t np, int slot_z, int slot_l, int slot_r, int order, size_t count, FoldPlan* plans,
                     uint64_t* challenges, int* flags, cudaStream_t s) {
     int e = load_rc();
     if (e) return e;
-    k_tr_round<<<(unsigned)((count + 31) / 32), 32, 0, s>>>(states, proofs, np, slot_z, slot_l, slot_r, order, count, plans, challenges, flags);
+    k_tr_round<<<(unsigned)((count * 16 + SIPP_TR_THREADS - 1) / SIPP_TR_THREADS), SIPP_TR_THREADS, 0, s>>>(states, proofs, np, slot_z, slot_l, slot_r, order, count, plans, challenges, flags);
     return (int)cudaGetLastError();
 }
 int launch_test_poseidon(uint64_t* states, size_t count, cudaStream_t s) {
     int e = load_rc();
     if (e) return e;
-    k_test_poseidon<<<(unsigned)((count + 31) / 32), 32, 0, s>>>(states, count);
+    k_test_poseidon<<<(unsigned)((count * 16 + SIPP_TR_THREADS - 1) / SIPP_TR_THREADS), SIPP_TR_THREADS, 0, s>>>(states, count);
     return (int)cudaGetLastError();
 }
 

@@ -999,7 +999,9 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         }
         {
             Span sp(2, s);
-            int e = g_opt_fold_straus ? launch_fold_straus(b.dA, b.dB, m / 2, n, count, b.plans, s)
+            // one thread per element (shared doublings) when the launch fills the GPU; otherwise the lane-split components, whose
+            // dependent chain is 3x shorter when a warp spans several instances (divergent digit tests)
+            int e = (g_opt_fold_straus && count * (m / 2) >= 16384) ? launch_fold_straus(b.dA, b.dB, m / 2, n, count, b.plans, s)
                                       : launch_fold_batch(b.dA, b.dB, m / 2, n, count, b.plans, s);  // :60-74
             if (e) return cuda_fail((cudaError_t)e, "k_fold_batch");
             g_stats.launches++;

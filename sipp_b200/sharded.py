@@ -37,6 +37,14 @@ def shard_points(A: bytes, B: bytes, rank: int, world: int):
             b"".join(B[G2_BYTES * i:G2_BYTES * (i + 1)] for i in idx))
 
 
+def shard_instances(count: int, rank: int, world: int):
+    """Batched instances (BASELINE config 5) are independent: rank g proves the contiguous slice [lo, hi) of the instances
+    and no collective is needed.  Slices differ by at most one instance."""
+    base, extra = divmod(count, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
 class CudaEngine:
     """Engine over libsipp_b200.so.  Tensors are uint8 CUDA tensors; partials are in the library's device format."""
 
