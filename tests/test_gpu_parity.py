@@ -349,3 +349,29 @@ def test_roundtrip_property_large(sipp):
     assert len(proof) == 27
     assert sipp.inner_product(A, B) == proof[-1]
     sipp.sipp_verify_native(A, B, proof)
+
+
+def test_bls_aggregation_shape(sipp, oracle, golden):
+    """The demo's instance shape (bin/bls_aggregation.rs:95-122): 127 (pk_i, H(m_i)) pairs and (-G1, sigma_agg); the product of
+    a valid aggregate signature is 1, and that 128-pair statement proves and verifies.  pk_i = [a_i]G1 and H_i = [b_i]G2 come from
+    the seeded generator (the demo's hash-to-G2 lives in an un-vendored crate), sigma_agg = [sum a_i b_i]G2 is built on the GPU
+    with the fold kernel (B1 + s B2 with B1 = identity)."""
+    n = 127
+    A, B = sipp.seeded_inputs(21, n)
+    sc = oracle.seeded_scalars(21, n)                       # a_0, b_0, a_1, b_1, ...
+    ks = [int.from_bytes(sc[32 * i:32 * i + 32], "little") for i in range(2 * n)]
+    s = sum(ks[2 * i] * ks[2 * i + 1] for i in range(n)) % R
+    g2 = H(golden["pairing_gen"]["b"])
+    ctx = sipp.ProverContext(bytes(64) + le(1) + le(2), bytes(128) + g2)
+    ctx.fold(le(1), le(s))                                  # B' = identity + s G2  (x^-1 slot carries the scalar)
+    _, sigma = ctx.read()
+    assert sigma == oracle.g2_mul(g2, le(s))
+    neg_g1 = le(1) + le(P - 2)
+    A2, B2 = A + neg_g1, B + sigma
+    assert sipp.inner_product(A2, B2) == ONE12              # assert!(inner_product(&A, &B) == Fq12::one())  :119
+    proof = sipp.sipp_prove_native(A2, B2)                  # :120-122
+    st = sipp.sipp_verify_native(A2, B2, proof)
+    assert proof[-1] == ONE12 and st.Z == ONE12
+    assert b"".join(proof) == oracle.sipp_prove(A2, B2, threads=8)
+    # a forged aggregate (one message signed with the wrong key) is not the identity
+    assert sipp.inner_product(A2, B + oracle.g2_mul(g2, le((s + 1) % R))) != ONE12
