@@ -292,7 +292,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=0, help="total pairs (default 2^12 per GPU)")
+    ap.add_argument("--n", "--pairs", dest="n", type=int, default=0, help="total pairs (default 2^12 per GPU); under torchrun spell it --pairs")
+    ap.add_argument("--quick", action="store_true", help="large-n runs (n = 2^20): one warm-up step, no separate e2e leg (reported as null)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--saturated-pairs", type=int, default=1 << 17)
@@ -325,7 +326,7 @@ def main():
     n = args.n or PAIRS_PER_GPU * world
     lib = _lib.load()
     _lib.require_gpu_once()
-    W, K = max(args.warmup, 3), args.steps
+    W, K = (1 if args.quick else max(args.warmup, 3)), args.steps
     if args.workload == "batch":
         return run_batch(args, world, rank, local_rank, W, K)
 
@@ -411,9 +412,12 @@ def main():
         t_res, proof_res = timed(step_resident, K)
         st = sipp_b200.stats(reset=True)
         sipp_b200.set_option(_lib.OPT_PROFILE, 0)
-        for _ in range(W):
-            step_e2e()
-        t_e2e, proof_e2e = timed(step_e2e, K)
+        if args.quick:
+            t_e2e, proof_e2e = float("nan"), proof_res
+        else:
+            for _ in range(W):
+                step_e2e()
+            t_e2e, proof_e2e = timed(step_e2e, K)
     clk = clocks.summary()
 
     # ---- IMAD peak (microbenchmark, this GPU, this run) and the saturated Miller-kernel leg ----
@@ -467,7 +471,7 @@ def main():
     line = {"metric": "SIPP native prove throughput (pairings aggregated per second)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": t_res / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integer)", "data": "synthetic",
-            "config": {"workload": "SIPP native prover, n=2^%d pairs, %dxB200%s" % (log2(n), world, "" if world == 1 else " strided shards (2^12 pairs per GPU)"),
+            "config": {"workload": "SIPP native prover, n=2^%d pairs, %dxB200%s" % (log2(n), world, "" if world == 1 else " strided shards (2^%d pairs per GPU)" % log2(n // world)),
                        "n": n, "seed": 2, "miller_loops_per_step": miller_loops_per_prove(n), "l2": "flushed between steps (256 MB write)",
                        "fe_normalisation": "exact", "fq12_transcript_order": "w-basis"},
             "prove_s": t_res / K, "miller_loops_per_s_per_gpu": miller_loops_per_prove(n) * K / t_res / world,
@@ -491,7 +495,10 @@ def main():
                                           "%.1f s; GPU proof of the same sample is byte-identical" % (sample_n, n, dt),
                                 "all_cores_fast_variant": {"value": sample_n / dt_fast, "cores": os.cpu_count() or 1,
                                                            "note": "product of Miller loops + one final exponentiation, pthreads"}}
-    if world == 1 and args.batch_instances:
+    if args.quick:
+        line["e2e"] = None
+        line["config"]["quick"] = "one warm-up step, e2e leg skipped (--quick)"
+    if world == 1 and args.batch_instances and not args.quick:
         # BASELINE config 5 beside the headline (one timed step; `--workload batch` is the full bench of that config)
         bm = measure_batch(args.batch_instances, 128, 1, 0, local_rank, 1, 1, barrier, lambda dt: dt, l2_flush)
         bst = bm["stats"]
