@@ -11,6 +11,7 @@ struct PoseidonFastTables {
     alignas(64) uint64_t w16[22][16];      // w16[r][i] = w_r[i - 1] for i = 1..11, 0 elsewhere
     alignas(64) double mds_c0a[8];         // CIRC[0] + 8 in lane 0, CIRC[0] elsewhere
     double mds_circ[12];
+    alignas(64) uint64_t mds_ix[3][8];     // permutex2var indices: per 256-bit half, shift the pair (a, b) down by 1, 2, 3 elements
     uint64_t post[22];
     uint64_t init[11][11];
     uint64_t vhat[22][11];
