@@ -10,10 +10,11 @@
 //                  (sums < 2^43 are exact in double), the rotations built in registers (valignq / two-source permutes:
 //                  a store-and-reload of the state cannot be forwarded and cost 60 ns of the 119 ns round)
 //   partial rounds sparse form (tables derived in transcript.cc): the lane-0 S-box and the 11-term dot product run on the
-//                  scalar ports (mulx / adc, 192-bit lazy accumulation; the term that depends on this round's S-box
-//                  enters the sum last, so that the other eleven are off the dependent chain) while the rank-1 update
-//                  of lanes 1..11 runs on the vector ports
-// Measured on the GPU box's Xeon: 1.506 -> 1.385 (dot order) -> 1.223 us per permutation (register MDS).
+//                  scalar ports (mulx / adc, 192-bit lazy accumulation in two carry chains) while the rank-1 update of
+//                  lanes 1..11 runs on the vector ports.  The 11-term sum of round r reads the state of round r - 1 (one
+//                  extra product restores the missing rank-1 term) and the constant of the S-box output is folded in, so
+//                  the dependent chain of a round is the S-box, one multiply-add and one reduction.
+// Measured on the GPU box's Xeon: 1.506 -> 1.385 (dot order) -> 1.223 (register MDS) -> 1.18 us per permutation.
 #include <immintrin.h>
 #include <stdint.h>
 #include <string.h>
@@ -73,6 +74,43 @@ SIPP_AVX512 inline uint64_t s_dot11p(const uint64_t* a, const uint64_t* b, uint6
     uint64_t t = (uint64_t)top << 32;  // top <= 12
     uint64_t d = r - t;
     if (__builtin_expect(r < t, 0)) d -= EPS;  // borrowed 2^64 = EPS
+    return d;
+}
+
+
+// 192-bit lazy sum of 11 products in two independent carry chains (even / odd terms)
+struct Acc192 { unsigned long long lo, hi, top; };
+SIPP_AVX512 inline Acc192 s_dot11_raw(const uint64_t* a, const uint64_t* b) {
+    unsigned long long lo0 = 0, hi0 = 0, top0 = 0, lo1 = 0, hi1 = 0, top1 = 0, pl, ph;
+    unsigned char c;
+#pragma GCC unroll 6
+    for (int i = 0; i < 11; i += 2) {
+        pl = _mulx_u64(a[i], b[i], &ph);
+        c = _addcarry_u64(0, lo0, pl, &lo0);
+        c = _addcarry_u64(c, hi0, ph, &hi0);
+        top0 += c;
+        if (i + 1 < 11) {
+            pl = _mulx_u64(a[i + 1], b[i + 1], &ph);
+            c = _addcarry_u64(0, lo1, pl, &lo1);
+            c = _addcarry_u64(c, hi1, ph, &hi1);
+            top1 += c;
+        }
+    }
+    c = _addcarry_u64(0, lo0, lo1, &lo0);
+    c = _addcarry_u64(c, hi0, hi1, &hi0);
+    return Acc192{lo0, hi0, top0 + top1 + c};
+}
+SIPP_AVX512 inline void acc_mul(Acc192& s, uint64_t a, uint64_t b) {
+    unsigned long long ph, pl = _mulx_u64(a, b, &ph);
+    unsigned char c = _addcarry_u64(0, s.lo, pl, &s.lo);
+    c = _addcarry_u64(c, s.hi, ph, &s.hi);
+    s.top += c;
+}
+SIPP_AVX512 inline uint64_t acc_reduce(const Acc192& s) {
+    uint64_t r = s_red128(s.lo, s.hi);
+    uint64_t t = (uint64_t)s.top << 32;  // top <= 13; 2^128 = -2^32
+    uint64_t d = r - t;
+    if (__builtin_expect(r < t, 0)) d -= EPS;
     return d;
 }
 
@@ -143,7 +181,7 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     const __m512d le1 = _mm512_shuffle_f64x2(l1, l0, 0x44), le2 = _mm512_shuffle_f64x2(l0, l1, 0x4E);
     const __m512d he1 = _mm512_shuffle_f64x2(h1, h0, 0x44), he2 = _mm512_shuffle_f64x2(h0, h1, 0x4E);
     __m512d al0 = _mm512_mul_pd(l0, _mm512_load_pd(T.mds_c0a)), ah0 = _mm512_mul_pd(h0, _mm512_load_pd(T.mds_c0a));
-    __m512d al1, ah1;
+    __m512d al1, ah1, al2, ah2, al3, ah3;
 #define SIPP_MDS_A(I, ACCL, ACCH, FIRST)                                                              \
     {                                                                                                 \
         const __m512d c = _mm512_set1_pd(T.mds_circ[I]);                                              \
@@ -152,16 +190,16 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
         ACCH = FIRST ? _mm512_mul_pd(wh, c) : _mm512_fmadd_pd(wh, c, ACCH);                           \
     }
     SIPP_MDS_A(1, al1, ah1, true)
-    SIPP_MDS_A(2, al0, ah0, false)
-    SIPP_MDS_A(3, al1, ah1, false)
+    SIPP_MDS_A(2, al2, ah2, true)
+    SIPP_MDS_A(3, al3, ah3, true)
     SIPP_MDS_A(4, al0, ah0, false)
     SIPP_MDS_A(5, al1, ah1, false)
-    SIPP_MDS_A(6, al0, ah0, false)
-    SIPP_MDS_A(7, al1, ah1, false)
+    SIPP_MDS_A(6, al2, ah2, false)
+    SIPP_MDS_A(7, al3, ah3, false)
     SIPP_MDS_A(8, al0, ah0, false)
     SIPP_MDS_A(9, al1, ah1, false)
-    SIPP_MDS_A(10, al0, ah0, false)
-    SIPP_MDS_A(11, al1, ah1, false)
+    SIPP_MDS_A(10, al2, ah2, false)
+    SIPP_MDS_A(11, al3, ah3, false)
 #undef SIPP_MDS_A
     // rows 8..11: ring of half-vectors F2, F0, F1, F2, ... starting at s[8]
     const __m512d f0 = _mm512_shuffle_f64x2(l0, h0, 0x44), f1 = _mm512_shuffle_f64x2(l0, h0, 0xEE), f2 = _mm512_shuffle_f64x2(l1, h1, 0x44);
@@ -189,7 +227,8 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
         __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
         return _mm512_mask_add_epi64(r, c2, r, eps);
     };
-    s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(al0, al1)), _mm512_cvtpd_epu64(_mm512_add_pd(ah0, ah1)));
+    s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al0, al1), _mm512_add_pd(al2, al3))),
+                 _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah0, ah1), _mm512_add_pd(ah2, ah3))));
     const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(b0, b1));  // lanes 0..3: low sums, lanes 4..7: high sums of rows 8..11
     s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));              // lanes 4..7 of s1 are don't-care
 }
@@ -221,18 +260,35 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
         for (int i = 0; i < 11; i++) ub[i + 1] = s_dot11p(T.init[i], buf + 1, zero, zero);
         ub[0] = 0; ub[12] = ub[13] = ub[14] = ub[15] = 0;
     }
+    // d_r = vhat_r . U_r + m00 x_r with U_r = U_{r-1} + x_{r-1} w_{r-1}, so d_r = vhat_r . U_{r-1} + x_{r-1} (vhat_r . w_{r-1}) + m00 x_r:
+    // the 11-term sum reads the state of ONE ROUND EARLIER (in memory long before it is needed), and the dependent chain of a
+    // round is the S-box plus two multiply-adds.  Two buffers alternate: round r reads U_{r-1}, writes U_{r+1}.
+    alignas(64) uint64_t um[2][16];
+    memcpy(um[0], ub, sizeof ub);
     __m512i v0 = _mm512_load_si512(ub), v1 = _mm512_load_si512(ub + 8);
+    uint64_t x_prev = 0;
     for (int r = 0; r < 22; r++) {
-        uint64_t x = s_add(s_pow7(u0), T.post[r]);
-        // d = m00 x + vhat . u ; u <- u + x w
-        uint64_t d = s_dot11p(T.vhat[r], ub + 1, x, T.m00);
+        Acc192 acc = s_dot11_raw(T.vhat[r], um[r == 0 ? 0 : (r + 1) & 1] + 1);
+        acc_mul(acc, x_prev, T.kprev[r]);
+        {   // + m00 post[r] (constant), off the chain
+            unsigned char c = _addcarry_u64(0, acc.lo, T.mpost[r], &acc.lo);
+            c = _addcarry_u64(c, acc.hi, 0, &acc.hi);
+            acc.top += c;
+        }
+        const uint64_t p7 = s_pow7(u0);
+        uint64_t x = s_add(p7, T.post[r]);
+        acc_mul(acc, p7, T.m00);
+        uint64_t d = acc_reduce(acc);
         __m512i xb = _mm512_set1_epi64((long long)x);
         v0 = v_add_canon(v0, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r]))));
         v1 = v_add_canon(v1, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r] + 8))));
-        _mm512_store_si512(ub, v0);
-        _mm512_store_si512(ub + 8, v1);
+        _mm512_store_si512(um[(r + 1) & 1], v0);
+        _mm512_store_si512(um[(r + 1) & 1] + 8, v1);
+        x_prev = x;
         u0 = d;
     }
+    _mm512_store_si512(ub, v0);
+    _mm512_store_si512(ub + 8, v1);
     ub[0] = u0;
     s0 = _mm512_load_si512(ub);
     s1 = _mm512_load_si512(ub + 8);

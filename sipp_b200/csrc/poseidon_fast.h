@@ -13,6 +13,8 @@ struct PoseidonFastTables {
     double mds_circ[12];
     alignas(64) uint64_t mds_ix[3][8];     // permutex2var indices: per 256-bit half, shift the pair (a, b) down by 1, 2, 3 elements
     uint64_t post[22];
+    uint64_t mpost[22];
+    uint64_t kprev[22];                    // kprev[r] = vhat[r] . w[r-1] (0 for r = 0)
     uint64_t init[11][11];
     uint64_t vhat[22][11];
     uint64_t m00;

@@ -195,6 +195,9 @@ struct FastPartialInit {
         for (int i = 0; i < 12; i++) g_tab.first[i] = g_fp.first[i];
         for (int r = 0; r < 22; r++) {
             g_tab.post[r] = g_fp.post[r];
+            g_tab.mpost[r] = gl_canon(gl_mul(g_fp.m00, g_fp.post[r]));
+            g_tab.kprev[r] = 0;
+            for (int i = 0; r > 0 && i < 11; i++) g_tab.kprev[r] = gl_canon(gl_add(g_tab.kprev[r], gl_mul(g_fp.vhat[r][i], g_fp.w[r - 1][i])));
             for (int i = 0; i < 11; i++) { g_tab.w16[r][i + 1] = g_fp.w[r][i]; g_tab.vhat[r][i] = g_fp.vhat[r][i]; }
         }
         for (int i = 0; i < 11; i++)
