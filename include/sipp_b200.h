@@ -137,6 +137,12 @@ int sipp_verify_native(const uint8_t *A, size_t a_len, const uint8_t *B, size_t 
  * (transcript_native.rs:14-66) ON THE DEVICE, so nothing crosses PCIe between the upload and the proofs.  Instances are
  * independent: a multi-GPU host gives each rank its own slice of instances, no collective. */
 int sipp_prove_native_batch(const uint8_t *A, const uint8_t *B, size_t n, size_t count, uint8_t *proofs);
+/* `count` verifications in lock-step (verifier_native.rs:14-85 per instance): results[j] = SIPP_OK for Ok(statement),
+ * SIPP_ERR_VERIFY for Err("Verification failed"); every instance's proof is proof_len x 384 B (>= sipp_proof_len(n), read
+ * from its end like the reference's pop()).  final_A (count x 64 B), final_B (count x 128 B), final_Z (count x 384 B) receive
+ * the computed statement members when non-NULL.  The return value reports whether the batch ran, not whether proofs verified. */
+int sipp_verify_native_batch(const uint8_t *A, const uint8_t *B, size_t n, size_t count, const uint8_t *proofs, size_t proof_len,
+                             int *results, uint8_t *final_A, uint8_t *final_B, uint8_t *final_Z);
 /* same with DEVICE buffers in boundary format (inputs resident in HBM, proofs left in HBM) */
 int sipp_prove_native_batch_device(const void *dA, const void *dB, size_t n, size_t count, void *d_proofs);
 

@@ -152,6 +152,35 @@ def sipp_prove_native_batch(A: Points, B: Points, n: int) -> List[List[bytes]]:
     return [_split(raw[j * plen * FQ12_BYTES:(j + 1) * plen * FQ12_BYTES], FQ12_BYTES) for j in range(count)]
 
 
+def sipp_verify_native_batch(A: Points, B: Points, n: int, proofs: Sequence[Sequence[bytes]]) -> List[Union[SIPPStatement, VerificationError]]:
+    """`count` independent verifications in lock-step (verifier_native.rs:14-85 per instance).  Returns, per instance, the
+    SIPPStatement (Ok) or a VerificationError instance (Err) -- a failed instance does not abort the others."""
+    a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)
+    na, nb = len(a) // G1_BYTES, len(b) // G2_BYTES
+    assert na == nb, "assert_eq!(A.len(), B.len())"
+    if n <= 0 or na % n or na // n != len(proofs):
+        raise ValueError("%d pairs / instance size %d does not match %d proofs" % (na, n, len(proofs)))
+    count = na // n
+    plen = len(proofs[0])
+    if any(len(p) != plen for p in proofs):
+        raise ValueError("all proofs of a batch must have the same length")
+    p = b"".join(_flat(pr, FQ12_BYTES) for pr in proofs)
+    _lib.require_gpu_once()
+    res = (ctypes.c_int * count)()
+    fa, fb, fz = (ctypes.create_string_buffer(s * count) for s in (G1_BYTES, G2_BYTES, FQ12_BYTES))
+    _lib.check(_lib.load().sipp_verify_native_batch(a, b, n, count, p, plen, res, fa, fb, fz))
+    out = []
+    for j in range(count):
+        if res[j] == _lib.ERR_VERIFY:
+            out.append(VerificationError("Verification failed"))
+        else:
+            out.append(SIPPStatement(A=_split(a[G1_BYTES * n * j:G1_BYTES * n * (j + 1)], G1_BYTES),
+                                     B=_split(b[G2_BYTES * n * j:G2_BYTES * n * (j + 1)], G2_BYTES), Z=bytes(proofs[j][-1]),
+                                     final_A=fa.raw[G1_BYTES * j:G1_BYTES * (j + 1)], final_B=fb.raw[G2_BYTES * j:G2_BYTES * (j + 1)],
+                                     final_Z=fz.raw[FQ12_BYTES * j:FQ12_BYTES * (j + 1)]))
+    return out
+
+
 def sipp_verify_native(A: Points, B: Points, proof: Sequence[bytes]) -> SIPPStatement:
     """verifier_native.rs:14-85; returns the SIPPStatement or raises VerificationError."""
     a, b = _flat(A, G1_BYTES), _flat(B, G2_BYTES)

@@ -20,7 +20,9 @@ namespace sipp {
 
 #define SIPP_LINE_WORDS 80                               // 5 Fq2
 #define SIPP_PAIR_LINE_WORDS (SIPP_LINES_PER_PAIR * SIPP_LINE_WORDS)
+#ifndef SIPP_ACCUM_THREADS
 #define SIPP_ACCUM_THREADS 128
+#endif
 #define SIPP_GROUPS_PER_WARP 5
 #define SIPP_ACCUM_GROUPS (SIPP_ACCUM_THREADS / 32 * SIPP_GROUPS_PER_WARP)
 
@@ -238,6 +240,43 @@ __global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_fe_batch(const uint32_t*
     }
 }
 
+// Batched verifier GT update (verifier_native.rs:59-61): Z <- Z_L^x * Z * Z_R^(x^-1) for every instance, 6 lanes per power
+// (two groups per instance, both in the same block).  Generic square-and-multiply over the 254 bits of the exponent -- proof
+// elements need not lie in the cyclotomic subgroup, and the reference's `pow` does not assume it -- with the multiplication
+// computed at every bit and selected (groups of one warp hold different exponents).  proofs: [count][stride][96] boundary
+// bytes; challenges: [count][8] u64 = x || x^-1; z: [count][96] boundary bytes, updated in place.
+__global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_gt_fold_batch(const uint32_t* __restrict__ proofs, size_t stride, int slot_l, int slot_r,
+                                                                    const uint64_t* __restrict__ challenges, uint32_t* __restrict__ z, size_t count) {
+    __shared__ __align__(16) uint32_t xch[SIPP_ACCUM_GROUPS * 96];
+    const Lane6 L = lane6_of_thread();
+    const int warp = threadIdx.x >> 5;
+    const bool active_lane = L.k < 6;
+    const int group = warp * SIPP_GROUPS_PER_WARP + (active_lane ? L.base / 6 : 0);
+    const int k = active_lane ? L.k : 0;
+    size_t g = (size_t)blockIdx.x * SIPP_ACCUM_GROUPS + group;
+    const bool have = active_lane && g < 2 * count;
+    if (g >= 2 * count) g = 2 * count - 1;
+    const size_t inst = g >> 1;
+    const int which = (int)(g & 1);
+    const int slot = (k & 1) * 3 + (k >> 1);
+    const Fq2 base = fq2_decode(proofs + (inst * stride + (size_t)(which ? slot_r : slot_l)) * 96 + 16 * slot);
+    const uint64_t* e = challenges + 8 * inst + 4 * which;
+    Fq2 acc = lane_one(k);
+#pragma unroll 1
+    for (int i = 253; i >= 0; i--) {
+        acc = coop_sqr(L, acc);
+        const Fq2 m = coop_mul(L, acc, base);
+        acc = select_fq2(((e[i >> 6] >> (i & 63)) & 1ull) != 0, m, acc);
+    }
+    if (have && which == 1) store_fq2_words(xch + group * 96 + k * 16, acc);
+    __syncthreads();
+    // group of Z_L (even g; its partner g + 1 is the next group of the same block: 20 groups per block)
+    const Fq2 zr_pow = load_fq2_words(xch + (which == 0 && group + 1 < SIPP_ACCUM_GROUPS ? group + 1 : group) * 96 + k * 16);
+    const Fq2 zc = fq2_decode(z + inst * 96 + 16 * slot);
+    const Fq2 r = coop_mul(L, coop_mul(L, acc, zc), zr_pow);
+    if (have && which == 0) fq2_encode(z + inst * 96 + 16 * slot, r);
+}
+
 // ------------------------------------------------------------------------------------------------ test hook
 // op: 0 mul, 1 sqr (via mul), 2 inv, 3..5 frobenius, 6 conj, 7 cyclotomic sqr, 8 cyclotomic ^x, 9 final exponentiation
 __global__ void __launch_bounds__(32) k_test_coop_op(int op, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out,
@@ -305,6 +344,13 @@ int launch_fe_batch(const uint32_t* partials, size_t nproducts, int gpp, int npr
                     cudaStream_t s) {
     k_fe_batch<<<(unsigned)((nproducts + SIPP_ACCUM_GROUPS - 1) / SIPP_ACCUM_GROUPS), SIPP_ACCUM_THREADS, 0, s>>>(partials, nproducts, gpp, nprod, out, out_stride,
                                                                                                                 slot0, slot1, ark_norm);
+    return (int)cudaGetLastError();
+}
+int launch_gt_fold_batch(const uint32_t* proofs, size_t stride, int slot_l, int slot_r, const uint64_t* challenges, uint32_t* z, size_t count,
+                         cudaStream_t s) {
+    size_t groups = 2 * count;
+    k_gt_fold_batch<<<(unsigned)((groups + SIPP_ACCUM_GROUPS - 1) / SIPP_ACCUM_GROUPS), SIPP_ACCUM_THREADS, 0, s>>>(proofs, stride, slot_l, slot_r, challenges,
+                                                                                                                   z, count);
     return (int)cudaGetLastError();
 }
 size_t lines_bytes_per_pair() { return (size_t)SIPP_PAIR_LINE_WORDS * sizeof(uint32_t); }

@@ -900,7 +900,7 @@ size_t pow2_floor(size_t v) {
 }
 
 // products of the current round of every instance: which = 0 -> Z (slot0), which = 1 -> Z_L (slot0), Z_R (slot1)
-int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m, int which, size_t np, int slot0, int slot1, cudaStream_t s) {
+int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m, int which, uint32_t* fe_out, size_t np, int slot0, int slot1, cudaStream_t s) {
     BatchJob job;
     job.stride = stride;
     if (which == 0) {
@@ -948,7 +948,7 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
     g_stats.miller_pairs += nproducts * job.h;
     {
         Span sp(1, s);
-        int e = launch_fe_batch(b.partials, nproducts, (int)gpp, job.nprod, b.proofs, np * 96, slot0, slot1, g_opt_fe_norm, s);
+        int e = launch_fe_batch(b.partials, nproducts, (int)gpp, job.nprod, fe_out, np * 96, slot0, slot1, g_opt_fe_norm, s);
         if (e) return cuda_fail((cudaError_t)e, "k_fe_batch");
     }
     g_stats.launches++;
@@ -981,13 +981,13 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         if (e) return cuda_fail((cudaError_t)e, "k_tr_absorb_pairs");
         g_stats.launches++;
     }
-    int rc = batch_products(b, n, count, n, 0, np, (int)np - 1, 0, s);        // let Z = inner_product(A, B);  :29 (pushed first, last after reverse)
+    int rc = batch_products(b, n, count, n, 0, b.proofs, np, (int)np - 1, 0, s);        // let Z = inner_product(A, B);  :29 (pushed first, last after reverse)
     if (rc) return rc;
     size_t m = n;
     int round = 1;
     while (m > 1) {                                                            // :45
         const int slot_l = (int)np - 2 * round, slot_r = (int)np - 1 - 2 * round;  // proof.reverse()  :78
-        rc = batch_products(b, n, count, m, 1, np, slot_l, slot_r, s);         // :46-49
+        rc = batch_products(b, n, count, m, 1, b.proofs, np, slot_l, slot_r, s);         // :46-49
         if (rc) return rc;
         if (round == 1) CK(order_after(s, side));
         {
@@ -1096,6 +1096,95 @@ int sipp_prove_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_t
     else cudaStreamSynchronize(g_stream);
     b.release();
     return rc;
+}
+
+// `count` independent verifications in lock-step (verifier_native.rs:14-85 per instance): the transcript replay, the folds and the
+// GT update Z_L^x Z Z_R^(x^-1) of every instance run in the same launches; the final pairing check (:80) is one batched
+// product of one pair per instance.  results[j] = SIPP_OK / SIPP_ERR_VERIFY.
+int sipp_verify_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_t count, const uint8_t* proofs, size_t proof_len, int* results,
+                             uint8_t* final_A, uint8_t* final_B, uint8_t* final_Z) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!results) return fail(SIPP_ERR_ARG, "null results");
+    rc = batch_args(A, B, n, count, proofs);
+    if (rc) return rc;
+    const size_t np = sipp_proof_len(n);
+    if (proof_len < np) return fail(SIPP_ERR_SHORT_PROOF, "proof.pop().unwrap() on an empty proof");  // verifier_native.rs:31,40,42
+    const size_t total = n * count, top = proof_len;  // the verifier pops from the end: Z = proof[top - 1]
+    cudaStream_t s = g_stream;
+    BatchBuffers b;
+    uint32_t *dproofs = nullptr, *dz = nullptr, *dpair = nullptr, *dfin = nullptr;
+    uint64_t* dchal = nullptr;
+    cudaError_t e = pool_alloc((void**)&b.bytesA, total * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.bytesB, total * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.dA, total * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.dB, total * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.partials, count * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.states, count * 32);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.plans, count * sizeof(FoldPlan));
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.flags, 2 * sizeof(int));
+    if (e == cudaSuccess) e = pool_alloc((void**)&dproofs, count * proof_len * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dz, count * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dpair, count * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dfin, count * 192);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dchal, count * 64);
+    auto release = [&]() {
+        b.release();
+        pool_free(dproofs); pool_free(dz); pool_free(dpair); pool_free(dfin); pool_free(dchal);
+    };
+    if (e != cudaSuccess) { release(); return cuda_fail(e, "cudaMalloc(verify batch)"); }
+    std::vector<uint8_t> hz(count * 384), hp(count * 384);
+    auto run = [&]() -> int {
+        CK(cudaMemcpyAsync(b.bytesA, A, total * 64, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b.bytesB, B, total * 128, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dproofs, proofs, count * proof_len * 384, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), s));
+        int le = launch_codec_decode(b.bytesA, b.dA, total * 2, b.flags + 1, s);
+        if (!le) le = launch_codec_decode(b.bytesB, b.dB, total * 4, b.flags + 1, s);
+        if (!le) le = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, s);                 // :25-28
+        if (le) return cuda_fail((cudaError_t)le, "verify batch: decode / absorb");
+        g_stats.launches += 3;
+        // let original_Z = proof.pop().unwrap();  :31   (Z of instance j = its last Fq12)
+        CK(cudaMemcpy2DAsync(dz, 384, (const uint8_t*)dproofs + (top - 1) * 384, proof_len * 384, 384, count, cudaMemcpyDeviceToDevice, s));
+        size_t m = n;
+        int round = 1;
+        while (m > 1) {                                                                                     // :35
+            const int slot_l = (int)top - 2 * round, slot_r = (int)top - 1 - 2 * round;                     // :40, :42
+            le = launch_tr_round(b.states, dproofs, proof_len, round == 1 ? (int)top - 1 : -1, slot_l, slot_r, g_opt_fq12_order, count, b.plans,
+                                 dchal, b.flags, s);                                                         // :33 (first round), :41-46
+            if (!le) le = (g_opt_fold_straus && count * (m / 2) >= 16384) ? launch_fold_straus(b.dA, b.dB, m / 2, n, count, b.plans, s)
+                                                                             : launch_fold_batch(b.dA, b.dB, m / 2, n, count, b.plans, s);  // :48-57
+            if (!le) le = launch_gt_fold_batch(dproofs, proof_len, slot_l, slot_r, dchal, dz, count, s);  // :59-61
+            if (le) return cuda_fail((cudaError_t)le, "verify batch: round");
+            g_stats.launches += 3;
+            g_stats.fold_points += count * (m / 2);
+            m /= 2;
+            round++;
+        }
+        // pairing(final_A, final_B) == final_Z   :80   (final_A = A[0], final_B = B[0] of every instance  :74-75)
+        int rc2 = batch_products(b, n, count, 1, 0, dpair, 1, 0, 0, s);
+        if (rc2) return rc2;
+        if (final_A || final_B) {
+            CK(cudaMemcpy2DAsync(b.bytesA, 64, b.dA, n * 64, 64, count, cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpy2DAsync(b.bytesB, 128, b.dB, n * 128, 128, count, cudaMemcpyDeviceToDevice, s));
+            le = launch_codec_encode(b.bytesA, dfin, count * 2, s);
+            if (!le) le = launch_codec_encode(b.bytesB, dfin + count * 16, count * 4, s);
+            if (le) return cuda_fail((cudaError_t)le, "verify batch: encode");
+            g_stats.launches += 2;
+            if (final_A) CK(cudaMemcpyAsync(final_A, dfin, count * 64, cudaMemcpyDeviceToHost, s));
+            if (final_B) CK(cudaMemcpyAsync(final_B, dfin + count * 16, count * 128, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaMemcpyAsync(hz.data(), dz, count * 384, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hp.data(), dpair, count * 384, cudaMemcpyDeviceToHost, s));
+        return batch_check_flags(b, s);
+    };
+    rc = run();
+    if (rc) cudaStreamSynchronize(s);
+    release();
+    if (rc) return rc;
+    for (size_t j = 0; j < count; j++) results[j] = memcmp(&hz[384 * j], &hp[384 * j], 384) == 0 ? SIPP_OK : SIPP_ERR_VERIFY;  // :81-84
+    if (final_Z) memcpy(final_Z, hz.data(), count * 384);
+    return SIPP_OK;
 }
 
 // `count` independent Poseidon permutations on the device (test hook for k_transcript.cu)

@@ -155,3 +155,39 @@ def test_batch_config5_sample(sipp, oracle):
         a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
         assert proofs[j][-1] == sipp.inner_product(a, b)
         sipp.sipp_verify_native(a, b, proofs[j])
+
+
+def test_verify_batch(sipp, oracle):
+    """batched verifier (verifier_native.rs:14-85 per instance): statements equal the single-instance verifier's and the oracle's;
+    a tampered proof / a wrong statement fails alone"""
+    n, count = 16, 7
+    A, B = oracle.seeded_inputs(91, n * count, threads=8)
+    proofs = sipp.sipp_prove_native_batch(A, B, n)
+    sts = sipp.sipp_verify_native_batch(A, B, n, proofs)
+    for j in range(count):
+        a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
+        one = sipp.sipp_verify_native(a, b, proofs[j])
+        assert not isinstance(sts[j], Exception), j
+        assert (sts[j].final_A, sts[j].final_B, sts[j].final_Z, sts[j].Z) == (one.final_A, one.final_B, one.final_Z, one.Z), j
+        if j < 2:
+            ok, ost = oracle.sipp_verify(a, b, b"".join(proofs[j]), threads=4)
+            assert ok and sts[j].final_A == ost["final_A"] and sts[j].final_B == ost["final_B"] and sts[j].final_Z == ost["final_Z"]
+    bad = [list(p) for p in proofs]
+    t = bytearray(bad[3][2]); t[100] ^= 4; bad[3][2] = bytes(t)          # a Z_L / Z_R of instance 3
+    t = bytearray(bad[5][-1]); t[0] ^= 1; bad[5][-1] = bytes(t)          # Z of instance 5
+    A2 = bytearray(A); A2[64 * n * 1:64 * n * 1 + 64] = A[64 * n * 2:64 * n * 2 + 64]   # instance 1 proves another statement
+    sts = sipp.sipp_verify_native_batch(bytes(A2), B, n, bad)
+    assert [isinstance(s, sipp.VerificationError) for s in sts] == [False, True, False, True, False, True, False]
+    with pytest.raises(sipp.SippError) as ei:
+        sipp.sipp_verify_native_batch(A, B, n, [p[:-2] for p in proofs])  # proof.pop().unwrap() on a short proof
+    assert ei.value.code == -5
+
+
+def test_verify_batch_n128(sipp):
+    """config-5 shape: every proof of a 64 x n = 128 batch verifies on the GPU, in lock-step"""
+    n, count = 128, 64
+    A, B = sipp.seeded_inputs(6, n * count)
+    proofs = sipp.sipp_prove_native_batch(A, B, n)
+    sts = sipp.sipp_verify_native_batch(A, B, n, proofs)
+    assert all(not isinstance(s, Exception) for s in sts)
+    assert all(s.final_Z != s.Z for s in sts)
