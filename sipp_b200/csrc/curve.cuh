@@ -13,8 +13,13 @@ namespace sipp {
 // field-generic helpers (overloads pick Fq or Fq2)
 SIPP_HD Fq f_add(const Fq& a, const Fq& b) { return fq_add(a, b); }
 SIPP_HD Fq f_sub(const Fq& a, const Fq& b) { return fq_sub(a, b); }
+#if defined(SIPP_FQ_CALLS)
+SIPP_HD Fq f_mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+SIPP_HD Fq f_sqr(const Fq& a) { return fq_mul_call(a, a); }
+#else
 SIPP_HD Fq f_mul(const Fq& a, const Fq& b) { return fq_mul(a, b); }
 SIPP_HD Fq f_sqr(const Fq& a) { return fq_sqr(a); }
+#endif
 SIPP_HD Fq f_dbl(const Fq& a) { return fq_dbl(a); }
 SIPP_HD Fq f_neg(const Fq& a) { return fq_neg(a); }
 SIPP_HD Fq f_inv(const Fq& a) { return fq_inv(a); }

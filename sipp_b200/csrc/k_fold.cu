@@ -2,6 +2,7 @@
 // Fq2 products are real calls: fully inlined the scalar-multiplication loops are 45-65k SASS instructions, several times the
 // instruction cache.
 #define SIPP_CURVE_FQ2_CALLS 1
+#define SIPP_FQ_CALLS 1
 #include "coop.cuh"
 #include "device_common.cuh"
 #include "fold_plan.h"

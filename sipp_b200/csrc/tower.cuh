@@ -75,8 +75,25 @@ SIPP_HD Fq2 fq2_sqr_inl(const Fq2& a) {  // (a0+a1)(a0-a1), 2 a0 a1
     Fq r0 = fq_mul(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
     return Fq2{r0, fq_dbl(m)};
 }
+#if defined(SIPP_FQ_CALLS)
+// smallest code: one out-of-line Fq multiplier shared by every product of the translation unit (the scalar-multiplication loops of
+// k_fold.cu stalled on instruction fetch even with Fq2 products as calls: ncu no_instruction 3.9 per issued instruction)
+SIPP_HD_NOINLINE Fq fq_mul_call(const Fq& a, const Fq& b) { return fq_mul(a, b); }
+SIPP_FQ2_CALL Fq2 fq2_mul(const Fq2& a, const Fq2& b) {
+    Fq v0 = fq_mul_call(a.c0, b.c0);
+    Fq v1 = fq_mul_call(a.c1, b.c1);
+    Fq s = fq_mul_call(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+    return Fq2{fq_sub(v0, v1), fq_sub(fq_sub(s, v0), v1)};
+}
+SIPP_FQ2_CALL Fq2 fq2_sqr(const Fq2& a) {
+    Fq m = fq_mul_call(a.c0, a.c1);
+    Fq r0 = fq_mul_call(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+    return Fq2{r0, fq_dbl(m)};
+}
+#else
 SIPP_FQ2_CALL Fq2 fq2_mul(const Fq2& a, const Fq2& b) { return fq2_mul_inl(a, b); }
 SIPP_FQ2_CALL Fq2 fq2_sqr(const Fq2& a) { return fq2_sqr_inl(a); }
+#endif
 
 SIPP_HD Fq2 fq2_mul_xi(const Fq2& a) {  // (9+u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
     Fq2 t = fq2_dbl(fq2_dbl(fq2_dbl(a)));
