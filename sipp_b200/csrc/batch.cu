@@ -1,0 +1,377 @@
+// batch.cu -- batched instances: `count` independent SIPP instances proved (and verified) in lock-step (C ABI: sipp_prove_native_batch,
+// sipp_prove_native_batch_device, sipp_verify_native_batch; BASELINE config "4096 independent n=128 SIPP instances").
+//
+// `count` independent SIPP instances of n pairs each, proved in lock-step: round k of every instance runs in the same launches
+// (BASELINE config "4096 independent n=128 SIPP instances").  Each instance is exactly sipp_prove_native (prover_native.rs:26-80);
+// what changes is where the glue runs: one transcript chain per instance on the device (k_transcript.cu), per-instance fold
+// plans, segmented products.  Nothing returns to the host between the upload and the proofs.
+#include <string.h>
+
+#include <vector>
+
+#include "host_state.h"
+
+using namespace sipp;
+using namespace sipp_host;
+
+namespace {
+
+struct BatchBuffers {
+    uint32_t *bytesA = nullptr, *bytesB = nullptr;  // boundary bytes (the transcript reads canonical limbs)
+    uint32_t *dA = nullptr, *dB = nullptr;          // Montgomery
+    uint32_t* proofs = nullptr;                     // [count][np][96]
+    uint32_t* partials = nullptr;
+    uint64_t* states = nullptr;
+    FoldPlan* plans = nullptr;
+    int* flags = nullptr;                           // [0] transcript / recoding, [1] encoding
+    void release() {
+        pool_free(bytesA); pool_free(bytesB); pool_free(dA); pool_free(dB); pool_free(proofs); pool_free(partials);
+        pool_free(states); pool_free(plans); pool_free(flags);
+    }
+};
+
+size_t pow2_floor(size_t v) {
+    size_t r = 1;
+    while (r * 2 <= v) r *= 2;
+    return r;
+}
+
+// products of the current round of every instance: which = 0 -> Z (slot0), which = 1 -> Z_L (slot0), Z_R (slot1)
+int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m, int which, uint32_t* fe_out, size_t np, int slot0, int slot1, cudaStream_t s) {
+    BatchJob job;
+    job.stride = stride;
+    if (which == 0) {
+        job.nprod = 1; job.h = m;
+        job.a_off[0] = job.b_off[0] = job.a_off[1] = job.b_off[1] = 0;
+    } else {
+        job.nprod = 2; job.h = m / 2;
+        job.a_off[0] = job.h; job.b_off[0] = 0;   // Z_L = inner_product(A2, B1)   prover_native.rs:48
+        job.a_off[1] = 0; job.b_off[1] = job.h;   // Z_R = inner_product(A1, B2)   prover_native.rs:49
+    }
+    const size_t nproducts = count * (size_t)job.nprod;
+    const size_t per_pair = lines_bytes_per_pair();
+    const size_t cap_bytes = (size_t)16 << 30;
+    size_t pc = cap_bytes / (job.h * per_pair);  // products per chunk (whole products only)
+    if (pc < 1) return fail(SIPP_ERR_ARG, "batched instances: one product exceeds the line buffer (use sipp_prove_native for large n)");
+    if (pc > nproducts) pc = nproducts;
+    // accumulator groups: kpg pairs of ONE product share an accumulator and its 64 squarings (5,070 Fq-mul-eq per group, 3,661
+    // per pair).  The GPU holds 2 blocks x 20 groups per SM at a time; pick the power of two that minimises waves x group length.
+    size_t kpg = 1;
+    {
+        const size_t wave = (size_t)g_sm_count * 40;
+        double best = 0;
+        for (size_t cand = 1; cand <= job.h && cand <= (size_t)g_opt_batch_kpg_max; cand *= 2) {
+            if (job.h % cand) break;  // h is a power of two in a proof; any h still works with kpg = 1
+            size_t groups = pc * job.h / cand;
+            double cost = (double)((groups + wave - 1) / wave) * (5070.0 + 3661.0 * (double)cand);
+            if (best == 0 || cost < best) { best = cost; kpg = cand; }
+        }
+    }
+    const size_t gpp = job.h / kpg;
+    int rc = lines_reserve(pc * job.h * per_pair);
+    if (rc) return rc;
+    {
+        Span sp(0, s);
+        for (size_t p0 = 0; p0 < nproducts; p0 += pc) {
+            size_t cur = nproducts - p0 < pc ? nproducts - p0 : pc;
+            int e = launch_lines_batch(b.dA, b.dB, job, p0, cur, lines_buffer(), s);
+            if (e) return cuda_fail((cudaError_t)e, "k_lines_batch");
+            e = launch_accum_batch(lines_buffer(), cur * job.h, (int)kpg, b.partials, p0 * gpp, s);
+            if (e) return cuda_fail((cudaError_t)e, "k_accum(batch)");
+            g_stats.launches += 2;
+            g_stats.miller_launches++;
+        }
+    }
+    g_stats.miller_pairs += nproducts * job.h;
+    {
+        Span sp(1, s);
+        int e = launch_fe_batch(b.partials, nproducts, (int)gpp, job.nprod, fe_out, np * 96, slot0, slot1, g_opt_fe_norm, s);
+        if (e) return cuda_fail((cudaError_t)e, "k_fe_batch");
+    }
+    g_stats.launches++;
+    return SIPP_OK;
+}
+
+// the whole batch on the device; bytesA / bytesB already hold the boundary bytes.  Enqueues everything, synchronises once.
+int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s) {
+    const size_t np = sipp_proof_len(n), total = n * count;
+    CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), s));
+    {
+        Span sp(3, s);
+        int e = launch_codec_decode(b.bytesA, b.dA, total * 2, b.flags + 1, s);
+        if (!e) e = launch_codec_decode(b.bytesB, b.dB, total * 4, b.flags + 1, s);
+        if (e) return cuda_fail((cudaError_t)e, "k_codec_decode");
+        g_stats.launches += 2;
+    }
+    // register A and B (prover_native.rs:36-39): independent of everything the products compute, so the chains run on a side
+    // stream next to Z and the first Z_L, Z_R
+    static cudaStream_t side = nullptr;
+    static int side_dev = -1;
+    if (side_dev != g_device) {
+        CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        side_dev = g_device;
+    }
+    CK(order_after(side, s));
+    {
+        Span sp(3, side);
+        int e = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, side);
+        if (e) return cuda_fail((cudaError_t)e, "k_tr_absorb_pairs");
+        g_stats.launches++;
+    }
+    int rc = batch_products(b, n, count, n, 0, b.proofs, np, (int)np - 1, 0, s);        // let Z = inner_product(A, B);  :29 (pushed first, last after reverse)
+    if (rc) return rc;
+    size_t m = n;
+    int round = 1;
+    while (m > 1) {                                                            // :45
+        const int slot_l = (int)np - 2 * round, slot_r = (int)np - 1 - 2 * round;  // proof.reverse()  :78
+        rc = batch_products(b, n, count, m, 1, b.proofs, np, slot_l, slot_r, s);         // :46-49
+        if (rc) return rc;
+        if (round == 1) CK(order_after(s, side));
+        {
+            Span sp(3, s);
+            int e = launch_tr_round(b.states, b.proofs, np, round == 1 ? (int)np - 1 : -1, slot_l, slot_r, g_opt_fq12_order, count, b.plans, nullptr,
+                                    b.flags, s);                               // :42-43 (first round), :52-58
+            if (e) return cuda_fail((cudaError_t)e, "k_tr_round");
+            g_stats.launches++;
+        }
+        {
+            Span sp(2, s);
+            // one thread per element (shared doublings) when the launch fills the GPU; otherwise the lane-split components, whose
+            // dependent chain is 3x shorter when a warp spans several instances (divergent digit tests)
+            int e = (g_opt_fold_straus && count * (m / 2) >= 16384) ? launch_fold_straus(b.dA, b.dB, m / 2, n, count, b.plans, s)
+                                      : launch_fold_batch(b.dA, b.dB, m / 2, n, count, b.plans, s);  // :60-74
+            if (e) return cuda_fail((cudaError_t)e, "k_fold_batch");
+            g_stats.launches++;
+            g_stats.fold_points += count * (m / 2);
+        }
+        m /= 2;
+        round++;
+    }
+    return SIPP_OK;
+}
+
+int batch_alloc(BatchBuffers& b, size_t n, size_t count) {
+    const size_t np = sipp_proof_len(n), total = n * count;
+    // worst case one accumulator group per pair
+    cudaError_t e = pool_alloc((void**)&b.bytesA, total * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.bytesB, total * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.dA, total * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.dB, total * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.proofs, count * np * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.partials, total * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.states, count * 32);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.plans, count * sizeof(FoldPlan));
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.flags, 2 * sizeof(int));
+    if (e != cudaSuccess) {
+        b.release();
+        return cuda_fail(e, "cudaMalloc(batch)");
+    }
+    return SIPP_OK;
+}
+
+int batch_check_flags(const BatchBuffers& b, cudaStream_t s) {
+    int flags[2] = {0, 0};
+    CK(cudaMemcpyAsync(flags, b.flags, sizeof flags, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (flags[1]) return fail(SIPP_ERR_ENCODING, "input coordinate >= p");
+    if (flags[0] & 1) return fail(SIPP_ERR_ZERO_CHALLENGE, "challenge is zero: x.inverse().unwrap() panics in the reference");
+    if (flags[0] & 2) return fail(SIPP_ERR_ENCODING, "fold scalar recoding failed");
+    return SIPP_OK;
+}
+
+int batch_args(const void* A, const void* B, size_t n, size_t count, const void* proofs) {
+    if (!A || !B || !proofs || count == 0) return fail(SIPP_ERR_ARG, "null pointer or count == 0");
+    if (!is_pow2(n)) return fail(SIPP_ERR_ARG, "n must be a non-zero power of two");
+    return SIPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sipp_prove_native_batch_device(const void* dA, const void* dB, size_t n, size_t count, void* d_proofs) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = batch_args(dA, dB, n, count, d_proofs);
+    if (rc) return rc;
+    const size_t np = sipp_proof_len(n);
+    BatchBuffers b;
+    rc = batch_alloc(b, n, count);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(b.bytesA, dA, n * count * 64, cudaMemcpyDeviceToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.bytesB, dB, n * count * 128, cudaMemcpyDeviceToDevice, g_stream);
+    if (e != cudaSuccess) { b.release(); return cuda_fail(e, "D2D"); }
+    rc = batch_prove_resident(b, n, count, g_stream);
+    if (!rc) {
+        e = cudaMemcpyAsync(d_proofs, b.proofs, count * np * 384, cudaMemcpyDeviceToDevice, g_stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "D2D");
+    }
+    if (!rc) rc = batch_check_flags(b, g_stream);
+    else cudaStreamSynchronize(g_stream);
+    b.release();
+    return rc;
+}
+
+int sipp_prove_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_t count, uint8_t* proofs) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = batch_args(A, B, n, count, proofs);
+    if (rc) return rc;
+    const size_t np = sipp_proof_len(n);
+    BatchBuffers b;
+    rc = batch_alloc(b, n, count);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(b.bytesA, A, n * count * 64, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.bytesB, B, n * count * 128, cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) { b.release(); return cuda_fail(e, "H2D"); }
+    rc = batch_prove_resident(b, n, count, g_stream);
+    if (!rc) {
+        e = cudaMemcpyAsync(proofs, b.proofs, count * np * 384, cudaMemcpyDeviceToHost, g_stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "D2H");
+    }
+    if (!rc) rc = batch_check_flags(b, g_stream);
+    else cudaStreamSynchronize(g_stream);
+    b.release();
+    return rc;
+}
+
+// `count` independent verifications in lock-step (verifier_native.rs:14-85 per instance): the transcript replay, the folds and the
+// GT update Z_L^x Z Z_R^(x^-1) of every instance run in the same launches; the final pairing check (:80) is one batched
+// product of one pair per instance.  results[j] = SIPP_OK / SIPP_ERR_VERIFY.
+int sipp_verify_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_t count, const uint8_t* proofs, size_t proof_len, int* results,
+                             uint8_t* final_A, uint8_t* final_B, uint8_t* final_Z) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!results) return fail(SIPP_ERR_ARG, "null results");
+    rc = batch_args(A, B, n, count, proofs);
+    if (rc) return rc;
+    const size_t np = sipp_proof_len(n);
+    if (proof_len < np) return fail(SIPP_ERR_SHORT_PROOF, "proof.pop().unwrap() on an empty proof");  // verifier_native.rs:31,40,42
+    const size_t total = n * count, top = proof_len;  // the verifier pops from the end: Z = proof[top - 1]
+    cudaStream_t s = g_stream;
+    BatchBuffers b;
+    uint32_t *dproofs = nullptr, *dz = nullptr, *dpair = nullptr, *dfin = nullptr;
+    uint64_t* dchal = nullptr;
+    cudaError_t e = pool_alloc((void**)&b.bytesA, total * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.bytesB, total * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.dA, total * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.dB, total * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.partials, count * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.states, count * 32);
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.plans, count * sizeof(FoldPlan));
+    if (e == cudaSuccess) e = pool_alloc((void**)&b.flags, 2 * sizeof(int));
+    if (e == cudaSuccess) e = pool_alloc((void**)&dproofs, count * proof_len * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dz, count * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dpair, count * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dfin, count * 192);
+    if (e == cudaSuccess) e = pool_alloc((void**)&dchal, count * 64);
+    auto release = [&]() {
+        b.release();
+        pool_free(dproofs); pool_free(dz); pool_free(dpair); pool_free(dfin); pool_free(dchal);
+    };
+    if (e != cudaSuccess) { release(); return cuda_fail(e, "cudaMalloc(verify batch)"); }
+    std::vector<uint8_t> hz(count * 384), hp(count * 384);
+    auto run = [&]() -> int {
+        CK(cudaMemcpyAsync(b.bytesA, A, total * 64, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b.bytesB, B, total * 128, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dproofs, proofs, count * proof_len * 384, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), s));
+        int le = launch_codec_decode(b.bytesA, b.dA, total * 2, b.flags + 1, s);
+        if (!le) le = launch_codec_decode(b.bytesB, b.dB, total * 4, b.flags + 1, s);
+        if (!le) le = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, s);                 // :25-28
+        if (le) return cuda_fail((cudaError_t)le, "verify batch: decode / absorb");
+        g_stats.launches += 3;
+        // let original_Z = proof.pop().unwrap();  :31   (Z of instance j = its last Fq12)
+        CK(cudaMemcpy2DAsync(dz, 384, (const uint8_t*)dproofs + (top - 1) * 384, proof_len * 384, 384, count, cudaMemcpyDeviceToDevice, s));
+        size_t m = n;
+        int round = 1;
+        while (m > 1) {                                                                                     // :35
+            const int slot_l = (int)top - 2 * round, slot_r = (int)top - 1 - 2 * round;                     // :40, :42
+            le = launch_tr_round(b.states, dproofs, proof_len, round == 1 ? (int)top - 1 : -1, slot_l, slot_r, g_opt_fq12_order, count, b.plans,
+                                 dchal, b.flags, s);                                                         // :33 (first round), :41-46
+            if (!le) le = (g_opt_fold_straus && count * (m / 2) >= 16384) ? launch_fold_straus(b.dA, b.dB, m / 2, n, count, b.plans, s)
+                                                                             : launch_fold_batch(b.dA, b.dB, m / 2, n, count, b.plans, s);  // :48-57
+            if (!le) le = launch_gt_fold_batch(dproofs, proof_len, slot_l, slot_r, dchal, dz, count, s);  // :59-61
+            if (le) return cuda_fail((cudaError_t)le, "verify batch: round");
+            g_stats.launches += 3;
+            g_stats.fold_points += count * (m / 2);
+            m /= 2;
+            round++;
+        }
+        // pairing(final_A, final_B) == final_Z   :80   (final_A = A[0], final_B = B[0] of every instance  :74-75)
+        int rc2 = batch_products(b, n, count, 1, 0, dpair, 1, 0, 0, s);
+        if (rc2) return rc2;
+        if (final_A || final_B) {
+            CK(cudaMemcpy2DAsync(b.bytesA, 64, b.dA, n * 64, 64, count, cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpy2DAsync(b.bytesB, 128, b.dB, n * 128, 128, count, cudaMemcpyDeviceToDevice, s));
+            le = launch_codec_encode(b.bytesA, dfin, count * 2, s);
+            if (!le) le = launch_codec_encode(b.bytesB, dfin + count * 16, count * 4, s);
+            if (le) return cuda_fail((cudaError_t)le, "verify batch: encode");
+            g_stats.launches += 2;
+            if (final_A) CK(cudaMemcpyAsync(final_A, dfin, count * 64, cudaMemcpyDeviceToHost, s));
+            if (final_B) CK(cudaMemcpyAsync(final_B, dfin + count * 16, count * 128, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaMemcpyAsync(hz.data(), dz, count * 384, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hp.data(), dpair, count * 384, cudaMemcpyDeviceToHost, s));
+        return batch_check_flags(b, s);
+    };
+    rc = run();
+    if (rc) cudaStreamSynchronize(s);
+    release();
+    if (rc) return rc;
+    for (size_t j = 0; j < count; j++) results[j] = memcmp(&hz[384 * j], &hp[384 * j], 384) == 0 ? SIPP_OK : SIPP_ERR_VERIFY;  // :81-84
+    if (final_Z) memcpy(final_Z, hz.data(), count * 384);
+    return SIPP_OK;
+}
+
+// `count` independent Poseidon permutations on the device (test hook for k_transcript.cu)
+int sipp_test_poseidon_device(uint64_t* states, size_t count) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!states || count == 0) return fail(SIPP_ERR_ARG, "bad argument");
+    uint64_t* d;
+    CK(cudaMalloc(&d, count * 96));
+    cudaError_t e = cudaMemcpyAsync(d, states, count * 96, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = (cudaError_t)launch_test_poseidon(d, count, g_stream);
+    g_stats.launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(states, d, count * 96, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "sipp_test_poseidon_device");
+    return SIPP_OK;
+}
+
+// device transcript of one round for `count` instances (test hook): states in/out (4 x u64 each), fq12s = count x nf x 384 B
+// (nf = 2: Z_L, Z_R; nf = 3: Z, Z_L, Z_R), out: count x 64 B = x || x^-1, plans_out: count x sizeof(FoldPlan) or NULL
+int sipp_test_transcript_round_device(uint64_t* states, const uint8_t* fq12s, int nf, size_t count, uint8_t* x_out, uint32_t* plans_out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!states || !fq12s || !x_out || count == 0 || (nf != 2 && nf != 3)) return fail(SIPP_ERR_ARG, "bad argument");
+    uint64_t *d_st, *d_x;
+    uint32_t* d_f;
+    FoldPlan* d_pl;
+    int* d_flags;
+    CK(cudaMalloc(&d_st, count * 32));
+    CK(cudaMalloc(&d_x, count * 64));
+    CK(cudaMalloc(&d_f, count * nf * 384));
+    CK(cudaMalloc(&d_pl, count * sizeof(FoldPlan)));
+    CK(cudaMalloc(&d_flags, sizeof(int)));
+    cudaMemsetAsync(d_flags, 0, sizeof(int), g_stream);
+    cudaMemcpyAsync(d_st, states, count * 32, cudaMemcpyHostToDevice, g_stream);
+    cudaMemcpyAsync(d_f, fq12s, count * nf * 384, cudaMemcpyHostToDevice, g_stream);
+    cudaError_t e = (cudaError_t)launch_tr_round(d_st, d_f, nf, nf == 3 ? 0 : -1, nf - 2, nf - 1, g_opt_fq12_order, count, d_pl, d_x, d_flags, g_stream);
+    g_stats.launches++;
+    int flags = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(states, d_st, count * 32, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(x_out, d_x, count * 64, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess && plans_out) e = cudaMemcpyAsync(plans_out, d_pl, count * sizeof(FoldPlan), cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    cudaFree(d_st); cudaFree(d_x); cudaFree(d_f); cudaFree(d_pl); cudaFree(d_flags);
+    if (e != cudaSuccess) return cuda_fail(e, "sipp_test_transcript_round_device");
+    if (flags & 1) return fail(SIPP_ERR_ZERO_CHALLENGE, "challenge is zero");
+    if (flags & 2) return fail(SIPP_ERR_ENCODING, "fold scalar recoding failed");
+    return SIPP_OK;
+}
+
+}  // extern "C"

@@ -197,3 +197,15 @@ def test_statement_public_input_vector(golden):
     assert api.SIPPStatement.from_vec(n, vec) == st
     with pytest.raises(AssertionError):
         api.SIPPStatement.from_vec(n, vec[:-1])
+
+
+def test_shard_instances_partition():
+    """batched instances are sharded by contiguous slices (no collective): the slices tile [0, count) and differ by at most one"""
+    from sipp_b200.sharded import shard_instances
+    for count in (1, 7, 8, 512, 4096, 4097):
+        for world in (1, 2, 3, 8):
+            parts = [shard_instances(count, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == count
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
