@@ -191,3 +191,38 @@ def test_verify_batch_n128(sipp):
     sts = sipp.sipp_verify_native_batch(A, B, n, proofs)
     assert all(not isinstance(s, Exception) for s in sts)
     assert all(s.final_Z != s.Z for s in sts)
+
+
+def test_batch_config5_full_size(sipp, oracle):
+    """BASELINE config 5 at its full size (SURVEY 8d C5): 4096 x n = 128, instance j = pairs [128 j, 128 (j + 1)) of the seed-5 stream;
+    64 of the 4096 proofs against the oracle, ALL of them verified on the GPU (batched verifier), one corrupted proof rejected alone"""
+    n, count = 128, 4096
+    A, B = sipp.seeded_inputs(5, n * count)
+    proofs = sipp.sipp_prove_native_batch(A, B, n)
+    assert len(proofs) == count
+    for j in range(0, count, 64):
+        a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
+        assert b"".join(proofs[j]) == oracle.sipp_prove(a, b, threads=16), j
+    bad = 1234
+    t = bytearray(proofs[bad][7]); t[3] ^= 0x10
+    proofs[bad] = proofs[bad][:7] + [bytes(t)] + proofs[bad][8:]
+    sts = sipp.sipp_verify_native_batch(A, B, n, proofs)
+    failed = [j for j, s in enumerate(sts) if isinstance(s, Exception)]
+    assert failed == [bad]
+    assert all(s.Z == proofs[j][-1] for j, s in enumerate(sts) if j != bad)
+
+
+def test_batch_degenerate_shapes(sipp, oracle):
+    """count = 1, n = 1 (proof = [Z]), and an instance made only of identity pairs (every product is 1)"""
+    A, B = oracle.seeded_inputs(3, 8, threads=2)
+    assert sipp.sipp_prove_native_batch(A, B, 8) == [sipp.sipp_prove_native(A, B)]
+    ones = sipp.sipp_prove_native_batch(A, B, 1)
+    assert [p[0] for p in ones] == [sipp.pairing(A[64 * i:64 * i + 64], B[128 * i:128 * i + 128]) for i in range(8)]
+    Az = bytes(64 * 4) + A[:64 * 4]
+    Bz = B[:128 * 4] + bytes(128 * 4)
+    got = sipp.sipp_prove_native_batch(Az, Bz, 4)
+    one12 = (1).to_bytes(32, "little") + bytes(352)
+    assert got[0] == sipp.sipp_prove_native(Az[:64 * 4], Bz[:128 * 4]) and all(z == one12 for z in got[0])
+    assert got[1] == sipp.sipp_prove_native(Az[64 * 4:], Bz[128 * 4:])
+    sts = sipp.sipp_verify_native_batch(Az, Bz, 4, got)
+    assert all(not isinstance(s, Exception) for s in sts)
