@@ -192,11 +192,18 @@ def measure_batch(count_total, n, world, rank, local_rank, W, K, barrier, all_ma
 
     for _ in range(W):
         step_resident()
-    sipp_b200.set_option(_lib.OPT_PROFILE, 1)
     sipp_b200.stats(reset=True)
     t_res = timed(step_resident, K)
+    launches = sipp_b200.stats(reset=True)["launches"]
+    # kernel-class shares and the roofline come from a separate profiled pass: with event spans on, the library runs the batch as
+    # one sub-batch so that the spans do not overlap (the timed steps above overlap sub-batches on several streams)
+    sipp_b200.set_option(_lib.OPT_PROFILE, 1)
+    sipp_b200.stats(reset=True)
+    t_prof = timed(step_resident, 1)
     st = sipp_b200.stats(reset=True)
     sipp_b200.set_option(_lib.OPT_PROFILE, 0)
+    st["launches"] = launches
+    st["profiled_step_ms"] = t_prof * 1e3
     for _ in range(W):
         step_e2e()
     t_e2e = timed(step_e2e, K)
@@ -266,9 +273,11 @@ def run_batch(args, world, rank, local_rank, W, K):
             "roofline": {"bound": "imad", "kernel": "k_lines_batch + k_accum (Miller loops of all instances of a round)", "achieved": mill_ach / 1e12,
                          "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak, "traffic": None,
                          "launches": int(st["miller_launches"]), "avg_launch_ms": st["miller_ms"] / max(1, st["miller_launches"]),
-                         "peak_source": "measured in this run (sipp_microbench)",
-                         "kernel_time_share": {"miller_ms": st["miller_ms"] / K, "final_exp_ms": st["reduce_fe_ms"] / K, "fold_ms": st["fold_ms"] / K,
-                                               "decode_transcript_ms(side stream, overlapped)": st["other_ms"] / K, "step_ms": m["t_res"] / K * 1e3},
+                         "peak_source": "measured in this run (sipp_microbench); kernel times from one profiled step",
+                         "kernel_time_share": {"miller_ms": st["miller_ms"], "final_exp_ms": st["reduce_fe_ms"], "fold_ms": st["fold_ms"],
+                                               "decode_transcript_ms(side stream, overlapped)": st["other_ms"],
+                                               "profiled_step_ms(single stream, event spans on)": st["profiled_step_ms"],
+                                               "step_ms": m["t_res"] / K * 1e3},
                          "microbench": peaks}}
     if not args.no_cpu_baseline:
         from oracle import pyoracle as o

@@ -62,6 +62,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
 #define SIPP_OPT_BATCH_KPG_MAX 9      /* batched instances: at most this many pairs of one product share an accumulator group */
 #define SIPP_OPT_FOLD_STRAUS 10       /* throughput folds: 1 = one thread per element with shared doublings (k_fold_straus) [default];
                                          0 = lane-split components (k_fold_batch / k_fold_split) */
+#define SIPP_OPT_BATCH_STREAMS 11     /* batched instances: number of independent sub-batches run on their own streams so that the
+                                         latency-bound late rounds overlap (1..8; 0 = default = 1: measured no gain on B200) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

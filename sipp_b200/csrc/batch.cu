@@ -37,7 +37,9 @@ size_t pow2_floor(size_t v) {
 }
 
 // products of the current round of every instance: which = 0 -> Z (slot0), which = 1 -> Z_L (slot0), Z_R (slot1)
-int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m, int which, uint32_t* fe_out, size_t np, int slot0, int slot1, cudaStream_t s) {
+// `lines` / `lines_cap`: this caller's slice of the process line table (sub-batches on different streams use disjoint slices)
+int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m, int which, uint32_t* fe_out, size_t np, int slot0, int slot1, uint32_t* lines,
+                   size_t lines_cap, cudaStream_t s) {
     BatchJob job;
     job.stride = stride;
     if (which == 0) {
@@ -50,8 +52,7 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
     }
     const size_t nproducts = count * (size_t)job.nprod;
     const size_t per_pair = lines_bytes_per_pair();
-    const size_t cap_bytes = (size_t)16 << 30;
-    size_t pc = cap_bytes / (job.h * per_pair);  // products per chunk (whole products only)
+    size_t pc = lines_cap / (job.h * per_pair);  // products per chunk (whole products only)
     if (pc < 1) return fail(SIPP_ERR_ARG, "batched instances: one product exceeds the line buffer (use sipp_prove_native for large n)");
     if (pc > nproducts) pc = nproducts;
     // accumulator groups: kpg pairs of ONE product share an accumulator and its 64 squarings (5,070 Fq-mul-eq per group, 3,661
@@ -68,15 +69,13 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
         }
     }
     const size_t gpp = job.h / kpg;
-    int rc = lines_reserve(pc * job.h * per_pair);
-    if (rc) return rc;
     {
         Span sp(0, s);
         for (size_t p0 = 0; p0 < nproducts; p0 += pc) {
             size_t cur = nproducts - p0 < pc ? nproducts - p0 : pc;
-            int e = launch_lines_batch(b.dA, b.dB, job, p0, cur, lines_buffer(), s);
+            int e = launch_lines_batch(b.dA, b.dB, job, p0, cur, lines, s);
             if (e) return cuda_fail((cudaError_t)e, "k_lines_batch");
-            e = launch_accum_batch(lines_buffer(), cur * job.h, (int)kpg, b.partials, p0 * gpp, s);
+            e = launch_accum_batch(lines, cur * job.h, (int)kpg, b.partials, p0 * gpp, s);
             if (e) return cuda_fail((cudaError_t)e, "k_accum(batch)");
             g_stats.launches += 2;
             g_stats.miller_launches++;
@@ -92,7 +91,37 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
     return SIPP_OK;
 }
 
-// the whole batch on the device; bytesA / bytesB already hold the boundary bytes.  Enqueues everything, synchronises once.
+// line-table budget of one batched call, split evenly over its sub-batches
+const size_t kBatchLinesCap = (size_t)16 << 30;
+
+// slice [i0, i0 + c) of the instances of a batch
+BatchBuffers batch_view(const BatchBuffers& b, size_t n, size_t np, size_t i0) {
+    BatchBuffers v = b;
+    v.bytesA = b.bytesA + i0 * n * 16; v.bytesB = b.bytesB + i0 * n * 32;
+    v.dA = b.dA + i0 * n * 16; v.dB = b.dB + i0 * n * 32;
+    v.proofs = b.proofs ? b.proofs + i0 * np * 96 : nullptr;
+    v.partials = b.partials + i0 * n * 96;
+    v.states = b.states + i0 * 4;
+    v.plans = b.plans + i0;
+    return v;
+}
+
+// Sub-batches (SIPP_OPT_BATCH_STREAMS, off by default): the late rounds of a batch are latency-bound (a launch of a few thousand
+// pairs does not fill 148 SMs), so a batch can be cut into independent sub-batches on their own streams whose kernels run side by
+// side.  Measured: no gain (see batch_sub_count) -- kept as an experiment switch.
+int g_sub_streams_dev = -1;
+cudaStream_t g_sub_streams[8];
+int batch_sub_count(size_t n, size_t count) {
+    if (g_opt_profile) return 1;  // per-kernel-class event spans are only meaningful when the launches do not overlap
+    int want = g_opt_batch_streams;
+    if (want <= 0) want = 1;  // measured on B200 (512 and 4096 instances of n = 128): 1 / 2 / 4 / 8 sub-batches = 95 / 98 / 104 / 103 ms and
+                              // 401 / 398 / 423 / 460 ms -- concurrent sub-batches run in the same phase and compete, so the default is one
+    if (want > 8) want = 8;
+    while (want > 1 && count / (size_t)want < 32) want /= 2;
+    return want < 1 ? 1 : want;
+}
+
+// the whole batch on the device; bytesA / bytesB already hold the boundary bytes.  Enqueues everything; the caller synchronises.
 int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s) {
     const size_t np = sipp_proof_len(n), total = n * count;
     CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), s));
@@ -111,6 +140,10 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         side_dev = g_device;
     }
+    if (g_sub_streams_dev != g_device) {
+        for (int k = 0; k < 8; k++) CK(cudaStreamCreateWithFlags(&g_sub_streams[k], cudaStreamNonBlocking));
+        g_sub_streams_dev = g_device;
+    }
     CK(order_after(side, s));
     {
         Span sp(3, side);
@@ -118,35 +151,54 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         if (e) return cuda_fail((cudaError_t)e, "k_tr_absorb_pairs");
         g_stats.launches++;
     }
-    int rc = batch_products(b, n, count, n, 0, b.proofs, np, (int)np - 1, 0, s);        // let Z = inner_product(A, B);  :29 (pushed first, last after reverse)
+    const int nsub = batch_sub_count(n, count);
+    // line table: every sub-batch gets a slice large enough for its largest launch (Z: all n pairs of its instances), within the budget
+    const size_t per_pair = lines_bytes_per_pair();
+    const size_t sub_max = (count + nsub - 1) / nsub;
+    size_t slice = sub_max * n * per_pair;
+    if (slice > kBatchLinesCap / nsub) slice = kBatchLinesCap / nsub;
+    slice = (slice + 255) & ~(size_t)255;
+    int rc = lines_reserve(slice * nsub);
     if (rc) return rc;
-    size_t m = n;
-    int round = 1;
-    while (m > 1) {                                                            // :45
-        const int slot_l = (int)np - 2 * round, slot_r = (int)np - 1 - 2 * round;  // proof.reverse()  :78
-        rc = batch_products(b, n, count, m, 1, b.proofs, np, slot_l, slot_r, s);         // :46-49
+    // fork: every sub-stream waits for the decode on `s` (ordered BEFORE any join below, or sub-batch k + 1 would wait for k)
+    for (int k = 0; k < nsub && nsub > 1; k++) CK(order_after(g_sub_streams[k], s));
+    for (int k = 0; k < nsub; k++) {
+        const size_t i0 = count * (size_t)k / nsub, i1 = count * (size_t)(k + 1) / nsub, c = i1 - i0;
+        if (c == 0) continue;
+        cudaStream_t sk = nsub == 1 ? s : g_sub_streams[k];
+        BatchBuffers v = batch_view(b, n, np, i0);
+        uint32_t* lines = lines_buffer() + (slice / 4) * k;
+        rc = batch_products(v, n, c, n, 0, v.proofs, np, (int)np - 1, 0, lines, slice, sk);   // let Z = inner_product(A, B);  :29 (pushed first)
         if (rc) return rc;
-        if (round == 1) CK(order_after(s, side));
-        {
-            Span sp(3, s);
-            int e = launch_tr_round(b.states, b.proofs, np, round == 1 ? (int)np - 1 : -1, slot_l, slot_r, g_opt_fq12_order, count, b.plans, nullptr,
-                                    b.flags, s);                               // :42-43 (first round), :52-58
-            if (e) return cuda_fail((cudaError_t)e, "k_tr_round");
-            g_stats.launches++;
+        size_t m = n;
+        int round = 1;
+        while (m > 1) {                                                            // :45
+            const int slot_l = (int)np - 2 * round, slot_r = (int)np - 1 - 2 * round;  // proof.reverse()  :78
+            rc = batch_products(v, n, c, m, 1, v.proofs, np, slot_l, slot_r, lines, slice, sk);  // :46-49
+            if (rc) return rc;
+            if (round == 1) CK(order_after(sk, side));
+            {
+                Span sp(3, sk);
+                int e = launch_tr_round(v.states, v.proofs, np, round == 1 ? (int)np - 1 : -1, slot_l, slot_r, g_opt_fq12_order, c, v.plans, nullptr,
+                                        b.flags, sk);                              // :42-43 (first round), :52-58
+                if (e) return cuda_fail((cudaError_t)e, "k_tr_round");
+                g_stats.launches++;
+            }
+            {
+                Span sp(2, sk);
+                // one thread per element (shared doublings) when the launch fills the GPU; otherwise the lane-split components, whose
+                // dependent chain is 3x shorter when a warp spans several instances (divergent digit tests)
+                int e = (g_opt_fold_straus && c * (m / 2) >= 16384) ? launch_fold_straus(v.dA, v.dB, m / 2, n, c, v.plans, sk)
+                                                                    : launch_fold_batch(v.dA, v.dB, m / 2, n, c, v.plans, sk);  // :60-74
+                if (e) return cuda_fail((cudaError_t)e, "k_fold_batch");
+                g_stats.launches++;
+                g_stats.fold_points += c * (m / 2);
+            }
+            m /= 2;
+            round++;
         }
-        {
-            Span sp(2, s);
-            // one thread per element (shared doublings) when the launch fills the GPU; otherwise the lane-split components, whose
-            // dependent chain is 3x shorter when a warp spans several instances (divergent digit tests)
-            int e = (g_opt_fold_straus && count * (m / 2) >= 16384) ? launch_fold_straus(b.dA, b.dB, m / 2, n, count, b.plans, s)
-                                      : launch_fold_batch(b.dA, b.dB, m / 2, n, count, b.plans, s);  // :60-74
-            if (e) return cuda_fail((cudaError_t)e, "k_fold_batch");
-            g_stats.launches++;
-            g_stats.fold_points += count * (m / 2);
-        }
-        m /= 2;
-        round++;
     }
+    for (int k = 0; k < nsub && nsub > 1; k++) CK(order_after(s, g_sub_streams[k]));  // join
     return SIPP_OK;
 }
 
@@ -299,7 +351,9 @@ int sipp_verify_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_
             round++;
         }
         // pairing(final_A, final_B) == final_Z   :80   (final_A = A[0], final_B = B[0] of every instance  :74-75)
-        int rc2 = batch_products(b, n, count, 1, 0, dpair, 1, 0, 0, s);
+        int rc2 = lines_reserve(count * lines_bytes_per_pair());
+        if (rc2) return rc2;
+        rc2 = batch_products(b, n, count, 1, 0, dpair, 1, 0, 0, lines_buffer(), count * lines_bytes_per_pair(), s);
         if (rc2) return rc2;
         if (final_A || final_B) {
             CK(cudaMemcpy2DAsync(b.bytesA, 64, b.dA, n * 64, 64, count, cudaMemcpyDeviceToDevice, s));

@@ -28,6 +28,7 @@ int g_opt_wide_accum_max = 1536;
 int g_opt_wide_max = 8192;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
 int g_sm_count = 148;
 int g_opt_fold_straus = 1;     // throughput folds (batched instances, large rounds): 1 = one thread per element, shared doublings
+int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own streams (0 = choose by batch size)
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
 
 struct TimedSpan {
@@ -377,6 +378,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_WIDE_ACCUM_MAX: g_opt_wide_accum_max = value < 0 ? 0 : value; return SIPP_OK;
         case SIPP_OPT_BATCH_KPG_MAX: g_opt_batch_kpg_max = value < 1 ? 1 : value; return SIPP_OK;
         case SIPP_OPT_FOLD_STRAUS: g_opt_fold_straus = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_BATCH_STREAMS: g_opt_batch_streams = value < 0 ? 0 : value; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -392,6 +394,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_WIDE_ACCUM_MAX: return g_opt_wide_accum_max;
         case SIPP_OPT_BATCH_KPG_MAX: return g_opt_batch_kpg_max;
         case SIPP_OPT_FOLD_STRAUS: return g_opt_fold_straus;
+        case SIPP_OPT_BATCH_STREAMS: return g_opt_batch_streams;
         default: return -1;
     }
 }
