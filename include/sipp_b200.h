@@ -186,6 +186,8 @@ int sipp_test_poseidon_device(uint64_t *states, size_t count);
  * or 3 (Z, Z_L, Z_R: first round); x_out = count x 64 B (challenge x || x^-1); plans_out = count x raw fold plan
  * (same words as sipp_test_fold_plan) or NULL */
 int sipp_test_transcript_round_device(uint64_t *states, const uint8_t *fq12s, int nf, size_t count, uint8_t *x_out, uint32_t *plans_out);
+/* host copy of the binary Fr inversion used by the device transcript (glv_core.h): 0 ok, -1 x >= r, -2 x == 0; no GPU needed */
+int sipp_test_fr_inverse_binary(const uint8_t x[32], uint8_t out[32]);
 int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);
 
 #ifdef __cplusplus

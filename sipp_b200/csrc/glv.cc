@@ -28,3 +28,12 @@ int fold_plan_build(const uint8_t x[32], const uint8_t x_inv[32], FoldPlan* plan
 }
 
 }  // namespace sipp
+
+// host copy of the inversion the device transcript uses (glv_core.h), for the CPU tests: 0 ok, -1 v >= r, -2 v == 0
+extern "C" int sipp_test_fr_inverse_binary(const uint8_t x[32], uint8_t out[32]) {
+    uint64_t v[4], o[4] = {0, 0, 0, 0};
+    memcpy(v, x, 32);
+    int rc = sipp::glv::fr_inverse_binary(v, o);
+    memcpy(out, o, 32);
+    return rc;
+}

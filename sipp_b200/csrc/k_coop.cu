@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_reduce_fe_coop(const uin
 // Batched instances: product P multiplies its `gpp` consecutive group results and takes ONE final exponentiation; 20 products
 // per block (6 lanes each).  out: instance `P / nprod` at out + inst * out_stride words, Fq12 slot slot0 (y = 0) / slot1 (y = 1),
 // boundary bytes -- the instance's proof vector, written in its final (reversed) order (prover_native.rs:78).
-__global__ void __launch_bounds__(SIPP_ACCUM_THREADS) k_fe_batch(const uint32_t* __restrict__ partials, size_t nproducts, int gpp, int nprod,
+__global__ void __launch_bounds__(SIPP_ACCUM_THREADS, 3) k_fe_batch(const uint32_t* __restrict__ partials, size_t nproducts, int gpp, int nprod,
                                                                uint32_t* __restrict__ out, size_t out_stride, int slot0, int slot1, int ark_norm) {
     const Lane6 L = lane6_of_thread();
     const int warp = threadIdx.x >> 5;

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(SIPP_TR_THREADS) k_tr_round(uint64_t* __restri
         }
     }
     uint64_t vi[4] = {0, 0, 0, 0};
-    int rc_inv = glv::fr_inverse(v, vi);                                    // prover_native.rs:58
+    int rc_inv = glv::fr_inverse_binary(v, vi);                                    // prover_native.rs:58
     if (challenges) {
         for (int i = 0; i < 4; i++) { challenges[8 * inst + i] = v[i]; challenges[8 * inst + 4 + i] = vi[i]; }
     }

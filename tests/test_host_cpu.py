@@ -209,3 +209,21 @@ def test_shard_instances_partition():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_fr_inverse_binary_matches_fermat():
+    """the binary inversion of the device transcript (glv_core.h, compiled for the host) == sipp_fr_inverse (x^(r-2)) == pow(x, -1, r)"""
+    import random
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    lib.sipp_test_fr_inverse_binary.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    rng = random.Random(5)
+    xs = [1, 2, 3, R - 1, R - 2, (R + 1) // 2, 2**253, 2**64, 2**64 - 1] + [rng.randrange(1, R) for _ in range(3000)]
+    for x in xs:
+        out = ctypes.create_string_buffer(32)
+        assert lib.sipp_test_fr_inverse_binary(x.to_bytes(32, "little"), out) == 0
+        assert int.from_bytes(out.raw, "little") == pow(x, -1, R), hex(x)
+    out = ctypes.create_string_buffer(32)
+    assert lib.sipp_test_fr_inverse_binary((0).to_bytes(32, "little"), out) == -2
+    assert lib.sipp_test_fr_inverse_binary(R.to_bytes(32, "little"), out) == -1
