@@ -64,6 +64,8 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          0 = lane-split components (k_fold_batch / k_fold_split) */
 #define SIPP_OPT_BATCH_STREAMS 11     /* batched instances: number of independent sub-batches run on their own streams so that the
                                          latency-bound late rounds overlap (1..8; 0 = default = 1: measured no gain on B200) */
+#define SIPP_OPT_BATCH_QLINES 12      /* batched instances: 1 = the line coefficients of every B_i are computed once and shared by Z
+                                         and the first Z_L / Z_R (k_qlines_batch + k_eval_lines_batch) [default]; 0 = recomputed */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

@@ -38,8 +38,9 @@ size_t pow2_floor(size_t v) {
 
 // products of the current round of every instance: which = 0 -> Z (slot0), which = 1 -> Z_L (slot0), Z_R (slot1)
 // `lines` / `lines_cap`: this caller's slice of the process line table (sub-batches on different streams use disjoint slices)
+// `qlines` (or NULL): Q-only line coefficients of every B point of the slice (k_qlines_batch), valid while B is unfolded
 int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m, int which, uint32_t* fe_out, size_t np, int slot0, int slot1, uint32_t* lines,
-                   size_t lines_cap, cudaStream_t s) {
+                   size_t lines_cap, const uint32_t* qlines, cudaStream_t s) {
     BatchJob job;
     job.stride = stride;
     if (which == 0) {
@@ -73,7 +74,7 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
         Span sp(0, s);
         for (size_t p0 = 0; p0 < nproducts; p0 += pc) {
             size_t cur = nproducts - p0 < pc ? nproducts - p0 : pc;
-            int e = launch_lines_batch(b.dA, b.dB, job, p0, cur, lines, s);
+            int e = qlines ? launch_eval_lines_batch(b.dA, b.dB, job, p0, cur, qlines, lines, s) : launch_lines_batch(b.dA, b.dB, job, p0, cur, lines, s);
             if (e) return cuda_fail((cudaError_t)e, "k_lines_batch");
             e = launch_accum_batch(lines, cur * job.h, (int)kpg, b.partials, p0 * gpp, s);
             if (e) return cuda_fail((cudaError_t)e, "k_accum(batch)");
@@ -160,6 +161,13 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
     slice = (slice + 255) & ~(size_t)255;
     int rc = lines_reserve(slice * nsub);
     if (rc) return rc;
+    // Q-only line coefficients of all B points, when they fit the budget (17,472 B per point)
+    uint32_t* qbuf = nullptr;
+    if (g_opt_batch_qlines && total * qlines_bytes_per_point() <= kBatchLinesCap) {
+        cudaError_t qe = pool_alloc((void**)&qbuf, total * qlines_bytes_per_point());
+        if (qe != cudaSuccess) return cuda_fail(qe, "cudaMalloc(qlines)");
+    }
+    struct QFree { uint32_t* p; ~QFree() { pool_free(p); } } qfree{qbuf};  // recycled block: later work on the same streams only
     // fork: every sub-stream waits for the decode on `s` (ordered BEFORE any join below, or sub-batch k + 1 would wait for k)
     for (int k = 0; k < nsub && nsub > 1; k++) CK(order_after(g_sub_streams[k], s));
     for (int k = 0; k < nsub; k++) {
@@ -168,13 +176,23 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         cudaStream_t sk = nsub == 1 ? s : g_sub_streams[k];
         BatchBuffers v = batch_view(b, n, np, i0);
         uint32_t* lines = lines_buffer() + (slice / 4) * k;
-        rc = batch_products(v, n, c, n, 0, v.proofs, np, (int)np - 1, 0, lines, slice, sk);   // let Z = inner_product(A, B);  :29 (pushed first)
+        // every B_i is paired twice before the first fold (in Z and in the first Z_L / Z_R): walk it through the schedule once
+        const uint32_t* ql = nullptr;
+        if (qbuf && n >= 2) {
+            uint32_t* q = qbuf + i0 * n * (qlines_bytes_per_point() / 4);
+            Span sp(0, sk);
+            int e = launch_qlines_batch(v.dB, c * n, q, sk);
+            if (e) return cuda_fail((cudaError_t)e, "k_qlines_batch");
+            g_stats.launches++;
+            ql = q;
+        }
+        rc = batch_products(v, n, c, n, 0, v.proofs, np, (int)np - 1, 0, lines, slice, ql, sk);   // let Z = inner_product(A, B);  :29 (pushed first)
         if (rc) return rc;
         size_t m = n;
         int round = 1;
         while (m > 1) {                                                            // :45
             const int slot_l = (int)np - 2 * round, slot_r = (int)np - 1 - 2 * round;  // proof.reverse()  :78
-            rc = batch_products(v, n, c, m, 1, v.proofs, np, slot_l, slot_r, lines, slice, sk);  // :46-49
+            rc = batch_products(v, n, c, m, 1, v.proofs, np, slot_l, slot_r, lines, slice, round == 1 ? ql : nullptr, sk);  // :46-49
             if (rc) return rc;
             if (round == 1) CK(order_after(sk, side));
             {
@@ -353,7 +371,7 @@ int sipp_verify_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_
         // pairing(final_A, final_B) == final_Z   :80   (final_A = A[0], final_B = B[0] of every instance  :74-75)
         int rc2 = lines_reserve(count * lines_bytes_per_pair());
         if (rc2) return rc2;
-        rc2 = batch_products(b, n, count, 1, 0, dpair, 1, 0, 0, lines_buffer(), count * lines_bytes_per_pair(), s);
+        rc2 = batch_products(b, n, count, 1, 0, dpair, 1, 0, 0, lines_buffer(), count * lines_bytes_per_pair(), nullptr, s);
         if (rc2) return rc2;
         if (final_A || final_B) {
             CK(cudaMemcpy2DAsync(b.bytesA, 64, b.dA, n * 64, 64, count, cudaMemcpyDeviceToDevice, s));

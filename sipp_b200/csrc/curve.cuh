@@ -6,6 +6,7 @@
 // Results are canonical affine points, so any correct algorithm is bit-identical to the reference's
 // MSB-first double-and-add.  The identity is encoded as x = y = 0 (ark's `infinity` has x=y=0).
 #pragma once
+#include "fold_plan.h"
 #include "tower.cuh"
 
 namespace sipp {
@@ -199,6 +200,27 @@ SIPP_HD Jac<F> jac_scalar_mul_naf(const Affine<F>& q, const uint32_t* plus, cons
             Affine<F> t = q;
             if (dm) t.y = f_neg(q.y);
             acc = jac_add_affine(acc, t);
+        }
+    }
+    return acc;
+}
+
+// joint (Straus / Shamir) form of the same sum for the throughput fold (k_fold_straus): the NC sub-scalars of an element share ONE
+// accumulator and its doublings; tbl[c] = (+-) endo^c(P), comps[c] the NAF masks of sub-scalar c (fold_plan.h)
+template <class F, int NC>
+SIPP_HD Jac<F> straus_naf(const Affine<F>* tbl, const FoldComp* comps, int bits) {
+    Jac<F> acc = jac_identity<F>();
+    for (int i = bits - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        const uint32_t m = 1u << (i & 31);
+        const int w = i >> 5;
+        for (int c = 0; c < NC; c++) {
+            const bool dp = (comps[c].plus[w] & m) != 0, dm = (comps[c].minus[w] & m) != 0;
+            if (dp || dm) {
+                Affine<F> t = tbl[c];
+                if (dm) t.y = f_neg(t.y);
+                acc = jac_add_affine(acc, t);
+            }
         }
     }
     return acc;

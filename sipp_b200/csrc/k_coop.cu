@@ -79,6 +79,61 @@ __global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_lines_batch(const 
     lines_of_pair(load_g1(A, base + job.a_off[y]), load_g2(B, base + job.b_off[y]), lines + t * SIPP_PAIR_LINE_WORDS);
 }
 
+// Line coefficients that depend on Q alone.  A line of the Miller loop is (l0 yP, l1 xP, l3) with (l0, l1, l3) functions of the
+// G2 point only, and the prover pairs every B_i twice before the first fold: with A_i in Z (prover_native.rs:29) and with its
+// cross partner in the first Z_L / Z_R (:48-49).  k_qlines_batch walks each G2 point through the schedule ONCE and keeps
+// (l0, l1, l3) (91 x 3 Fq2 = 17,472 B per point); k_eval_lines_batch turns them into the line table of a launch (two Fq2-by-Fq
+// scalings per line: 364 of the 3,155 Fq-mul of a full line computation; memory-bound).
+#define SIPP_QLINE_WORDS 48
+__global__ void __launch_bounds__(64, SIPP_LINES_MINBLOCKS) k_qlines_batch(const uint32_t* __restrict__ B, size_t npoints, uint32_t* __restrict__ qlines) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npoints) return;
+    const G2A q = load_g2(B, t);
+    if (affine_is_identity(q)) return;  // never read: k_eval_lines_batch writes the constant-1 lines for such a pair
+    G1A unit;
+    unit.x = fq_one(); unit.y = fq_one();
+    uint32_t* out = qlines + t * (size_t)(SIPP_LINES_PER_PAIR * SIPP_QLINE_WORDS);
+    miller_lines(
+        unit, q, [](int) {},
+        [&](int s, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
+            uint32_t* o = out + s * SIPP_QLINE_WORDS;
+            store_fq2_words(o, l0);
+            store_fq2_words(o + 16, l1);
+            store_fq2_words(o + 32, l3);
+        });
+}
+// one thread per (pair, step); same pair indexing as k_lines_batch, same output layout as k_lines
+__global__ void __launch_bounds__(128) k_eval_lines_batch(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, BatchJob job, size_t p0, size_t np,
+                                                          const uint32_t* __restrict__ qlines, uint32_t* __restrict__ lines) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np * job.h * SIPP_LINES_PER_PAIR) return;
+    const size_t pair = t / SIPP_LINES_PER_PAIR;
+    const int step = (int)(t - pair * SIPP_LINES_PER_PAIR);
+    const size_t P = p0 + pair / job.h, i = pair % job.h;
+    const size_t inst = P / (size_t)job.nprod;
+    const int y = (int)(P % (size_t)job.nprod);
+    const size_t ia = inst * job.stride + i + job.a_off[y], ib = inst * job.stride + i + job.b_off[y];
+    const G1A p = load_g1(A, ia);
+    uint32_t* o = lines + t * SIPP_LINE_WORDS;
+    // identity test of Q on its first 64 bytes is not enough (x = 0 alone is a valid coordinate): read both halves
+    const G2A q = load_g2(B, ib);
+    if (affine_is_identity(p) || affine_is_identity(q)) {
+        store_fq2_words(o, fq2_one());
+        store_fq2_words(o + 16, fq2_zero());
+        store_fq2_words(o + 32, fq2_zero());
+        store_fq2_words(o + 48, fq2_zero());
+        store_fq2_words(o + 64, fq2_zero());
+        return;
+    }
+    const uint32_t* src = qlines + (ib * SIPP_LINES_PER_PAIR + step) * SIPP_QLINE_WORDS;
+    const Fq2 l0 = fq2_scale(load_fq2_words(src), p.y), l1 = fq2_scale(load_fq2_words(src + 16), p.x), l3 = load_fq2_words(src + 32);
+    store_fq2_words(o, l0);
+    store_fq2_words(o + 16, l1);
+    store_fq2_words(o + 32, fq2_mul_xi(l1));
+    store_fq2_words(o + 48, l3);
+    store_fq2_words(o + 64, fq2_mul_xi(l3));
+}
+
 // ------------------------------------------------------------------------------------------------ A: accumulation
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -353,6 +408,17 @@ int launch_gt_fold_batch(const uint32_t* proofs, size_t stride, int slot_l, int 
                                                                                                                    z, count);
     return (int)cudaGetLastError();
 }
+int launch_qlines_batch(const uint32_t* B, size_t npoints, uint32_t* qlines, cudaStream_t s) {
+    k_qlines_batch<<<(unsigned)((npoints + 63) / 64), 64, 0, s>>>(B, npoints, qlines);
+    return (int)cudaGetLastError();
+}
+int launch_eval_lines_batch(const uint32_t* A, const uint32_t* B, const BatchJob& job, size_t p0, size_t np, const uint32_t* qlines, uint32_t* lines,
+                            cudaStream_t s) {
+    size_t threads = np * job.h * SIPP_LINES_PER_PAIR;
+    k_eval_lines_batch<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(A, B, job, p0, np, qlines, lines);
+    return (int)cudaGetLastError();
+}
+size_t qlines_bytes_per_point() { return (size_t)SIPP_LINES_PER_PAIR * SIPP_QLINE_WORDS * sizeof(uint32_t); }
 size_t lines_bytes_per_pair() { return (size_t)SIPP_PAIR_LINE_WORDS * sizeof(uint32_t); }
 
 }  // namespace sipp

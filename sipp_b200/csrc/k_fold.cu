@@ -146,27 +146,6 @@ __global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_batch(uint32_t* __re
 // the GPU: batched instances and the first rounds of a large proof.  plans[inst] as in k_fold_batch (count = 1: one proof).
 #define SIPP_STRAUS_THREADS 64
 
-template <class F, int NC>
-__device__ __forceinline__ Jac<F> straus_naf(const Affine<F>* tbl, const FoldComp* comps, int bits) {
-    Jac<F> acc = jac_identity<F>();
-#pragma unroll 1
-    for (int i = bits - 1; i >= 0; i--) {
-        acc = jac_dbl(acc);
-        const uint32_t m = 1u << (i & 31);
-        const int w = i >> 5;
-#pragma unroll 1
-        for (int c = 0; c < NC; c++) {
-            const bool dp = (comps[c].plus[w] & m) != 0, dm = (comps[c].minus[w] & m) != 0;
-            if (dp || dm) {
-                Affine<F> t = tbl[c];
-                if (dm) t.y = f_neg(t.y);
-                acc = jac_add_affine(acc, t);
-            }
-        }
-    }
-    return acc;
-}
-
 __global__ void __launch_bounds__(SIPP_STRAUS_THREADS) k_fold_straus(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, size_t stride, size_t count,
                                                                    const FoldPlan* __restrict__ plans, unsigned g2_blocks) {
     const size_t total = count * h;

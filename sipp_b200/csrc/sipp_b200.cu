@@ -29,6 +29,7 @@ int g_opt_wide_max = 8192;  // pairs per launch up to which the 16-lanes-per-pai
 int g_sm_count = 148;
 int g_opt_fold_straus = 1;     // throughput folds (batched instances, large rounds): 1 = one thread per element, shared doublings
 int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own streams (0 = choose by batch size)
+int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
 
 struct TimedSpan {
@@ -379,6 +380,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_BATCH_KPG_MAX: g_opt_batch_kpg_max = value < 1 ? 1 : value; return SIPP_OK;
         case SIPP_OPT_FOLD_STRAUS: g_opt_fold_straus = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_BATCH_STREAMS: g_opt_batch_streams = value < 0 ? 0 : value; return SIPP_OK;
+        case SIPP_OPT_BATCH_QLINES: g_opt_batch_qlines = value ? 1 : 0; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -395,6 +397,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_BATCH_KPG_MAX: return g_opt_batch_kpg_max;
         case SIPP_OPT_FOLD_STRAUS: return g_opt_fold_straus;
         case SIPP_OPT_BATCH_STREAMS: return g_opt_batch_streams;
+        case SIPP_OPT_BATCH_QLINES: return g_opt_batch_qlines;
         default: return -1;
     }
 }

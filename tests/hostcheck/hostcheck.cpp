@@ -112,3 +112,29 @@ extern "C" int hc_fold_split_g2(const uint8_t* p1, const uint8_t* p2, const uint
     g2_encode(W(out), jac_to_affine(jac_add_affine(acc, b1)));
     return 0;
 }
+
+// shared-doubling fold (k_fold_straus): one accumulator for all components of an element, same plan
+extern "C" int hc_fold_straus_g1(const uint8_t* p1, const uint8_t* p2, const uint8_t* x, const uint8_t* xinv, uint8_t* out) {
+    FoldPlan plan;
+    if (fold_plan_build(x, xinv, &plan)) return -1;
+    G1A a1 = g1_decode(W(p1)), a2 = g1_decode(W(p2)), tbl[2];
+    for (int c = 0; c < 2; c++) {
+        tbl[c] = endo_apply(a2, c);
+        if (plan.g1[c].neg) tbl[c].y = f_neg(tbl[c].y);
+    }
+    Jac<Fq> acc = straus_naf<Fq, 2>(tbl, plan.g1, plan.g1_bits);
+    g1_encode(W(out), jac_to_affine(jac_add_affine(acc, a1)));
+    return 0;
+}
+extern "C" int hc_fold_straus_g2(const uint8_t* p1, const uint8_t* p2, const uint8_t* x, const uint8_t* xinv, uint8_t* out) {
+    FoldPlan plan;
+    if (fold_plan_build(x, xinv, &plan)) return -1;
+    G2A b1 = g2_decode(W(p1)), b2 = g2_decode(W(p2)), tbl[4];
+    for (int c = 0; c < 4; c++) {
+        tbl[c] = endo_apply(b2, c);
+        if (plan.g2[c].neg) tbl[c].y = f_neg(tbl[c].y);
+    }
+    Jac<Fq2> acc = straus_naf<Fq2, 4>(tbl, plan.g2, plan.g2_bits);
+    g2_encode(W(out), jac_to_affine(jac_add_affine(acc, b1)));
+    return 0;
+}

@@ -122,6 +122,11 @@ def test_batch_kpg_variants_and_identity(sipp, oracle):
                 a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
                 assert b"".join(got[j]) == oracle.sipp_prove(a, b, threads=8)
         assert got == want, kpg
+    sipp.set_option(12, 0)  # line coefficients of B recomputed for Z and the first Z_L / Z_R instead of shared
+    try:
+        assert sipp.sipp_prove_native_batch(A, B, n) == want
+    finally:
+        sipp.set_option(12, 1)
     sipp.set_option(10, 0)  # lane-split component fold instead of the shared-doubling (Straus) fold
     try:
         assert sipp.sipp_prove_native_batch(A, B, n) == want

@@ -99,13 +99,13 @@ def test_fold_split(hc, oracle):
         x = le(k)
         cases1 = [(a1, a2), (bytes(64), a2), (a1, bytes(64)), (oracle.g1_mul(a2, x), a2), (oracle.g1_mul(a2, le(R - k)), a2)]
         for p1, p2 in cases1:
-            for fn in (hc.hc_fold_split_g1, hc.hc_fold_wide_g1):  # per-thread components / components on the lane engine
+            for fn in (hc.hc_fold_split_g1, hc.hc_fold_wide_g1, hc.hc_fold_straus_g1):  # per-thread components / lane engine / shared doublings
                 out = _buf(64)
                 assert fn(p1, p2, x, x, out) == 0
                 assert out.raw == oracle.fold_g1(p1 + p2, x)
         cases2 = [(b1, b2), (bytes(128), b2), (b1, bytes(128)), (oracle.g2_mul(b2, x), b2), (oracle.g2_mul(b2, le(R - k)), b2)]
         for p1, p2 in cases2:
-            for fn in (hc.hc_fold_split_g2, hc.hc_fold_wide_g2):
+            for fn in (hc.hc_fold_split_g2, hc.hc_fold_wide_g2, hc.hc_fold_straus_g2):
                 out = _buf(128)
                 assert fn(p1, p2, x, x, out) == 0
                 assert out.raw == oracle.fold_g2(p1 + p2, x)
