@@ -74,7 +74,10 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
         Span sp(0, s);
         for (size_t p0 = 0; p0 < nproducts; p0 += pc) {
             size_t cur = nproducts - p0 < pc ? nproducts - p0 : pc;
-            int e = qlines ? launch_eval_lines_batch(b.dA, b.dB, job, p0, cur, qlines, lines, s) : launch_lines_batch(b.dA, b.dB, job, p0, cur, lines, s);
+            // shared coefficients (Z, first cross products) / 16 lanes per pair for a launch that cannot fill the GPU / one thread per pair
+            int e = qlines ? launch_eval_lines_batch(b.dA, b.dB, job, p0, cur, qlines, lines, s)
+                    : cur * job.h <= (size_t)g_opt_wide_max ? launch_lines_wide_batch(b.dA, b.dB, job, p0, cur, lines, s)
+                                                            : launch_lines_batch(b.dA, b.dB, job, p0, cur, lines, s);
             if (e) return cuda_fail((cudaError_t)e, "k_lines_batch");
             e = launch_accum_batch(lines, cur * job.h, (int)kpg, b.partials, p0 * gpp, s);
             if (e) return cuda_fail((cudaError_t)e, "k_accum(batch)");

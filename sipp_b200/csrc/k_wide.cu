@@ -71,6 +71,45 @@ __global__ void __launch_bounds__(SIPP_WIDE_THREADS) k_lines_wide(const uint32_t
     lp_miller(mach);
 }
 
+// batched instances (launch.h BatchJob): same engine, pair index decomposed as (product, pair) like k_lines_batch -- the late rounds
+// of a batch that does not fill the GPU with one thread per pair (a launch of a few thousand pairs takes the length of the
+// per-thread chain, 1.8 ms, whatever its size; 16 lanes per pair bring it to 0.4 ms)
+__global__ void __launch_bounds__(SIPP_WIDE_THREADS) k_lines_wide_batch(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, BatchJob job, size_t p0,
+                                                                       size_t np, uint32_t* __restrict__ lines) {
+    __shared__ __align__(16) uint32_t smem[SIPP_WIDE_GROUPS * SIPP_LP_SLOTS * 8];
+    __shared__ int ident_flag[SIPP_WIDE_GROUPS];
+    const int group = threadIdx.x / SIPP_LP_LANES, lane = threadIdx.x % SIPP_LP_LANES;
+    const size_t total = np * job.h;
+    size_t t = (size_t)blockIdx.x * SIPP_WIDE_GROUPS + group;
+    const bool valid = t < total;
+    if (!valid) t = total - 1;  // surplus groups shadow the last pair (uniform control flow), nothing is stored
+    const size_t P = p0 + t / job.h, i = t % job.h;
+    const size_t inst = P / (size_t)job.nprod;
+    const int y = (int)(P % (size_t)job.nprod);
+    const size_t base = inst * job.stride + i;
+    uint32_t* slots = smem + group * (SIPP_LP_SLOTS * 8);
+    if (lane == 0) {
+        const G1A p = load_g1(A, base + job.a_off[y]);
+        const G2A q = load_g2(B, base + job.b_off[y]);
+        ident_flag[group] = (affine_is_identity(p) || affine_is_identity(q)) ? 1 : 0;
+        lp_fill_fixed(slots, p.x, p.y, q.x, q.y);
+    }
+    __syncwarp();
+    DevMachine mach;
+    mach.slots = slots;
+    mach.out = lines + t * (size_t)(SIPP_LINES_PER_PAIR * SIPP_LINE_WORDS);
+    mach.lane = lane;
+    mach.store = valid;
+    mach.ident = ident_flag[group] != 0;
+    lp_miller(mach);
+}
+
+int launch_lines_wide_batch(const uint32_t* A, const uint32_t* B, const BatchJob& job, size_t p0, size_t np, uint32_t* lines, cudaStream_t s) {
+    const size_t groups = np * job.h;
+    k_lines_wide_batch<<<(unsigned)((groups + SIPP_WIDE_GROUPS - 1) / SIPP_WIDE_GROUPS), SIPP_WIDE_THREADS, 0, s>>>(A, B, job, p0, np, lines);
+    return (int)cudaGetLastError();
+}
+
 int launch_lines_wide(const uint32_t* A, const uint32_t* B, const MillerJob& job, int nprod, size_t c0, size_t mc, uint32_t* lines, cudaStream_t s) {
     const size_t groups = mc * (size_t)nprod;
     k_lines_wide<<<(unsigned)((groups + SIPP_WIDE_GROUPS - 1) / SIPP_WIDE_GROUPS), SIPP_WIDE_THREADS, 0, s>>>(A, B, job, nprod, c0, mc, lines);
