@@ -484,7 +484,21 @@ int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
     {
         Span sp(2, g_stream);
         // new_A = a1 + a2.mul(x)  prover_native.rs:60-64;  new_B = b1 + b2.mul(inv_x)  :65-69
-        int e = h <= (size_t)g_opt_wide_fold_max ? launch_fold_wide(c->dA, c->dB, h, plan, g_stream) : launch_fold(c->dA, c->dB, h, plan, g_stream);
+        int e;
+        if (g_opt_fold_straus && h >= 16384) {
+            // a launch that fills the GPU: one thread per element, doublings shared by the components (k_fold_straus reads the plan
+            // from device memory: the batched prover has one per instance)
+            static FoldPlan* d_plan = nullptr;
+            static int d_plan_dev = -1;
+            if (d_plan_dev != g_device) {
+                CK(cudaMalloc(&d_plan, sizeof(FoldPlan)));
+                d_plan_dev = g_device;
+            }
+            CK(cudaMemcpyAsync(d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice, g_stream));  // pageable source: staged before the call returns
+            e = launch_fold_straus(c->dA, c->dB, h, c->n, 1, d_plan, g_stream);
+        } else {
+            e = h <= (size_t)g_opt_wide_fold_max ? launch_fold_wide(c->dA, c->dB, h, plan, g_stream) : launch_fold(c->dA, c->dB, h, plan, g_stream);
+        }
         if (e) return cuda_fail((cudaError_t)e, "k_fold");
     }
     g_stats.launches += 1;

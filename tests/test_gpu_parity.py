@@ -375,3 +375,35 @@ def test_bls_aggregation_shape(sipp, oracle, golden):
     assert b"".join(proof) == oracle.sipp_prove(A2, B2, threads=8)
     # a forged aggregate (one message signed with the wrong key) is not the identity
     assert sipp.inner_product(A2, B + oracle.g2_mul(g2, le((s + 1) % R))) != ONE12
+
+
+def test_fold_large_round_straus_vs_split(sipp, oracle):
+    """a round large enough for the throughput fold (k_fold_straus, h >= 16384): same bytes as the lane-split kernel, a sample of
+    elements against the oracle's plain double-and-add, exceptional points included"""
+    n = 1 << 15
+    rng = random.Random(8)
+    A, B = sipp.seeded_inputs(12, n)
+    x = le(rng.randrange(1, R)); xinv = oracle.fr_inverse(x)
+    A = bytearray(A); B = bytearray(B)
+    h = n // 2
+    A[64 * 5:64 * 6] = bytes(64)                                   # A1[5] = O
+    B[128 * (h + 7):128 * (h + 8)] = bytes(128)                    # B2[7] = O
+    A[64 * 9:64 * 10] = oracle.g1_mul(bytes(A[64 * (h + 9):64 * (h + 10)]), x)                                   # doubling case
+    B[128 * 11:128 * 12] = oracle.g2_mul(bytes(B[128 * (h + 11):128 * (h + 12)]), le(R - int.from_bytes(xinv, "little")))  # sum = O
+    A, B = bytes(A), bytes(B)
+    outs = []
+    for straus in (1, 0):
+        sipp.set_option(10, straus)
+        try:
+            ctx = sipp.ProverContext(A, B)
+            ctx.fold(x, xinv)
+            outs.append(ctx.read())
+            ctx.close()
+        finally:
+            sipp.set_option(10, 1)
+    assert outs[0] == outs[1]
+    fa, fb = outs[0]
+    assert fb[128 * 11:128 * 12] == bytes(128)
+    for i in (0, 5, 7, 9, 11, 123, h - 1):
+        assert fa[64 * i:64 * i + 64] == oracle.fold_g1(A[64 * i:64 * i + 64] + A[64 * (h + i):64 * (h + i) + 64], x), i
+        assert fb[128 * i:128 * i + 128] == oracle.fold_g2(B[128 * i:128 * i + 128] + B[128 * (h + i):128 * (h + i) + 128], xinv), i

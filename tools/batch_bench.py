@@ -70,10 +70,17 @@ def main():
     for j in (0, count // 2, count - 1):
         a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
         assert proofs[j * plen * 384:(j + 1) * plen * 384] == b"".join(sipp_b200.sipp_prove_native(a, b)), j
+    # batched verifier on the same proofs (host buffers in, one result per instance out)
+    res = (ctypes.c_int * count)()
+    lib.sipp_verify_native_batch(A, B, n, count, out.raw, plen, res, None, None, None)
+    t0 = time.perf_counter()
+    _lib.check(lib.sipp_verify_native_batch(A, B, n, count, out.raw, plen, res, None, None, None))
+    t_ver = time.perf_counter() - t0
+    assert all(r == 0 for r in res), "a valid proof failed the batched verifier"
     loops = count * (3 * n - 2)
     print(json.dumps({"count": count, "n": n, "steps": steps, "kpg_max": kpg or 32, "streams": streams,
                       "resident_s": t_res, "instances_per_s": count / t_res, "pairs_per_s": total / t_res,
-                      "e2e_s": t_e2e, "e2e_instances_per_s": count / t_e2e,
+                      "e2e_s": t_e2e, "e2e_instances_per_s": count / t_e2e, "verify_batch_s": t_ver, "verified_per_s": count / t_ver,
                       "miller_ms": st["miller_ms"] / steps, "fe_ms": st["reduce_fe_ms"] / steps, "fold_ms": st["fold_ms"] / steps,
                       "other_ms(decode+transcript)": st["other_ms"] / steps, "launches": st["launches"] // steps,
                       "miller_loops_per_s": loops / (st["miller_ms"] / steps * 1e-3),
