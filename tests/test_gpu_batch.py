@@ -231,3 +231,19 @@ def test_batch_degenerate_shapes(sipp, oracle):
     assert got[1] == sipp.sipp_prove_native(Az[64 * 4:], Bz[128 * 4:])
     sts = sipp.sipp_verify_native_batch(Az, Bz, 4, got)
     assert all(not isinstance(s, Exception) for s in sts)
+
+
+def test_batch_random_shapes(sipp):
+    """random (n, count) shapes, counts that are not powers of two: every instance of the batch == the single-instance prover"""
+    rng = random.Random(2026)
+    for trial in range(8):
+        n = 1 << rng.randrange(0, 6)
+        count = rng.randrange(1, 12)
+        A, B = sipp.seeded_inputs(1000 + trial, n * count)
+        proofs = sipp.sipp_prove_native_batch(A, B, n)
+        assert len(proofs) == count
+        for j in range(count):
+            a, b = A[64 * n * j:64 * n * (j + 1)], B[128 * n * j:128 * n * (j + 1)]
+            assert proofs[j] == sipp.sipp_prove_native(a, b), (n, count, j)
+        sts = sipp.sipp_verify_native_batch(A, B, n, proofs)
+        assert all(not isinstance(s, Exception) for s in sts), (n, count)
