@@ -238,6 +238,117 @@ __global__ void __launch_bounds__(SIPP_WIDE_THREADS) k_fold_wide(uint32_t* __res
     }
 }
 
+// batched instances: the plan is read per instance (plans[inst]); otherwise as k_fold_wide
+__global__ void __launch_bounds__(SIPP_WIDE_THREADS) k_fold_wide_batch(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, size_t stride, size_t count,
+                                                                      const FoldPlan* __restrict__ plans, unsigned g2_blocks) {
+    __shared__ __align__(16) uint32_t smem[SIPP_WIDE_GROUPS * SIPP_LP_SLOTS * 8];
+    __shared__ __align__(16) uint32_t xch[SIPP_WIDE_GROUPS * 48];  // one Jacobian point per group (G2: 48 words, G1: 24)
+    // the two groups of a warp must run the same digit schedule: they take two elements of the SAME instance (h >= 2: h is even
+    // and element pairs start at even indices), or the same element twice when an instance has a single element left (h == 1)
+    const size_t total = count * h;
+    const int epw = h >= 2 ? 2 : 1;
+    const int warp = threadIdx.x >> 5, group = threadIdx.x / SIPP_LP_LANES, lane = threadIdx.x % SIPP_LP_LANES, gi = group & 1;
+    uint32_t* slots = smem + group * (SIPP_LP_SLOTS * 8);
+    DevMachine mach;
+    mach.slots = slots; mach.out = nullptr; mach.lane = lane; mach.store = false; mach.ident = false;
+    if (blockIdx.x < g2_blocks) {
+        const int comp = warp;                       // 4 warps = 4 GLS components, 2 elements per block
+        size_t E = (size_t)blockIdx.x * epw + (gi % epw);
+        const bool valid = E < total && gi < epw;
+        if (E >= total) E = total - 1;
+        const size_t inst = E / h, e = inst * stride + E % h;
+        const FoldPlan& plan = plans[inst];
+        const FoldDigits d = fold_digits(plan.g2[comp], plan.g2_bits);
+        bool ident = false;
+        if (lane == 0) {
+            G2A q = load_g2(B, e + h);
+            ident = affine_is_identity(q);
+            q = endo_apply(q, comp);
+            if ((plan.g2[comp].neg != 0) != d.flip) q.y = fq2_neg(q.y);
+            lp_fill_fixed(slots, fq_zero(), fq_zero(), q.x, q.y);
+        }
+        __syncwarp();
+        if (d.top >= 0) {
+            mach.run(SIPP_LP_SETUP_FIRST, SIPP_LP_SETUP_LEVELS);
+            lp_scalar_mul(mach, true, d.plus, d.minus, d.top);
+        }
+        if (lane == 0) {
+            Jac<Fq2> r = jac_identity<Fq2>();
+            if (!ident && d.top >= 0) {
+                const Fq2 X{lp_load(slots, SIPP_LP_SLOT_X0), lp_load(slots, SIPP_LP_SLOT_X1)}, Y{lp_load(slots, SIPP_LP_SLOT_Y0), lp_load(slots, SIPP_LP_SLOT_Y1)};
+                const Fq2 Z = fq2_mul_xi(Fq2{lp_load(slots, SIPP_LP_SLOT_ZH0), lp_load(slots, SIPP_LP_SLOT_ZH1)});
+                r.x = fq2_mul(X, Z);                 // homogeneous (X : Y : Z)  ->  Jacobian (X Z, Y Z^2, Z)
+                r.y = fq2_mul(Y, fq2_sqr(Z));
+                r.z = Z;
+            }
+            uint32_t* o = xch + group * 48;
+            store_words(o, r.x.c0); store_words(o + 8, r.x.c1); store_words(o + 16, r.y.c0); store_words(o + 24, r.y.c1);
+            store_words(o + 32, r.z.c0); store_words(o + 40, r.z.c1);
+        }
+        __syncthreads();
+        if (warp == 0 && lane == 0) {
+            Jac<Fq2> acc;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t* o = xch + ((j * 2 + gi) * 48);   // group of component j, element gi
+                Jac<Fq2> t;
+                t.x = Fq2{load_words(o), load_words(o + 8)}; t.y = Fq2{load_words(o + 16), load_words(o + 24)}; t.z = Fq2{load_words(o + 32), load_words(o + 40)};
+                acc = j ? jac_add(acc, t) : t;
+            }
+            const G2A r = jac_to_affine(jac_add_affine(acc, load_g2(B, e)));
+            if (valid) store_g2(B, e, r);
+        }
+    } else {
+        const int comp = warp & 1, pair = warp >> 1;  // warps (0,1) and (2,3): the two GLV components of 2 x 2 elements
+        size_t E = (size_t)(blockIdx.x - g2_blocks) * (2 * epw) + pair * epw + (gi % epw);
+        const bool valid = E < total && gi < epw;
+        if (E >= total) E = total - 1;
+        const size_t inst = E / h, e = inst * stride + E % h;
+        const FoldPlan& plan = plans[inst];
+        const FoldDigits d = fold_digits(plan.g1[comp], plan.g1_bits);
+        bool ident = false;
+        if (lane == 0) {
+            G1A q = load_g1(A, e + h);
+            ident = affine_is_identity(q);
+            q = endo_apply(q, comp);
+            if ((plan.g1[comp].neg != 0) != d.flip) q.y = fq_neg(q.y);
+            lp_store(slots, SIPP_LP_SLOT_ZERO, fq_zero());
+            lp_store(slots, SIPP_LP_SLOT_QX0, q.x); lp_store(slots, SIPP_LP_SLOT_QY0, q.y);
+            lp_store(slots, SIPP_LP_SLOT_X1, q.x); lp_store(slots, SIPP_LP_SLOT_Y1, q.y); lp_store(slots, SIPP_LP_SLOT_Z1, fq_one());
+        }
+        __syncwarp();
+        if (d.top >= 0) lp_scalar_mul(mach, false, d.plus, d.minus, d.top);
+        if (lane == 0) {
+            Jac<Fq> r = jac_identity<Fq>();
+            if (!ident && d.top >= 0) {
+                const Fq X = lp_load(slots, SIPP_LP_SLOT_X1), Y = lp_load(slots, SIPP_LP_SLOT_Y1), Z = lp_load(slots, SIPP_LP_SLOT_Z1);
+                r.x = fq_mul(X, Z);
+                r.y = fq_mul(Y, fq_sqr(Z));
+                r.z = Z;
+            }
+            uint32_t* o = xch + group * 48;
+            store_words(o, r.x); store_words(o + 8, r.y); store_words(o + 16, r.z);
+        }
+        __syncthreads();
+        if (comp == 0 && lane == 0) {
+            Jac<Fq> acc, t;
+            const uint32_t* o0 = xch + group * 48;              // component 0 of this element
+            const uint32_t* o1 = xch + (group + 2) * 48;        // component 1: next warp, same group-in-warp
+            acc.x = load_words(o0); acc.y = load_words(o0 + 8); acc.z = load_words(o0 + 16);
+            t.x = load_words(o1); t.y = load_words(o1 + 8); t.z = load_words(o1 + 16);
+            acc = jac_add(acc, t);
+            const G1A r = jac_to_affine(jac_add_affine(acc, load_g1(A, e)));
+            if (valid) store_g1(A, e, r);
+        }
+    }
+}
+
+
+int launch_fold_wide_batch(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t count, const FoldPlan* plans, cudaStream_t s) {
+    const size_t total = count * h, epw = h >= 2 ? 2 : 1;
+    const unsigned g2_blocks = (unsigned)((total + epw - 1) / epw), g1_blocks = (unsigned)((total + 2 * epw - 1) / (2 * epw));
+    k_fold_wide_batch<<<g2_blocks + g1_blocks, SIPP_WIDE_THREADS, 0, s>>>(A, B, h, stride, count, plans, g2_blocks);
+    return (int)cudaGetLastError();
+}
 int launch_fold_wide(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s) {
     const unsigned g2_blocks = (unsigned)((h + 1) / 2), g1_blocks = (unsigned)((h + 3) / 4);
     k_fold_wide<<<g2_blocks + g1_blocks, SIPP_WIDE_THREADS, 0, s>>>(A, B, h, plan, g2_blocks);
