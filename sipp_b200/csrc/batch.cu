@@ -88,7 +88,10 @@ int batch_products(const BatchBuffers& b, size_t stride, size_t count, size_t m,
     g_stats.miller_pairs += nproducts * job.h;
     {
         Span sp(1, s);
-        int e = launch_fe_batch(b.partials, nproducts, (int)gpp, job.nprod, fe_out, np * 96, slot0, slot1, g_opt_fe_norm, s);
+        // one 32-lane machine per product while they all fit the GPU at once (3 blocks x 4 machines per SM), 6-lane groups beyond
+        int e = (g_opt_fe_engine && nproducts <= (size_t)g_sm_count * 12)
+                    ? launch_fe_batch_eng(b.partials, nproducts, (int)gpp, job.nprod, fe_out, np * 96, slot0, slot1, g_opt_fe_norm, s)
+                    : launch_fe_batch(b.partials, nproducts, (int)gpp, job.nprod, fe_out, np * 96, slot0, slot1, g_opt_fe_norm, s);
         if (e) return cuda_fail((cudaError_t)e, "k_fe_batch");
     }
     g_stats.launches++;
