@@ -5,6 +5,7 @@
 // (BASELINE config "4096 independent n=128 SIPP instances").  Each instance is exactly sipp_prove_native (prover_native.rs:26-80);
 // what changes is where the glue runs: one transcript chain per instance on the device (k_transcript.cu), per-instance fold
 // plans, segmented products.  Nothing returns to the host between the upload and the proofs.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -151,10 +152,15 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         for (int k = 0; k < 8; k++) CK(cudaStreamCreateWithFlags(&g_sub_streams[k], cudaStreamNonBlocking));
         g_sub_streams_dev = g_device;
     }
-    CK(order_after(side, s));
+    // small batches: the chains are latency-bound and slow down several times when they share the SMs with the Miller kernels,
+    // which then wait for them at the first challenge -- run them first, alone (SIPP_BATCH_ABSORB=side|inline overrides)
+    static const char* absorb_env = getenv("SIPP_BATCH_ABSORB");
+    const bool absorb_inline = absorb_env ? absorb_env[0] == 'i' : total < ((size_t)1 << 18);
+    cudaStream_t absorb_stream = absorb_inline ? s : side;
+    if (!absorb_inline) CK(order_after(side, s));
     {
-        Span sp(3, side);
-        int e = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, side);
+        Span sp(3, absorb_stream);
+        int e = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, absorb_stream);
         if (e) return cuda_fail((cudaError_t)e, "k_tr_absorb_pairs");
         g_stats.launches++;
     }
@@ -200,7 +206,7 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
             const int slot_l = (int)np - 2 * round, slot_r = (int)np - 1 - 2 * round;  // proof.reverse()  :78
             rc = batch_products(v, n, c, m, 1, v.proofs, np, slot_l, slot_r, lines, slice, round == 1 ? ql : nullptr, sk);  // :46-49
             if (rc) return rc;
-            if (round == 1) CK(order_after(sk, side));
+            if (round == 1 && !absorb_inline) CK(order_after(sk, side));
             {
                 Span sp(3, sk);
                 int e = launch_tr_round(v.states, v.proofs, np, round == 1 ? (int)np - 1 : -1, slot_l, slot_r, g_opt_fq12_order, c, v.plans, nullptr,
