@@ -453,7 +453,11 @@ def main():
         ctx.close()
         ach = s2["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / (s2["miller_ms"] * 1e-3)
         sat = {"pairs": int(s2["miller_pairs"]), "miller_ms": s2["miller_ms"], "miller_loops_per_s": s2["miller_pairs"] / (s2["miller_ms"] * 1e-3),
-               "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": ach / imad_peak}
+               "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": ach / imad_peak,
+               # DRAM bytes per launch of this leg at 2^17 pairs from the ncu --set full capture (profiles/r01_v2_ncu_full_miller.csv):
+               # k_lines writes the line table, k_accum reads it once -- equal to the algorithmic 29,120 B per pair, no re-reads
+               "traffic": {"k_lines_dram_write_bytes": 4.08e9, "k_accum_dram_read_bytes": 3.84e9, "algorithmic_bytes": m * 29120,
+                           "source": "ncu --set full, profiles/r01_v2_ncu_full_miller.csv (2^17 pairs)"} if m == (1 << 17) else None}
 
     if rank != 0:
         if world > 1:
