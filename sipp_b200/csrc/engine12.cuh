@@ -65,14 +65,18 @@ SIPP_HD bool f12_eval(int type, const F12Ins& ins, const uint32_t* slots, const 
 #define F12_OP3(mc, NAME, d, a, b) (mc).run(SIPP_F12_##NAME##_FIRST, SIPP_F12_##NAME##_LEVELS, d, a, b)
 #define F12_OP2(mc, NAME, d, a) (mc).run(SIPP_F12_##NAME##_FIRST, SIPP_F12_##NAME##_LEVELS, d, a, a)
 
-// d = a^x for the BN parameter x (a in the cyclotomic subgroup); d != a
+// d = a^x for the BN parameter x (a in the cyclotomic subgroup); d != a.  The 62 squarings and 27 products are chain links
+// (CSQRX / MUL12X): the xi-multiples an operation reads are left behind by the closing LIN level of the previous one (and
+// once for the base by XI6), so every link is two levels -- products, closing LIN -- instead of three.  The three
+// exponentiations are 60 % of the levels of a final exponentiation, and a LIN level costs a third of a squaring's products.
 template <class M>
 SIPP_HD void f12_exp_x(M& mc, int d, int a) {
-    F12_OP2(mc, COPY, d, a);
+    F12_OP2(mc, XI6, a, a);
+    F12_OP2(mc, COPYX, d, a);
     const unsigned long long x = SIPP_BN_X;
     for (int b = 61; b >= 0; b--) {
-        F12_OP2(mc, CSQR, d, d);
-        if ((x >> b) & 1ull) F12_OP3(mc, MUL12, d, d, a);
+        F12_OP2(mc, CSQRX, d, d);
+        if ((x >> b) & 1ull) F12_OP3(mc, MUL12X, d, d, a);
     }
 }
 

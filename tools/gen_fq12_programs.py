@@ -76,12 +76,22 @@ def reg2(r, k, xi=False):
     return (f(r, k, 0), f(r, k, 1))
 
 
-def emit_mul12(p, d, a, b):
-    """d = a * b (dense):  c_k = sum_{i<=k} a_i b_{k-i} + xi sum_{i>k} a_i b_{k-i+6}"""
+def xi_of_sum(dst, srcs):
+    """dst (an Fq2 slot pair) = xi * sum_j c_j src_j for at most two (c_j, src_j) Fq2 sources: two LIN ops of four terms"""
+    assert len(srcs) <= 2
+    return [(dst[0], [(9 * c, s[0]) for c, s in srcs] + [(-c, s[1]) for c, s in srcs]),
+            (dst[1], [(c, s[0]) for c, s in srcs] + [(9 * c, s[1]) for c, s in srcs])]
+
+
+def emit_mul12(p, d, a, b, pre=True, post_xi=False):
+    """d = a * b (dense):  c_k = sum_{i<=k} a_i b_{k-i} + xi sum_{i>k} a_i b_{k-i+6}.
+    pre = False: the xi-multiples of b are already in its xi slots; post_xi: also leave xi * d_3..5 in d's xi slots (what a
+    following cyclotomic squaring of d reads), so that chains of squarings and products need no LIN level of their own"""
     ops = []
-    for k in range(6):
-        ops += xi_lin(reg2(b, k, True), reg2(b, k))
-    p.lin(ops)
+    if pre:
+        for k in range(6):
+            ops += xi_lin(reg2(b, k, True), reg2(b, k))
+        p.lin(ops)
     ops = []
     for h in range(2):
         for k in range(6):
@@ -96,7 +106,11 @@ def emit_mul12(p, d, a, b):
                     terms += fq2_mul_terms(reg2(a, i), reg2(b, j, wrapped), c)
                 ops.append((H(h * 12 + 2 * k + c), terms))
     p.dot(6, ops)
-    p.lin([(val(d, k, c), [(1, H(2 * k + c)), (1, H(12 + 2 * k + c))]) for k in range(6) for c in range(2)])
+    ops = [(val(d, k, c), [(1, H(2 * k + c)), (1, H(12 + 2 * k + c))]) for k in range(6) for c in range(2)]
+    if post_xi:
+        for k in range(3, 6):
+            ops += xi_of_sum(reg2(d, k, True), [(1, (H(2 * k), H(2 * k + 1))), (1, (H(12 + 2 * k), H(12 + 2 * k + 1)))])
+    p.lin(ops)
 
 
 def build_mul12():
@@ -105,15 +119,42 @@ def build_mul12():
     return p
 
 
-def build_csqr():
-    """Granger-Scott squaring in the cyclotomic subgroup, D = A^2 (tower.cuh fq12_cyc_sqr):
+def build_mul12x():
+    """link of an exponentiation chain: D = A * B with B's xi slots valid on entry, D's xi slots 3..5 valid on exit"""
+    p = Program("MUL12X")
+    emit_mul12(p, "D", "A", "B", pre=False, post_xi=True)
+    return p
+
+
+def build_xi6():
+    """xi slots of D <- xi * D (all six coefficients): what MUL12X expects of its second operand"""
+    p = Program("XI6")
+    ops = []
+    for k in range(6):
+        ops += xi_lin(reg2("D", k, True), reg2("D", k))
+    p.lin(ops)
+    return p
+
+
+def build_copyx():
+    """D <- A including the xi slots"""
+    p = Program("COPYX")
+    p.lin([(("D", j), [(1, ("A", j))]) for j in range(24)])
+    return p
+
+
+def build_csqr(fused=False):
+    """fused = True (CSQRX): link of an exponentiation chain -- A's xi slots 3..5 are valid on entry (no LIN level before the
+    products) and D's are valid on exit (six more outputs of the closing LIN level).
+    Granger-Scott squaring in the cyclotomic subgroup, D = A^2 (tower.cuh fq12_cyc_sqr):
        pairs (a, b) = (g_k, g_{k+3}): t0 = a^2 + xi b^2, ab = a b;  r0 = 3 t0(0) - 2 g0, r3 = 6 ab(0) + 2 g3,
        r1 = 6 xi ab(2) + 2 g1, r4 = 3 t0(2) - 2 g4, r2 = 3 t0(1) - 2 g2, r5 = 6 ab(1) + 2 g5"""
-    p = Program("CSQR")
+    p = Program("CSQRX" if fused else "CSQR")
     ops = []
-    for k in range(3):
-        ops += xi_lin(reg2("A", k + 3, True), reg2("A", k + 3))
-    p.lin(ops)
+    if not fused:
+        for k in range(3):
+            ops += xi_lin(reg2("A", k + 3, True), reg2("A", k + 3))
+        p.lin(ops)
     ops = []
     for k in range(3):
         a, b, xb = reg2("A", k), reg2("A", k + 3), reg2("A", k + 3, True)
@@ -133,6 +174,10 @@ def build_csqr():
     x = xi_lin((val("D", 1, 0), val("D", 1, 1)), ab(2), 6)
     ops.append((x[0][0], x[0][1] + [(2, val("A", 1, 0))]))
     ops.append((x[1][0], x[1][1] + [(2, val("A", 1, 1))]))
+    if fused:
+        ops += xi_of_sum(reg2("D", 3, True), [(6, ab(0)), (2, reg2("A", 3))])
+        ops += xi_of_sum(reg2("D", 4, True), [(3, t0(2)), (-2, reg2("A", 4))])
+        ops += xi_of_sum(reg2("D", 5, True), [(6, ab(1)), (2, reg2("A", 5))])
     p.lin(ops)
     return p
 
@@ -290,6 +335,20 @@ def self_check(progs):
     mc.set12("R1", cyc)
     mc.run(progs["CSQR"], "R1", "R1")
     assert mc.get12("R1") == m.f12_sqr(cyc)
+    # exponentiation chain links: XI6 / COPYX once, then CSQRX / MUL12X without LIN levels of their own
+    mc.set12("R7", cyc)
+    mc.run(progs["XI6"], "R7", "R7")
+    mc.run(progs["COPYX"], "R8", "R7")
+    want = cyc
+    for step in range(9):
+        mc.run(progs["CSQRX"], "R8", "R8")
+        want = m.f12_sqr(want)
+        assert mc.get12("R8") == want, step
+        if step % 3 != 1:
+            mc.run(progs["MUL12X"], "R8", "R8", "R7")
+            want = m.f12_mul(want, cyc)
+            assert mc.get12("R8") == want, step
+    assert mc.get12("R7") == cyc
     return True
 
 
@@ -303,7 +362,7 @@ def enc_slot(s):
 
 
 def emit(progs, path):
-    order = ["MUL12", "CSQR", "FROB1", "FROB2", "FROB3", "CONJ", "COPY", "INV12", "SPARSE"]
+    order = ["MUL12", "CSQR", "FROB1", "FROB2", "FROB3", "CONJ", "COPY", "INV12", "SPARSE", "MUL12X", "CSQRX", "XI6", "COPYX"]
     code, types, index = [], [], {}
     dump = ("G", 63)  # idle lanes write X(2), which no program reads
     for name in order:
@@ -362,7 +421,8 @@ def emit(progs, path):
 
 def main():
     progs = {"MUL12": build_mul12(), "CSQR": build_csqr(), "FROB1": build_frob(1), "FROB2": build_frob(2), "FROB3": build_frob(3),
-             "CONJ": build_conj(), "COPY": build_copy(), "INV12": build_inv12(), "SPARSE": build_sparse()}
+             "CONJ": build_conj(), "COPY": build_copy(), "INV12": build_inv12(), "SPARSE": build_sparse(),
+             "MUL12X": build_mul12x(), "CSQRX": build_csqr(fused=True), "XI6": build_xi6(), "COPYX": build_copyx()}
     if "--check" in sys.argv:
         self_check(progs)
         print("self-check against the model: ok")
