@@ -159,12 +159,13 @@ def build_add(name, q, sign):
 
 def build_dbl1():
     """G1 (y^2 = x^3 + 3 over Fq), T <- 2T (x4) in homogeneous projective coordinates (X1, Y1, Z1):
-         b = Y^2, c = Z^2, e = 3 b Z^2 = 9c, f = 3e ; X' = 2 XY (b - f), Y' = (b + f)^2 - 12 e^2, Z' = 8 b (YZ)"""
+         b = Y^2, c = Z^2, e = 3 b Z^2 = 9c, f = 3e ; X' = 2 XY (b - f), Y' = (b + f)^2 - 12 e^2, Z' = 8 b (YZ)
+       expanded so that no linear level sits between the two product levels (the G1 components are the longest chain of
+       k_fold_wide: 128 doublings):  X' = 2 (XY b) - 54 (XY c),  Y' = b^2 + 54 bc - 243 c^2,  Z' = 8 b (YZ)"""
     p = Program("DBL1")
     p.mul1([("XY1", "X1", "Y1"), ("B1", "Y1", "Y1"), ("C1", "Z1", "Z1"), ("YZ1", "Y1", "Z1")])
-    p.lin([("E1", [(9, "C1")]), ("BMF1", [(1, "B1"), (-27, "C1")]), ("BPF1", [(1, "B1"), (27, "C1")])])
-    p.mul1([("E21", "E1", "E1"), ("G21", "BPF1", "BPF1"), ("XN1", "XY1", "BMF1"), ("ZN1", "B1", "YZ1")])
-    p.lin([("X1", [(2, "XN1")]), ("Y1", [(1, "G21"), (-12, "E21")]), ("Z1", [(8, "ZN1")])])
+    p.mul1([("BB1", "B1", "B1"), ("BC1", "B1", "C1"), ("CC1", "C1", "C1"), ("XYB1", "XY1", "B1"), ("XYC1", "XY1", "C1"), ("BYZ1", "B1", "YZ1")])
+    p.lin([("X1", [(2, "XYB1"), (-54, "XYC1")]), ("Y1", [(1, "BB1"), (54, "BC1"), (-243, "CC1")]), ("Z1", [(8, "BYZ1")])])
     return p
 
 
