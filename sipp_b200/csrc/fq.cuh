@@ -361,7 +361,7 @@ SIPP_HD void limbs_shl1(uint32_t* x) {
     for (int i = 7; i > 0; i--) x[i] = (x[i] << 1) | (x[i - 1] >> 31);
     x[0] <<= 1;
 }
-SIPP_HD_NOINLINE Fq fq_inv(const Fq& a) {
+SIPP_HD_NOINLINE Fq fq_inv_kaliski(const Fq& a) {
     if (fq_is_zero(a)) return fq_zero();  // same convention as a^(p-2)
     const uint32_t P[8] = {SIPP_P0, SIPP_P1, SIPP_P2, SIPP_P3, SIPP_P4, SIPP_P5, SIPP_P6, SIPP_P7};
     uint32_t u[8], v[8], r[8], s[8], t[8];
@@ -404,6 +404,128 @@ SIPP_HD_NOINLINE Fq fq_inv(const Fq& a) {
     }
     x = fq_mul(fq_mul(x, fq_r2()), p1);   // x 2^e1
     return fq_mul(fq_mul(x, fq_r2()), p2);  // x 2^e1 2^e2
+}
+
+// ---- inversion by divsteps (Bernstein-Yang "safegcd", the variable-time form with 30-bit signed limbs) -------------------
+// f = p, g = a, d = 0, e = 1 and the invariants  d a = f,  e a = g  (mod p).  An outer iteration runs 30 divsteps on the low
+// words of f and g alone, collecting a 2x2 transition matrix t with  t (f, g) = 2^30 (f', g'),  and applies t / 2^30 to (f, g)
+// exactly and to (d, e) modulo p.  g reaches 0 after at most 20 outer iterations (19 observed on 10^6 values; 590 divsteps is
+// the proven bound for 256 bits), f = +-1, and a^-1 = +-d.  The binary algorithm above does one 256-bit shift / compare / add per
+// BIT; here the per-bit work is on single words and the 256-bit updates happen once per 30 bits.  Measured in place: fold of an
+// n = 2^12 prove 8.2 -> 7.8 ms (12 launches, one inversion on the chain of each), final exponentiation launch 0.912 -> 0.90 ms.
+// Data-dependent trip counts only (the inner loop strips trailing zeros of g).
+SIPP_HD int fq_ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+SIPP_HD_NOINLINE Fq fq_inv(const Fq& a) {
+    if (fq_is_zero(a)) return fq_zero();  // same convention as a^(p-2)
+    const int32_t M30 = 0x3fffffff;
+    const int32_t PM[9] = {0x187cfd47, 0x3082305b, 0x071ca8d3, 0x205aa45a, 0x01585d97, 0x0116da06, 0x1a029b85, 0x139cb84c, 0x00003064};
+    const uint32_t PINV30 = 0x1b799c77u;  // p^-1 mod 2^30
+    int32_t f[9], g[9], d[9], e[9];
+    {   // 8 x 32 bits -> 9 x 30 bits
+        uint64_t acc = 0;
+        int bits = 0, k = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            acc |= (uint64_t)a.l[i] << bits;
+            bits += 32;
+            while (bits >= 30) { g[k++] = (int32_t)(acc & (uint64_t)M30); acc >>= 30; bits -= 30; }
+        }
+        g[k] = (int32_t)acc;  // k == 8
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) { f[i] = PM[i]; d[i] = 0; e[i] = 0; }
+    e[0] = 1;
+    int32_t eta = -1;
+    for (int iter = 0; iter < 24; iter++) {
+        int32_t gz = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) gz |= g[i];
+        if (gz == 0) break;
+        // ---- 30 divsteps on the low words -> t = (u v; q r)
+        uint32_t u = 1, v = 0, q = 0, r = 1, fl = (uint32_t)f[0] | ((uint32_t)f[1] << 30), gl = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
+        int i = 30;
+        for (;;) {
+            const int zeros = fq_ctz32(gl | (0xffffffffu << i));
+            gl >>= zeros; u <<= zeros; v <<= zeros; eta -= zeros; i -= zeros;
+            if (i == 0) break;
+            if (eta < 0) {
+                eta = -eta;
+                uint32_t t;
+                t = fl; fl = gl; gl = 0u - t;
+                t = u; u = q; q = 0u - t;
+                t = v; v = r; r = 0u - t;
+            }
+            gl += fl; q += u; r += v;  // both odd: g even again
+        }
+        // 32-bit factors: every product below is one widening multiply-add (mul.wide.s32), not a 64 x 64 product
+        const int32_t tu = (int32_t)u, tv = (int32_t)v, tq = (int32_t)q, tr = (int32_t)r;
+#define SIPP_W(a, b) ((int64_t)(a) * (int64_t)(b))
+        {   // (d, e) <- t (d, e) / 2^30 mod p, kept in (-2p, p)
+            const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+            int32_t md = ((int32_t)u & sd) + ((int32_t)v & se), me = ((int32_t)q & sd) + ((int32_t)r & se);
+            int64_t cd = SIPP_W(tu, d[0]) + SIPP_W(tv, e[0]), ce = SIPP_W(tq, d[0]) + SIPP_W(tr, e[0]);
+            md -= (int32_t)((PINV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+            me -= (int32_t)((PINV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+            cd += SIPP_W(PM[0], md); ce += SIPP_W(PM[0], me);
+            cd >>= 30; ce >>= 30;
+#pragma unroll
+            for (int k = 1; k < 9; k++) {
+                cd += SIPP_W(tu, d[k]) + SIPP_W(tv, e[k]) + SIPP_W(PM[k], md);
+                ce += SIPP_W(tq, d[k]) + SIPP_W(tr, e[k]) + SIPP_W(PM[k], me);
+                d[k - 1] = (int32_t)cd & M30; cd >>= 30;
+                e[k - 1] = (int32_t)ce & M30; ce >>= 30;
+            }
+            d[8] = (int32_t)cd; e[8] = (int32_t)ce;
+        }
+        {   // (f, g) <- t (f, g) / 2^30 (exact)
+            int64_t cf = SIPP_W(tu, f[0]) + SIPP_W(tv, g[0]), cg = SIPP_W(tq, f[0]) + SIPP_W(tr, g[0]);
+            cf >>= 30; cg >>= 30;
+#pragma unroll
+            for (int k = 1; k < 9; k++) {
+                cf += SIPP_W(tu, f[k]) + SIPP_W(tv, g[k]);
+                cg += SIPP_W(tq, f[k]) + SIPP_W(tr, g[k]);
+                f[k - 1] = (int32_t)cf & M30; cf >>= 30;
+                g[k - 1] = (int32_t)cg & M30; cg >>= 30;
+            }
+            f[8] = (int32_t)cf; g[8] = (int32_t)cg;
+        }
+#undef SIPP_W
+    }
+    // a^-1 = sign(f) d, brought from (-2p, p) to [0, p)
+    auto add_p = [&]() {
+        int32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int32_t t = d[k] + PM[k] + c; d[k] = t & M30; c = t >> 30; }
+        d[8] += PM[8] + c;
+    };
+    if (d[8] < 0) add_p();
+    if (f[8] < 0) {
+        int32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int32_t t = c - d[k]; d[k] = t & M30; c = t >> 30; }
+        d[8] = c - d[8];
+    }
+    if (d[8] < 0) add_p();
+    Fq x;
+    {   // 9 x 30 bits -> 8 x 32 bits
+        uint64_t acc = 0;
+        int bits = 0, k = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            acc |= (uint64_t)(uint32_t)d[i] << bits;
+            bits += 30;
+            if (bits >= 32 && k < 8) { x.l[k++] = (uint32_t)acc; acc >>= 32; bits -= 32; }
+        }
+        if (k < 8) x.l[k] = (uint32_t)acc;
+    }
+    // the input is a Montgomery representative a = A R: a^-1 = A^-1 R^-1, and two products by R^2 give A^-1 R
+    return fq_mul(fq_mul(x, fq_r2()), fq_r2());
 }
 
 }  // namespace sipp
