@@ -33,6 +33,14 @@ sys.path.insert(0, ROOT)
 FQMUL_PER_MILLER = 9008      # 64 x 107 + 27 x 80
 IMAD_PER_FQMUL = 264         # 8x32-bit CIOS Montgomery: 128 product halves + 136 reduction
 PAIRS_PER_GPU = 1 << 12
+# DRAM bytes per launch of the dominant kernels (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full captures
+# under profiles/ (tools/ncu_traffic.sh writes them); None until a capture of the current kernels is committed
+NCU_TRAFFIC = {}
+try:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as _f:
+        NCU_TRAFFIC = json.load(_f)
+except Exception:
+    pass
 
 
 def log2(n):
@@ -120,8 +128,9 @@ def run_reference(args):
         return 0
     n = args.n or PAIRS_PER_GPU * args.gpus
     A, B = o.seeded_inputs(2, n, threads=cores)
-    # bounded sample: one step = one faithful prove of the first `sample_n` pairs (work is linear in n)
-    sample_n = min(n, 512)
+    # one step = one faithful prove of the whole configuration (n = 2^12: ~1.4 s with 16 threads); beyond 2^15 pairs a step is
+    # the first 2^15 pairs (work is linear in n) so that the run stays within minutes
+    sample_n = min(n, 1 << 15)
     As, Bs = A[:64 * sample_n], B[:128 * sample_n]
     for _ in range(args.warmup):
         o.sipp_prove(As[:64 * 32], Bs[:128 * 32], o.FAITHFUL, cores)
@@ -132,14 +141,20 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
     value = sample_n / per_step
+    t0 = time.perf_counter()
+    o.sipp_prove(As[:64 * 128], Bs[:128 * 128], o.FAITHFUL, 1)   # the reference as written is single-threaded
+    single = 128 / (time.perf_counter() - t0)
     line = {"impl": "reference", "metric": "SIPP native prove throughput (pairings aggregated per second)", "value": value,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integer)",
             "data": "synthetic", "config": {"workload": "SIPP native prover, n=%d pairs (CPU restatement of the reference; "
                                                         "no Rust toolchain, see DESIGN.md)" % n, "n": n},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": "faithful prove (one full pairing per pair, naive folds, Poseidon transcript) of the first %d of %d "
-                                       "pairs per step; work is linear in n" % (sample_n, n)},
+                             "sample": ("faithful prove (one full pairing per pair, naive folds, Poseidon transcript) of all %d pairs per step" % n)
+                             if sample_n == n else ("faithful prove of the first %d of %d pairs per step; work is linear in n" % (sample_n, n)),
+                             "same_config": sample_n == n,
+                             "single_thread": {"value": single, "unit": "pairs/s", "cores": 1,
+                                               "sample": "faithful prove of 128 pairs on one thread (the reference itself is single-threaded)"}},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -296,6 +311,79 @@ def run_batch(args, world, rank, local_rank, W, K):
     return 0
 
 
+def golden_large():
+    """oracle digests of the BASELINE configurations (tests/golden/gen_large_digests.py wrote them; committed)"""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "sipp_large.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def measure_large(k, seed, world, rank, local_rank, barrier, all_max, flush):
+    """One BASELINE large configuration (configs[2]: n = 2^16, configs[3]: n = 2^20) through the PUBLIC call with HOST buffers:
+    every rank uploads its strided shard inside the timed region, rank 0 runs the transcript.  One timed prove (plus one
+    warm-up for n <= 2^16), CUDA-event spans on.  The proof is compared with the oracle's digest of the same seeded inputs."""
+    import hashlib
+    import torch
+    import sipp_b200
+    from sipp_b200 import _lib
+    from sipp_b200.sharded import sharded_prove
+    lib = _lib.load()
+    n = 1 << k
+    dA = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    dB = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    t0 = time.perf_counter()
+    _lib.check(lib.sipp_seeded_inputs_device(seed, n, dA.data_ptr(), dB.data_ptr()))   # fixed-base keygen on the GPU (k_seeded_inputs)
+    t_gen = time.perf_counter() - t0
+    Al = dA.view(n, 64)[rank::world].contiguous().cpu().pin_memory()
+    Bl = dB.view(n, 128)[rank::world].contiguous().cpu().pin_memory()
+    A = B = None
+    if rank == 0:
+        A, B = dA.cpu().numpy().tobytes(), dB.cpu().numpy().tobytes()
+    del dA, dB
+    torch.cuda.empty_cache()
+    Alb, Blb = ctypes_ptr(Al), ctypes_ptr(Bl)
+
+    def step():
+        return sharded_prove(Alb, Blb, n, A, B)
+
+    if k <= 16:
+        step()
+    sipp_b200.set_option(_lib.OPT_PROFILE, 1)
+    sipp_b200.stats(reset=True)
+    flush()
+    barrier()
+    t0 = time.perf_counter()
+    proof = step()
+    barrier()
+    dt = all_max(time.perf_counter() - t0)
+    st = sipp_b200.stats(reset=True)
+    sipp_b200.set_option(_lib.OPT_PROFILE, 0)
+    if rank != 0:
+        return None
+    g = golden_large().get("n=2^%d" % k)
+    digest = hashlib.sha256(b"".join(proof)).hexdigest()
+    ok = None
+    if g is not None:
+        assert hashlib.sha256(A).hexdigest() == g["sha256_A"] and hashlib.sha256(B).hexdigest() == g["sha256_B"], "seeded inputs differ from the oracle's"
+        ok = digest == g["sha256_proof"]
+        assert ok, "n = 2^%d proof differs from the oracle digest" % k
+    return {"n": n, "seed": seed, "n_gpus": world, "prove_s": dt, "pairs_per_s": n / dt, "timed": "one prove through host buffers (H2D of every "
+            "rank's shard and D2H of the proof inside), after %s" % ("one warm-up prove" if k <= 16 else "the n = 2^16 run as warm-up"),
+            "h2d_bytes": n * 192, "d2h_bytes": 384 * (2 * k + 1), "sha256_proof": digest,
+            "parity": ("bit-exact: sha256(proof) equals the oracle's digest (tests/golden/sipp_large.json)" if ok else "no golden digest for this size"),
+            "rank0_kernel_ms": {"miller": st["miller_ms"], "reduce_final_exp": st["reduce_fe_ms"], "fold": st["fold_ms"], "other": st["other_ms"]},
+            "host_transcript_exposed_ms": st["transcript_ms"], "miller_pairs_rank0": int(st["miller_pairs"]),
+            "miller_loops_per_s_rank0": st["miller_pairs"] / max(st["miller_ms"] * 1e-3, 1e-12),
+            "input_generation_s": t_gen}
+
+
+def ctypes_ptr(t):
+    import ctypes
+    return ctypes.cast(t.data_ptr(), ctypes.c_char_p)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,7 +399,8 @@ def main():
                          "n=128 instances in lock-step, sharded by instance over the GPUs")
     ap.add_argument("--instances", type=int, default=4096)
     ap.add_argument("--instance-n", type=int, default=128)
-    ap.add_argument("--batch-instances", type=int, default=4096, help="config-5 summary added to the default line at N=1 (0 = skip)")
+    ap.add_argument("--batch-instances", type=int, default=4096, help="config-5 summary added to the default line (0 = skip)")
+    ap.add_argument("--large", default="16,20", help="log2 sizes of the BASELINE large configurations added to the default line ('' = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -321,7 +410,7 @@ def main():
     import torch.distributed as dist
     import sipp_b200
     from sipp_b200 import _lib
-    from sipp_b200.sharded import CudaEngine, shard_points, sharded_prove
+    from sipp_b200.sharded import comm_init_torch, sharded_prove
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -335,14 +424,22 @@ def main():
     n = args.n or PAIRS_PER_GPU * world
     lib = _lib.load()
     _lib.require_gpu_once()
+    if world > 1:
+        comm_init_torch()   # NCCL communicator INSIDE the library (sipp_comm_init); torch only ships the 128-byte unique id
     W, K = (1 if args.quick else max(args.warmup, 3)), args.steps
     if args.workload == "batch":
         return run_batch(args, world, rank, local_rank, W, K)
 
     # ---- synthetic inputs (seeded, generated on the GPU; same stream as the oracle's generator) ----
-    A, B = sipp_b200.seeded_inputs(2, n)
-    A_pin = torch.frombuffer(bytearray(A), dtype=torch.uint8).pin_memory()
-    B_pin = torch.frombuffer(bytearray(B), dtype=torch.uint8).pin_memory()
+    dA = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    dB = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.sipp_seeded_inputs_device(2, n, dA.data_ptr(), dB.data_ptr()))
+    A, B = dA.cpu().numpy().tobytes(), dB.cpu().numpy().tobytes()   # every rank: the single-GPU check below runs on rank 0 only
+    dAl = dA.view(n, 64)[rank::world].contiguous()                   # strided ownership: rank g holds the pairs i = g (mod world)
+    dBl = dB.view(n, 128)[rank::world].contiguous()
+    Al_pin, Bl_pin = dAl.cpu().pin_memory(), dBl.cpu().pin_memory()
+    del dA, dB
+    A0, B0 = (A, B) if rank == 0 else (None, None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def l2_flush():
@@ -353,6 +450,13 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_max(dt):
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return dt
 
     def timed(fn, steps):
         """K steps, each bracketed by barrier + synchronize; L2 flushed between steps outside the timed spans.
@@ -368,49 +472,18 @@ def main():
             res = fn()
             e1.record()
             barrier()
-            dt = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
-            if world > 1:
-                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            total += dt
+            total += all_max(max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3))
         return total, res
 
-    if world == 1:
-        dA = torch.frombuffer(bytearray(A), dtype=torch.uint8).cuda()
-        dB = torch.frombuffer(bytearray(B), dtype=torch.uint8).cuda()
-        plen = lib.sipp_proof_len(n)
+    # one code path for every N: the library's sharded prover (a world of one is sipp_prove_native on one GPU)
+    def step_resident():
+        return sharded_prove(None, None, n, A0, B0, device_ptrs=(dAl.data_ptr(), dBl.data_ptr()))
 
-        def step_resident():
-            ctx = sipp_b200.ProverContext(device_ptrs=(dA.data_ptr(), dB.data_ptr()), n=n)
-            proof = ctx.prove(A, B)
-            ctx.close()
-            return proof
-
-        def step_e2e():
-            # the public call: host buffers in, proof out (H2D of A, B and D2H of results inside)
-            out = ctypes.create_string_buffer(384 * plen)
-            _lib.check(lib.sipp_prove_native(ctypes.c_char_p(A_pin.data_ptr()), n, ctypes.c_char_p(B_pin.data_ptr()), n, out))
-            return out.raw
-        h2d = n * 192
-        d2h = 384 * plen
-    else:
-        eng = CudaEngine(local_rank)
-        Al, Bl = shard_points(A, B, rank, world)
-        dAl = torch.frombuffer(bytearray(Al), dtype=torch.uint8).cuda()
-        dBl = torch.frombuffer(bytearray(Bl), dtype=torch.uint8).cuda()
-        Al_pin = torch.frombuffer(bytearray(Al), dtype=torch.uint8).pin_memory()
-        Bl_pin = torch.frombuffer(bytearray(Bl), dtype=torch.uint8).pin_memory()
-
-        def step_resident():
-            return sharded_prove(eng, None, None, n, A if rank == 0 else None, B if rank == 0 else None,
-                                 device_ptrs=(dAl.data_ptr(), dBl.data_ptr()))
-
-        def step_e2e():
-            return sharded_prove(eng, bytes(Al_pin.numpy().tobytes()), bytes(Bl_pin.numpy().tobytes()), n,
-                                 A if rank == 0 else None, B if rank == 0 else None)
-        h2d = (n // world) * 192
-        d2h = 384 * (2 * log2(n) + 1)
+    def step_e2e():
+        # the public call: host buffers in (pinned), proof out -- H2D of every rank's shard and D2H of the results inside
+        return sharded_prove(ctypes_ptr(Al_pin), ctypes_ptr(Bl_pin), n, A0, B0)
+    h2d = n * 192                       # summed over the ranks (each uploads its n / world pairs)
+    d2h = 384 * (2 * log2(n) + 1)       # rank 0 reads every Z / Z_L / Z_R = the proof
 
     # ---- warm-up, then the timed region (profile spans on: CUDA events around every kernel class) ----
     for _ in range(W):
@@ -453,26 +526,45 @@ def main():
         ctx.close()
         ach = s2["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / (s2["miller_ms"] * 1e-3)
         sat = {"pairs": int(s2["miller_pairs"]), "miller_ms": s2["miller_ms"], "miller_loops_per_s": s2["miller_pairs"] / (s2["miller_ms"] * 1e-3),
-               "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": ach / imad_peak,
-               # DRAM bytes per launch of this leg at 2^17 pairs from the ncu --set full capture (profiles/r01_v2_ncu_full_miller.csv):
-               # k_lines writes the line table, k_accum reads it once -- equal to the algorithmic 29,120 B per pair, no re-reads
-               "traffic": {"k_lines_dram_write_bytes": 4.08e9, "k_accum_dram_read_bytes": 3.84e9, "algorithmic_bytes": m * 29120,
-                           "source": "ncu --set full, profiles/r01_v2_ncu_full_miller.csv (2^17 pairs)"} if m == (1 << 17) else None}
+               "kernels": "k_lines + k_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": ach / imad_peak,
+               "algorithmic_input_bytes": m * 192, "traffic": NCU_TRAFFIC.get("saturated")}
+
+    # ---- the other BASELINE configurations beside the headline (every rank takes part) ----
+    large = []
+    if not args.quick and not args.n:
+        for k in [int(x) for x in args.large.split(",") if x]:
+            r = measure_large(k, {16: 3, 20: 4}.get(k, 7), world, rank, local_rank, barrier, all_max, l2_flush)
+            if r is not None:
+                r["miller_frac_of_imad_peak_rank0"] = r["miller_loops_per_s_rank0"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / imad_peak
+                large.append(r)
+    bm = None
+    if args.batch_instances and not args.quick and not args.n:
+        # BASELINE config 5 beside the headline (one timed step; `--workload batch` is the full bench of that config)
+        bm = measure_batch(args.batch_instances, 128, world, rank, local_rank, 1, 1, barrier, all_max, l2_flush)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    assert b"".join(proof_res) == (proof_e2e if isinstance(proof_e2e, bytes) else b"".join(proof_e2e)), "resident and e2e proofs differ"
+    import hashlib
+    assert b"".join(proof_res) == b"".join(proof_e2e), "resident and e2e proofs differ"
+    parity = None
+    g = golden_large().get("seed2_n=2^%d" % log2(n))
+    if g is not None:
+        assert hashlib.sha256(b"".join(proof_res)).hexdigest() == g["sha256_proof"], "proof differs from the oracle digest"
+        parity = "bit-exact: sha256(proof) equals the oracle's digest (tests/golden/sipp_large.json)"
     if world > 1:
         # the sharded proof must be byte-identical to the single-GPU proof of the same inputs (BASELINE config 3)
         assert b"".join(proof_res) == b"".join(sipp_b200.sipp_prove_native(A, B)), "sharded proof differs from the single-GPU proof"
     value = n * K / t_res
     e2e = n * K / t_e2e
     mill_ach = st["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / max(st["miller_ms"] * 1e-3, 1e-12)
-    roofline = {"bound": "imad", "kernel": "k_miller (optimal-ate Miller loops + block product)", "achieved": mill_ach / 1e12,
-                "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak, "traffic": None,
+    roofline = {"bound": "imad", "kernel": "k_lines / k_lines_wide + k_accum / k_accum_eng (line functions of every pair + accumulation "
+                                           "into the Miller product, rank 0's launches of the timed proves)",
+                "achieved": mill_ach / 1e12,
+                "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak, "traffic": NCU_TRAFFIC.get("headline"),
+                "algorithmic_input_bytes_per_pair": 192, "line_table_bytes_per_pair": 29120,
                 "launches": int(st["miller_launches"]), "avg_launch_ms": st["miller_ms"] / max(1, st["miller_launches"]),
                 "peak_source": "measured in this run (sipp_microbench: max of IMAD, 2 x IMAD.WIDE, lo/hi carry chain, all in "
                                "32x32 product halves/s); MEASURED_PEAKS.json has no integer peak",
@@ -484,11 +576,14 @@ def main():
     line = {"metric": "SIPP native prove throughput (pairings aggregated per second)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": t_res / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integer)", "data": "synthetic",
-            "config": {"workload": "SIPP native prover, n=2^%d pairs, %dxB200%s" % (log2(n), world, "" if world == 1 else " strided shards (2^%d pairs per GPU)" % log2(n // world)),
+            "config": {"workload": "SIPP native prover, n=2^%d pairs, %dxB200%s" % (log2(n), world, "" if world == 1 else " strided shards (2^%d pairs per GPU), "
+                                   "NCCL all-gather of the partial products inside the library" % log2(n // world)),
                        "n": n, "seed": 2, "miller_loops_per_step": miller_loops_per_prove(n), "l2": "flushed between steps (256 MB write)",
-                       "fe_normalisation": "exact", "fq12_transcript_order": "w-basis"},
+                       "fe_normalisation": "exact", "fq12_transcript_order": "w-basis", "parity": parity,
+                       "nccl_version": lib.sipp_comm_nccl_version() if world > 1 else None},
             "prove_s": t_res / K, "miller_loops_per_s_per_gpu": miller_loops_per_prove(n) * K / t_res / world,
-            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / K * 1e3},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / K * 1e3,
+                    "note": "h2d summed over the ranks; rank 0 additionally reads the full host copy of A, B for the transcript (no device traffic)"},
             "gpu_launches": int(st["launches"]), "clocks": clk, "roofline": roofline}
 
     if not args.no_cpu_baseline and world == 1:
@@ -511,14 +606,15 @@ def main():
     if args.quick:
         line["e2e"] = None
         line["config"]["quick"] = "one warm-up step, e2e leg skipped (--quick)"
-    if world == 1 and args.batch_instances and not args.quick:
-        # BASELINE config 5 beside the headline (one timed step; `--workload batch` is the full bench of that config)
-        bm = measure_batch(args.batch_instances, 128, 1, 0, local_rank, 1, 1, barrier, lambda dt: dt, l2_flush)
+    if large:
+        line["baseline_configs"] = large
+    if bm is not None:
         bst = bm["stats"]
-        line["batched_instances"] = {"workload": "%d independent n=128 instances, lock-step, transcripts on the device" % args.batch_instances,
+        line["batched_instances"] = {"workload": "%d independent n=128 instances over %d GPU(s), lock-step, transcripts on the device, instances sharded by "
+                                                 "rank (no collective)" % (args.batch_instances, world),
                                      "instances_per_s": args.batch_instances / bm["t_res"], "e2e_instances_per_s": args.batch_instances / bm["t_e2e"],
                                      "pairs_per_s": args.batch_instances * 128 / bm["t_res"], "ms": bm["t_res"] * 1e3,
-                                     "miller_ms": bst["miller_ms"], "final_exp_ms": bst["reduce_fe_ms"], "fold_ms": bst["fold_ms"],
+                                     "rank0_miller_ms": bst["miller_ms"], "rank0_final_exp_ms": bst["reduce_fe_ms"], "rank0_fold_ms": bst["fold_ms"],
                                      "miller_frac_of_imad_peak": bst["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL
                                      / max(bst["miller_ms"] * 1e-3, 1e-12) / imad_peak}
     print(json.dumps(line))

@@ -35,7 +35,8 @@ typedef enum {
     SIPP_ERR_ZERO_CHALLENGE = -4, /* x.inverse().unwrap()     -- reference panics: prover_native.rs:58 */
     SIPP_ERR_SHORT_PROOF = -5, /* proof.pop().unwrap()        -- reference panics: verifier_native.rs:31,40,42 */
     SIPP_ERR_ENCODING = -6,    /* a field element >= p */
-    SIPP_ERR_VERIFY = -7       /* Err("Verification failed")  -- verifier_native.rs:83 */
+    SIPP_ERR_VERIFY = -7,      /* Err("Verification failed")  -- verifier_native.rs:83 */
+    SIPP_ERR_COMM = -8         /* multi-GPU exchange failed (NCCL missing or in error, host collective callback failed) */
 } sipp_status;
 
 typedef struct sipp_ctx sipp_ctx;
@@ -86,7 +87,7 @@ int sipp_ctx_fold(sipp_ctx *ctx, const uint8_t x[32], const uint8_t x_inv[32]);
 /* current A, B back to the host (final_A / final_B: verifier_native.rs:74-75; every round in tests) */
 int sipp_ctx_read(sipp_ctx *ctx, uint8_t *A_out, uint8_t *B_out);
 
-/* ---- multi-GPU: strided shards exchange 384-byte partial Miller products ------------------------------- */
+/* ---- multi-GPU building blocks (for a host that runs its own exchange; the complete prover is below) ---------------- */
 /* Writes this shard's un-exponentiated partial products (device format, SIPP_PARTIAL_BYTES each) to DEVICE memory
  * `d_out`, on `stream` (a cudaStream_t; NULL = the legacy default stream, the library orders its own non-blocking
  * stream against it with events): 1 partial for `which` = 0 (Z), 2 for `which` = 1 (Z_L, Z_R).
@@ -96,6 +97,56 @@ int sipp_ctx_partial_products(sipp_ctx *ctx, int which, void *d_out, void *strea
 /* product over `count` gathered partial sets (layout [rank][nprod][384 B], DEVICE memory), one final exponentiation
  * per product, results to HOST `out` (nprod x 384 B, boundary format) */
 int sipp_combine_partials(const void *d_partials, int count, int nprod, uint8_t *out, void *stream);
+
+/* ---- multi-GPU prover inside the library: one process per GPU, strided shards, NCCL on the library stream ---------- */
+/* The loop of prover_native.rs:45-75 over `world` ranks.  Rank g holds the pairs i = g (mod world) of A and B
+ * ("strided ownership": a pair and its fold partner i + n/2 stay on one rank while n >= 2 world, so folds never move a
+ * point).  Per round the reduce kernel writes each rank's two 384-byte partial Miller products into its slot of a gather
+ * buffer, ONE in-place ncclAllGather follows on the library stream, rank 0 multiplies the partials, runs one final
+ * exponentiation per product, feeds the Fiat-Shamir transcript (which it alone owns: the chain is serial) and broadcasts
+ * (x, x^-1); when each rank is down to one pair the `world` pairs are gathered to rank 0, which finishes alone.
+ * Call sipp_init(device) first, then ONE of the two sipp_comm_init*; world must be a power of two. */
+#define SIPP_COMM_ID_BYTES 128
+int sipp_comm_get_unique_id(uint8_t id[SIPP_COMM_ID_BYTES]);   /* rank 0: ncclGetUniqueId; ship the bytes to the other ranks */
+int sipp_comm_init(const uint8_t id[SIPP_COMM_ID_BYTES], int rank, int world);   /* ncclCommInitRank on this process's device */
+/* the same protocol over the caller's own fabric: collectives on HOST memory (MPI, gloo, a socket ...).  allgather:
+ * every rank sends `bytes` from `send`, `recv` receives world x bytes in rank order; broadcast: `buf` of `root` to all.
+ * Both return 0 on success.  (Also what the single-GPU tests use to run several ranks on one device.) */
+typedef int (*sipp_allgather_fn)(void *user, const void *send, void *recv, size_t bytes);
+typedef int (*sipp_broadcast_fn)(void *user, void *buf, size_t bytes, int root);
+int sipp_comm_init_host(int rank, int world, sipp_allgather_fn allgather, sipp_broadcast_fn broadcast, void *user);
+int sipp_comm_destroy(void);
+int sipp_comm_rank(void);
+int sipp_comm_world(void);
+int sipp_comm_nccl_version(void);     /* ncclGetVersion of the libnccl bound at run time (dlopen), 0 if there is none */
+/* pub fn sipp_prove_native(A, B) -> Vec<Fq12>   prover_native.rs:26-80, collectively: every rank passes its strided shard
+ * (n / world pairs: A_local[j] = A[j * world + rank]) and the TOTAL n; rank 0 also passes the full A, B (the transcript
+ * absorbs every input point, :36-39) and receives the proof ((2 log2 n + 1) x 384 B, returned order); the other ranks may
+ * pass NULL for A_full, B_full and proof.  Without a communicator this is sipp_prove_native on one GPU. */
+int sipp_prove_native_sharded(const uint8_t *A_local, const uint8_t *B_local, size_t n, const uint8_t *A_full, const uint8_t *B_full,
+                              uint8_t *proof);
+/* same with the shard already resident in HBM (DEVICE pointers, boundary format) */
+int sipp_prove_native_sharded_device(const void *dA_local, const void *dB_local, size_t n, const uint8_t *A_full, const uint8_t *B_full,
+                                     uint8_t *proof);
+/* The protocol loop itself with the compute / exchange side supplied by the caller (the library's own backend is the
+ * CUDA kernels + the communicator above).  Host code only: it needs no GPU, which is how the CPU tests run the loop.
+ * products(which): this rank's partial products of the round (0: Z; 1: Z_L, Z_R) and their all-gather; combine: rank 0,
+ * product over the ranks + one final exponentiation per product -> nprod x 384 B; broadcast: SIPP_SHARD_XS_BYTES from
+ * rank 0 (x || x^-1 || status); fold: A <- A1 + x A2, B <- B1 + x^-1 B2 on the local shard; collapse: gather the last pair
+ * of every rank to rank 0, after which rank 0's products / combine are local.  All return 0 or a negative sipp_status. */
+#define SIPP_SHARD_XS_BYTES 72
+typedef struct sipp_shard_backend {
+    void *user;
+    int rank, world;
+    size_t (*local_len)(void *user);
+    int (*products)(void *user, int which);
+    int (*combine)(void *user, int nprod, uint8_t *out);
+    int (*broadcast)(void *user, uint8_t *xs);
+    int (*fold)(void *user, const uint8_t *x, const uint8_t *x_inv);
+    int (*collapse)(void *user);
+} sipp_shard_backend;
+int sipp_prove_native_sharded_backend(const sipp_shard_backend *backend, size_t n, const uint8_t *A_full, const uint8_t *B_full,
+                                      uint8_t *proof);
 
 /* ---- stand-alone operations --------------------------------------------------------------------------- */
 /* pairing(a, b)                                                verifier_native.rs:80, prover_native.rs:20 */
@@ -134,6 +185,19 @@ int sipp_ctx_prove(sipp_ctx *ctx, const uint8_t *A, const uint8_t *B, uint8_t *p
  * final_A[64], final_B[128], final_Z[384] when non-NULL (A, B, Z are the caller's own inputs: statements.rs:80-88) */
 int sipp_verify_native(const uint8_t *A, size_t a_len, const uint8_t *B, size_t b_len, const uint8_t *proof, size_t proof_len,
                        uint8_t *final_A, uint8_t *final_B, uint8_t *final_Z);
+
+/* ---- witness hand-off to the untouched circuit side (host only, no GPU) --------------------------------------------------- */
+/* The u32 public-input vector of a SIPPStatement: what `SIPPStatement::from_vec` parses (statements.rs:133-170) and the verifier
+ * circuit emits (`SIPPStatementTarget::to_vec`, statements.rs:24-39; compared at verifier_circuit.rs:255-268).  8 little-endian
+ * limbs per Fq: A (n x 16) | B (n x 32) | Z (96) | final_A (16) | final_B (32) | final_Z (96); an Fq12 is `MyFq12.coeffs`
+ * (statements.rs:120-131; order switch SIPP_OPT_FQ12_ORDER as for the transcript). */
+size_t sipp_statement_u32_len(size_t n);                 /* 48 n + 240 */
+int sipp_statement_to_u32(const uint8_t *A, const uint8_t *B, size_t n, const uint8_t Z[384], const uint8_t final_A[64],
+                          const uint8_t final_B[128], const uint8_t final_Z[384], uint32_t *out, size_t out_len);
+/* SIPP_ERR_LENGTH when in_len != sipp_statement_u32_len(n) (the reference asserts, statements.rs:139); SIPP_ERR_ENCODING for a
+ * limb group >= p */
+int sipp_statement_from_u32(size_t n, const uint32_t *in, size_t in_len, uint8_t *A, uint8_t *B, uint8_t Z[384], uint8_t final_A[64],
+                            uint8_t final_B[128], uint8_t final_Z[384]);
 
 /* ---- batched instances: `count` independent proofs in lock-step (BASELINE config "4096 independent n=128 instances") ---- */
 /* Equivalent to `count` calls of sipp_prove_native (prover_native.rs:26-80) on A[j*n .. (j+1)*n), B[j*n .. (j+1)*n):

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIPP_LIB") or os.path.join(_HERE, "libsipp_b200.so")  # SIPP_LIB: A/B builds of the same ABI
 
-OK, ERR_CUDA, ERR_ARG, ERR_LENGTH, ERR_ZERO_CHALLENGE, ERR_SHORT_PROOF, ERR_ENCODING, ERR_VERIFY = 0, -1, -2, -3, -4, -5, -6, -7
+OK, ERR_CUDA, ERR_ARG, ERR_LENGTH, ERR_ZERO_CHALLENGE, ERR_SHORT_PROOF, ERR_ENCODING, ERR_VERIFY, ERR_COMM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 OPT_FE_NORMALISATION, OPT_FQ12_ORDER, OPT_PROFILE, OPT_PIPELINE, OPT_WIDE_LINES_MAX, OPT_FE_ENGINE, OPT_WIDE_FOLD_MAX, OPT_WIDE_ACCUM_MAX = 1, 2, 3, 4, 5, 6, 7, 8
 OPT_BATCH_KPG_MAX, OPT_FOLD_STRAUS, OPT_BATCH_STREAMS, OPT_BATCH_QLINES = 9, 10, 11, 12
 
@@ -28,6 +28,23 @@ class Stats(ctypes.Structure):
 
 class TranscriptState(ctypes.Structure):
     _fields_ = [("state", ctypes.c_uint64 * 4)]
+
+
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+BROADCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int)
+SHARD_XS_BYTES = 72
+
+
+class ShardBackend(ctypes.Structure):
+    """sipp_shard_backend (include/sipp_b200.h): the compute / exchange side of the sharded protocol loop"""
+    LEN_FN = ctypes.CFUNCTYPE(ctypes.c_size_t, ctypes.c_void_p)
+    PRODUCTS_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int)
+    COMBINE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
+    BROADCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
+    FOLD_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+    COLLAPSE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
+    _fields_ = [("user", ctypes.c_void_p), ("rank", ctypes.c_int), ("world", ctypes.c_int), ("local_len", LEN_FN), ("products", PRODUCTS_FN),
+                ("combine", COMBINE_FN), ("broadcast", BROADCAST_FN), ("fold", FOLD_FN), ("collapse", COLLAPSE_FN)]
 
 
 _lib = None
@@ -88,6 +105,17 @@ def load():
     lib.sipp_test_poseidon_device.argtypes = [ctypes.POINTER(ctypes.c_uint64), sz]
     lib.sipp_test_transcript_round_device.argtypes = [ctypes.POINTER(ctypes.c_uint64), u8p, i, sz, u8p, ctypes.POINTER(ctypes.c_uint32)]
     lib.sipp_test_fold_plan.argtypes = [u8p, u8p, ctypes.POINTER(ctypes.c_uint32), sz]
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    lib.sipp_statement_u32_len.argtypes = [sz]
+    lib.sipp_statement_u32_len.restype = sz
+    lib.sipp_statement_to_u32.argtypes = [u8p, u8p, sz, u8p, u8p, u8p, u8p, u32p, sz]
+    lib.sipp_statement_from_u32.argtypes = [sz, u32p, sz, u8p, u8p, u8p, u8p, u8p, u8p]
+    lib.sipp_comm_get_unique_id.argtypes = [u8p]
+    lib.sipp_comm_init.argtypes = [u8p, i, i]
+    lib.sipp_comm_init_host.argtypes = [i, i, ALLGATHER_FN, BROADCAST_FN, vp]
+    lib.sipp_prove_native_sharded.argtypes = [u8p, u8p, sz, u8p, u8p, u8p]
+    lib.sipp_prove_native_sharded_device.argtypes = [vp, vp, sz, u8p, u8p, u8p]
+    lib.sipp_prove_native_sharded_backend.argtypes = [ctypes.POINTER(ShardBackend), sz, u8p, u8p, u8p]
     lib.sipp_microbench.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib

@@ -38,26 +38,26 @@ class SIPPStatement:
     final_Z: bytes
 
     def to_vec(self) -> List[int]:
-        """the u32 public-input vector `SIPPStatement::from_vec` parses (statements.rs:133-170)"""
-        import struct
-        raw = b"".join(self.A) + b"".join(self.B) + fq12_to_myfq12_bytes(self.Z) + self.final_A + self.final_B + fq12_to_myfq12_bytes(self.final_Z)
-        return list(struct.unpack("<%dI" % (len(raw) // 4), raw))
+        """the u32 public-input vector `SIPPStatement::from_vec` parses (statements.rs:133-170): sipp_statement_to_u32"""
+        lib = _lib.load()
+        n = len(self.A)
+        total = lib.sipp_statement_u32_len(n)
+        out = (ctypes.c_uint32 * total)()
+        _lib.check(lib.sipp_statement_to_u32(b"".join(self.A), b"".join(self.B), n, self.Z, self.final_A, self.final_B, self.final_Z, out, total))
+        return list(out)
 
     @staticmethod
     def from_vec(n: int, vec: Sequence[int]) -> "SIPPStatement":
-        """statements.rs:133-170, same length assertion"""
-        import struct
-        total = 16 * n + 32 * n + 96 + 16 + 32 + 96
-        assert len(vec) == total, "assert!(input.len() == total_len)"
-        raw = struct.pack("<%dI" % total, *vec)
-        o = 0
-        A = [raw[o + G1_BYTES * i:o + G1_BYTES * (i + 1)] for i in range(n)]; o += G1_BYTES * n
-        B = [raw[o + G2_BYTES * i:o + G2_BYTES * (i + 1)] for i in range(n)]; o += G2_BYTES * n
-        Z = myfq12_bytes_to_fq12(raw[o:o + FQ12_BYTES]); o += FQ12_BYTES
-        fa = raw[o:o + G1_BYTES]; o += G1_BYTES
-        fb = raw[o:o + G2_BYTES]; o += G2_BYTES
-        fz = myfq12_bytes_to_fq12(raw[o:o + FQ12_BYTES])
-        return SIPPStatement(A=A, B=B, Z=Z, final_A=fa, final_B=fb, final_Z=fz)
+        """statements.rs:133-170 (sipp_statement_from_u32), same length assertion"""
+        lib = _lib.load()
+        arr = (ctypes.c_uint32 * len(vec))(*vec)
+        A, B = ctypes.create_string_buffer(max(1, G1_BYTES * n)), ctypes.create_string_buffer(max(1, G2_BYTES * n))
+        Z, fa, fb, fz = (ctypes.create_string_buffer(k) for k in (FQ12_BYTES, G1_BYTES, G2_BYTES, FQ12_BYTES))
+        rc = lib.sipp_statement_from_u32(n, arr, len(vec), A, B, Z, fa, fb, fz)
+        assert rc != _lib.ERR_LENGTH, "assert!(input.len() == total_len)"
+        _lib.check(rc)
+        return SIPPStatement(A=_split(A.raw[:G1_BYTES * n], G1_BYTES), B=_split(B.raw[:G2_BYTES * n], G2_BYTES), Z=Z.raw, final_A=fa.raw,
+                             final_B=fb.raw, final_Z=fz.raw)
 
 
 # ---- hand-off to the circuit side: statements.rs:90-170 (`SIPPStatement::from_vec`) ---------------------------------------

@@ -8,6 +8,13 @@
 #include "../../include/sipp_b200.h"
 #include "launch.h"
 
+// device-resident A, B of the current round of one prover (or one rank's strided shard of it)
+struct sipp_ctx {
+    uint32_t* dA = nullptr;  // n x 16 words, Montgomery
+    uint32_t* dB = nullptr;  // n x 32 words
+    size_t n = 0, cap = 0;
+};
+
 namespace sipp_host {
 
 extern int g_device;             // CUDA device of this process, -1 before sipp_init
@@ -21,6 +28,8 @@ int cuda_fail(cudaError_t e, const char* what);   // same for a CUDA error, retu
 int ensure_init();
 bool is_pow2(size_t n);
 
+// context with uninitialised device arrays for n points (pool blocks)
+int ctx_alloc(size_t n, sipp_ctx** out);
 // grow-only device memory pool (cudaFree synchronises the device; blocks are recycled, released in sipp_shutdown)
 cudaError_t pool_alloc(void** out, size_t bytes);
 void pool_free(void* p);

@@ -187,12 +187,6 @@ cudaError_t order_after(cudaStream_t later, cudaStream_t earlier) {
 }  // namespace sipp_host
 using namespace sipp_host;
 
-struct sipp_ctx {
-    uint32_t* dA = nullptr;  // n x 16 words, Montgomery
-    uint32_t* dB = nullptr;  // n x 32 words
-    size_t n = 0, cap = 0;
-};
-
 namespace {
 
 // decode boundary bytes already on the device (d_bytes) into Montgomery limbs (d_out); n_fq field elements
@@ -307,6 +301,9 @@ int ctx_products(sipp_ctx* c, int which, uint8_t* out0, uint8_t* out1) {
     return SIPP_OK;
 }
 
+}  // namespace
+
+namespace sipp_host {
 int ctx_alloc(size_t n, sipp_ctx** out) {
     sipp_ctx* c = new sipp_ctx();
     c->n = c->cap = n;
@@ -320,8 +317,7 @@ int ctx_alloc(size_t n, sipp_ctx** out) {
     *out = c;
     return SIPP_OK;
 }
-
-}  // namespace
+}  // namespace sipp_host
 
 extern "C" {
 
@@ -355,6 +351,7 @@ int sipp_init(int device) {
 int sipp_shutdown(void) {
     if (g_device < 0) return SIPP_OK;
     collect_spans();
+    sipp_comm_destroy();
     if (g_scr.partials) cudaFree(g_scr.partials);
     if (g_scr.out) cudaFree(g_scr.out);
     if (g_scr.h_out) cudaFreeHost(g_scr.h_out);

@@ -187,8 +187,9 @@ def test_statement_public_input_vector(golden):
     assert [int.from_bytes(my[32 * i:32 * i + 32], "little") for i in range(12)] == m.f12_myfq12_coeffs(f)
     assert api.myfq12_bytes_to_fq12(my) == ark
     n = 4
-    A = [bytes(rng.randrange(256) for _ in range(64)) for _ in range(n)]
-    B = [bytes(rng.randrange(256) for _ in range(128)) for _ in range(n)]
+    fq = lambda: rng.randrange(m.P).to_bytes(32, "little")  # noqa: E731
+    A = [fq() + fq() for _ in range(n)]
+    B = [fq() + fq() + fq() + fq() for _ in range(n)]
     st = api.SIPPStatement(A=A, B=B, Z=ark, final_A=A[1], final_B=B[2], final_Z=m.f12_bytes(list(reversed(f))))
     vec = st.to_vec()
     assert len(vec) == 16 * n + 32 * n + 96 + 16 + 32 + 96 and all(0 <= v < 2**32 for v in vec)
@@ -197,6 +198,27 @@ def test_statement_public_input_vector(golden):
     assert api.SIPPStatement.from_vec(n, vec) == st
     with pytest.raises(AssertionError):
         api.SIPPStatement.from_vec(n, vec[:-1])
+    # straight through the C ABI (what a Rust host binds): lengths, round trip, a limb group >= p is refused, H2 switch
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    total = lib.sipp_statement_u32_len(n)
+    assert total == 48 * n + 240
+    out = (ctypes.c_uint32 * total)()
+    assert lib.sipp_statement_to_u32(b"".join(A), b"".join(B), n, st.Z, st.final_A, st.final_B, st.final_Z, out, total) == 0
+    assert list(out) == vec
+    assert lib.sipp_statement_to_u32(b"".join(A), b"".join(B), n, st.Z, st.final_A, st.final_B, st.final_Z, out, total - 1) == _lib.ERR_LENGTH
+    bad = list(vec)
+    bad[8:16] = [0xFFFFFFFF] * 8
+    with pytest.raises(_lib.SippError) as ei:
+        api.SIPPStatement.from_vec(n, bad)
+    assert ei.value.code == _lib.ERR_ENCODING
+    lib.sipp_set_option(_lib.OPT_FQ12_ORDER, 1)
+    try:
+        nested = st.to_vec()
+        assert nested[48 * n:48 * n + 96] == [int.from_bytes(ark[4 * i:4 * i + 4], "little") for i in range(96)]
+        assert api.SIPPStatement.from_vec(n, nested) == st
+    finally:
+        lib.sipp_set_option(_lib.OPT_FQ12_ORDER, 0)
 
 
 def test_shard_instances_partition():
