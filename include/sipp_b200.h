@@ -34,7 +34,7 @@ typedef enum {
     SIPP_ERR_LENGTH = -3,      /* A.len() != B.len()          -- reference panics: prover_native.rs:16,27 */
     SIPP_ERR_ZERO_CHALLENGE = -4, /* x.inverse().unwrap()     -- reference panics: prover_native.rs:58 */
     SIPP_ERR_SHORT_PROOF = -5, /* proof.pop().unwrap()        -- reference panics: verifier_native.rs:31,40,42 */
-    SIPP_ERR_ENCODING = -6,    /* a field element >= p */
+    SIPP_ERR_ENCODING = -6,    /* a field element >= p, a point off the curve or (G2) outside the order-r subgroup */
     SIPP_ERR_VERIFY = -7,      /* Err("Verification failed")  -- verifier_native.rs:83 */
     SIPP_ERR_COMM = -8         /* multi-GPU exchange failed (NCCL missing or in error, host collective callback failed) */
 } sipp_status;
@@ -68,6 +68,11 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          latency-bound late rounds overlap (1..8; 0 = default = 1: measured no gain on B200) */
 #define SIPP_OPT_BATCH_QLINES 12      /* batched instances: 1 = the line coefficients of every B_i are computed once and shared by Z
                                          and the first Z_L / Z_R (k_qlines_batch + k_eval_lines_batch) [default]; 0 = recomputed */
+#define SIPP_OPT_VALIDATE_POINTS 13   /* 1 = every entry point that takes points checks them [default]: A_i on y^2 = x^3 + 3, B_i on the
+                                         twist AND in the order-r subgroup (what G1Affine::new / G2Affine::new assert when the reference's
+                                         inputs are built); failure = SIPP_ERR_ENCODING.  0 = trusted inputs: the caller guarantees it (the folds
+                                         use the GLV / GLS endomorphisms, which act as scalars only on the r-torsion -- results for other points
+                                         are unspecified) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 
@@ -207,7 +212,7 @@ int sipp_statement_from_u32(size_t n, const uint32_t *in, size_t in_len, uint8_t
  * independent: a multi-GPU host gives each rank its own slice of instances, no collective. */
 int sipp_prove_native_batch(const uint8_t *A, const uint8_t *B, size_t n, size_t count, uint8_t *proofs);
 /* `count` verifications in lock-step (verifier_native.rs:14-85 per instance): results[j] = SIPP_OK for Ok(statement),
- * SIPP_ERR_VERIFY for Err("Verification failed"); every instance's proof is proof_len x 384 B (>= sipp_proof_len(n), read
+ * SIPP_ERR_VERIFY for Err("Verification failed"), SIPP_ERR_ENCODING for a proof with a coordinate >= p; every instance's proof is proof_len x 384 B (>= sipp_proof_len(n), read
  * from its end like the reference's pop()).  final_A (count x 64 B), final_B (count x 128 B), final_Z (count x 384 B) receive
  * the computed statement members when non-NULL.  The return value reports whether the batch ran, not whether proofs verified. */
 int sipp_verify_native_batch(const uint8_t *A, const uint8_t *B, size_t n, size_t count, const uint8_t *proofs, size_t proof_len,

@@ -130,7 +130,22 @@ int batch_sub_count(size_t n, size_t count) {
 }
 
 // the whole batch on the device; bytesA / bytesB already hold the boundary bytes.  Enqueues everything; the caller synchronises.
+cudaStream_t g_side = nullptr;  // transcript absorb chains of a large batch, next to the first products
+int g_side_dev = -1;
+
+int batch_prove_enqueue(BatchBuffers& b, size_t n, size_t count, cudaStream_t s, bool* side_used, int* subs_used);
 int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s) {
+    bool side_used = false;
+    int subs_used = 0;
+    const int rc = batch_prove_enqueue(b, n, count, s, &side_used, &subs_used);
+    // whatever happened (an error return in the middle of a round included), `s` must not run ahead of the side stream and the
+    // sub-batch streams: the caller synchronises `s` only and then recycles the buffers they may still be using
+    if (side_used) order_after(s, g_side);
+    for (int k = 0; k < subs_used; k++) order_after(s, g_sub_streams[k]);
+    return rc;
+}
+
+int batch_prove_enqueue(BatchBuffers& b, size_t n, size_t count, cudaStream_t s, bool* side_used, int* subs_used) {
     const size_t np = sipp_proof_len(n), total = n * count;
     CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), s));
     {
@@ -139,15 +154,19 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
         if (!e) e = launch_codec_decode(b.bytesB, b.dB, total * 4, b.flags + 1, s);
         if (e) return cuda_fail((cudaError_t)e, "k_codec_decode");
         g_stats.launches += 2;
+        if (g_opt_validate) {  // on the curve, B_i in the order-r subgroup (SIPP_OPT_VALIDATE_POINTS)
+            e = launch_validate_points(b.dA, b.dB, total, b.flags + 1, s);
+            if (e) return cuda_fail((cudaError_t)e, "k_validate_points");
+            g_stats.launches++;
+        }
     }
     // register A and B (prover_native.rs:36-39): independent of everything the products compute, so the chains run on a side
     // stream next to Z and the first Z_L, Z_R
-    static cudaStream_t side = nullptr;
-    static int side_dev = -1;
-    if (side_dev != g_device) {
-        CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-        side_dev = g_device;
+    if (g_side_dev != g_device) {
+        CK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+        g_side_dev = g_device;
     }
+    cudaStream_t side = g_side;
     if (g_sub_streams_dev != g_device) {
         for (int k = 0; k < 8; k++) CK(cudaStreamCreateWithFlags(&g_sub_streams[k], cudaStreamNonBlocking));
         g_sub_streams_dev = g_device;
@@ -157,7 +176,10 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
     static const char* absorb_env = getenv("SIPP_BATCH_ABSORB");
     const bool absorb_inline = absorb_env ? absorb_env[0] == 'i' : total < ((size_t)1 << 18);
     cudaStream_t absorb_stream = absorb_inline ? s : side;
-    if (!absorb_inline) CK(order_after(side, s));
+    if (!absorb_inline) {
+        CK(order_after(side, s));
+        *side_used = true;
+    }
     {
         Span sp(3, absorb_stream);
         int e = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, absorb_stream);
@@ -182,6 +204,7 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
     struct QFree { uint32_t* p; ~QFree() { pool_free(p); } } qfree{qbuf};  // recycled block: later work on the same streams only
     // fork: every sub-stream waits for the decode on `s` (ordered BEFORE any join below, or sub-batch k + 1 would wait for k)
     for (int k = 0; k < nsub && nsub > 1; k++) CK(order_after(g_sub_streams[k], s));
+    *subs_used = nsub > 1 ? nsub : 0;
     for (int k = 0; k < nsub; k++) {
         const size_t i0 = count * (size_t)k / nsub, i1 = count * (size_t)(k + 1) / nsub, c = i1 - i0;
         if (c == 0) continue;
@@ -230,8 +253,7 @@ int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s
             round++;
         }
     }
-    for (int k = 0; k < nsub && nsub > 1; k++) CK(order_after(s, g_sub_streams[k]));  // join
-    return SIPP_OK;
+    return SIPP_OK;  // the caller (batch_prove_resident) joins the side stream and the sub-streams into `s`
 }
 
 int batch_alloc(BatchBuffers& b, size_t n, size_t count) {
@@ -257,7 +279,9 @@ int batch_check_flags(const BatchBuffers& b, cudaStream_t s) {
     int flags[2] = {0, 0};
     CK(cudaMemcpyAsync(flags, b.flags, sizeof flags, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (flags[1]) return fail(SIPP_ERR_ENCODING, "input coordinate >= p");
+    if (flags[1] & 1) return fail(SIPP_ERR_ENCODING, "input coordinate >= p");
+    if (flags[1] & 2) return fail(SIPP_ERR_ENCODING, "input point is not on the curve");
+    if (flags[1] & 4) return fail(SIPP_ERR_ENCODING, "input G2 point is not in the prime-order subgroup");
     if (flags[0] & 1) return fail(SIPP_ERR_ZERO_CHALLENGE, "challenge is zero: x.inverse().unwrap() panics in the reference");
     if (flags[0] & 2) return fail(SIPP_ERR_ENCODING, "fold scalar recoding failed");
     return SIPP_OK;
@@ -362,6 +386,7 @@ int sipp_verify_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_
         CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), s));
         int le = launch_codec_decode(b.bytesA, b.dA, total * 2, b.flags + 1, s);
         if (!le) le = launch_codec_decode(b.bytesB, b.dB, total * 4, b.flags + 1, s);
+        if (!le && g_opt_validate) { le = launch_validate_points(b.dA, b.dB, total, b.flags + 1, s); g_stats.launches++; }
         if (!le) le = launch_tr_absorb_pairs(b.bytesA, b.bytesB, n, count, b.states, s);                 // :25-28
         if (le) return cuda_fail((cudaError_t)le, "verify batch: decode / absorb");
         g_stats.launches += 3;
@@ -405,7 +430,12 @@ int sipp_verify_native_batch(const uint8_t* A, const uint8_t* B, size_t n, size_
     if (rc) cudaStreamSynchronize(s);
     release();
     if (rc) return rc;
-    for (size_t j = 0; j < count; j++) results[j] = memcmp(&hz[384 * j], &hp[384 * j], 384) == 0 ? SIPP_OK : SIPP_ERR_VERIFY;  // :81-84
+    for (size_t j = 0; j < count; j++) {
+        // a proof with a coordinate >= p is one the reference could not have deserialised: refused on its own, like a bad A or B
+        const uint8_t* pj = proofs + (j * proof_len + (proof_len - np)) * 384;
+        results[j] = !fq_bytes_canonical(pj, 12 * np) ? SIPP_ERR_ENCODING
+                     : memcmp(&hz[384 * j], &hp[384 * j], 384) == 0 ? SIPP_OK : SIPP_ERR_VERIFY;  // :81-84
+    }
     if (final_Z) memcpy(final_Z, hz.data(), count * 384);
     return SIPP_OK;
 }

@@ -80,6 +80,30 @@ SIPP_HD void f12_exp_x(M& mc, int d, int a) {
     }
 }
 
+// register 0 <- a^k for a 256-bit exponent k (8 x u32, little endian), a = register 1 on entry; registers 2, 3 become a^2, a^3.
+// GENERIC arithmetic (no cyclotomic shortcut: this is the verifier's Z_L.pow(x), /root/reference/src/verifier_native.rs:59-61,
+// on proof elements that need not lie in GT): fixed 2-bit windows, every squaring and product a MUL12Y chain link (two levels).
+// Returns false when k == 0 (register 0 untouched: the caller writes 1).  On exit register 0's xi slots are valid.
+template <class M>
+SIPP_HD bool f12_pow_w2(M& mc, const uint32_t* k) {
+    F12_OP2(mc, XI6, 1, 1);
+    F12_OP3(mc, MUL12Y, 2, 1, 1);
+    F12_OP3(mc, MUL12Y, 3, 2, 1);
+    bool started = false;
+    for (int i = 127; i >= 0; i--) {
+        const int d = (int)((k[i >> 4] >> (2 * (i & 15))) & 3u);
+        if (started) {
+            F12_OP3(mc, MUL12Y, 0, 0, 0);
+            F12_OP3(mc, MUL12Y, 0, 0, 0);
+            if (d) F12_OP3(mc, MUL12Y, 0, 0, d);
+        } else if (d) {
+            F12_OP2(mc, COPYX, 0, d);
+            started = true;
+        }
+    }
+    return started;
+}
+
 #define SIPP_F12_FE_REGS 11
 // register 0 holds f on entry; returns the register that holds f^((p^12-1)/r) (+ the arkworks multiple if ark_norm).
 // Same formulas, in the same order, as coop_final_exp (coop.cuh) / final_exponentiation (pairing.cuh).

@@ -5,6 +5,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <thread>
+
 #include "../../include/sipp_b200.h"
 #include "launch.h"
 
@@ -20,7 +23,7 @@ namespace sipp_host {
 extern int g_device;             // CUDA device of this process, -1 before sipp_init
 extern int g_sm_count;
 extern cudaStream_t g_stream;    // the library's non-blocking stream
-extern int g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine;
+extern int g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate;
 extern sipp_stats g_stats;
 
 int fail(int code, const char* what);             // records the message for sipp_last_error, returns `code`
@@ -30,6 +33,21 @@ bool is_pow2(size_t n);
 
 // context with uninitialised device arrays for n points (pool blocks)
 int ctx_alloc(size_t n, sipp_ctx** out);
+// true when all `n_fq` little-endian 32-byte integers are < p (the canonical encoding ark-serialize requires: a proof element with a
+// coordinate c + p would hash differently in the transcript while reducing to the same field element)
+inline bool fq_bytes_canonical(const uint8_t* b, size_t n_fq) {
+    static const uint64_t PM[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+    for (size_t i = 0; i < n_fq; i++) {
+        uint64_t w[4];
+        __builtin_memcpy(w, b + 32 * i, 32);
+        bool less = false;
+        for (int k = 3; k >= 0; k--) {
+            if (w[k] != PM[k]) { less = w[k] < PM[k]; break; }
+        }
+        if (!less) return false;
+    }
+    return true;
+}
 // grow-only device memory pool (cudaFree synchronises the device; blocks are recycled, released in sipp_shutdown)
 cudaError_t pool_alloc(void** out, size_t bytes);
 void pool_free(void* p);
@@ -38,6 +56,29 @@ int lines_reserve(size_t bytes);
 uint32_t* lines_buffer();
 // make `later` wait for everything already enqueued on `earlier`
 cudaError_t order_after(cudaStream_t later, cudaStream_t earlier);
+
+// The registration of A and B in the transcript (prover_native.rs:36-39, verifier_native.rs:25-28): 8n strictly serial Poseidon
+// permutations that depend on nothing the GPU computes, so they run on a host thread from the moment the inputs are known --
+// under the upload, the decode + validation kernels, Z and the first Z_L / Z_R.  join() returns the milliseconds the caller
+// had to wait (the exposed part of the chain).
+struct AbsorbJob {
+    sipp_transcript tr;
+    std::thread th;
+    std::atomic<bool> cancel{false};
+    void start(const uint8_t* A, const uint8_t* B, size_t n) {
+        sipp_transcript_new(&tr);
+        th = std::thread([this, A, B, n]() {
+            const size_t chunk = 512;
+            for (size_t i = 0; i < n && !cancel.load(std::memory_order_relaxed); i += chunk)
+                sipp_transcript_append_pairs(&tr, A + 64 * i, B + 128 * i, n - i < chunk ? n - i : chunk);
+        });
+    }
+    double join();
+    ~AbsorbJob() {
+        cancel.store(true);
+        if (th.joinable()) th.join();
+    }
+};
 
 // CUDA-event span around a kernel class (SIPP_OPT_PROFILE): kind 0 miller, 1 reduce / final exponentiation, 2 fold, 3 other
 int span_begin(int kind, cudaStream_t s);

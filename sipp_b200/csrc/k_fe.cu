@@ -219,6 +219,55 @@ int launch_fe_batch_eng(const uint32_t* partials, size_t nproducts, int gpp, int
     return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ verifier GT update on the machine
+// k_gt_fold_eng: out = zl^x * z * zr^xinv (verifier_native.rs:59-61).  Two machines (warps), one power each, GENERIC arithmetic
+// (a proof element need not lie in the cyclotomic subgroup and the reference's `pow` does not assume it): fixed 2-bit windows
+// over the table {a, a^2, a^3}, every squaring and product a MUL12Y chain link of two levels -- 254 squarings + ~95 products
+// per power, against the 254 x (squaring + product) of one thread per power in k_gt_fold (14.5 ms per call).
+// in: 3 x 96 words boundary format (zl, z, zr); out: 96 words boundary format.
+#define SIPP_GTF_REGS 6  // 0 accumulator, 1..3 table, 4 the other power, 5 z
+#define SIPP_GTF_SLOTS (SIPP_F12_GLOBAL_SLOTS + SIPP_F12_REG_SLOTS * SIPP_GTF_REGS)
+__global__ void __launch_bounds__(64) k_gt_fold_eng(const uint32_t* __restrict__ in, Scalar256 x, Scalar256 xinv, uint32_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t smem[2 * SIPP_GTF_SLOTS * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* slots = smem + warp * (SIPP_GTF_SLOTS * 8);
+    for (int j = lane; j < 37; j += 32) f12_fill_global(slots, j);
+    auto load12 = [&](int reg, const uint32_t* src) {  // boundary bytes -> register `reg` (slot 2k + c of the w-basis coefficient k)
+        if (lane < 6) {
+            const Fq2 g = fq2_decode(src + 16 * ((lane & 1) * 3 + (lane >> 1)));
+            lp_store(slots, f12_reg_base(reg) + 2 * lane, g.c0);
+            lp_store(slots, f12_reg_base(reg) + 2 * lane + 1, g.c1);
+        }
+        __syncwarp();
+    };
+    DevMachine12 mc;
+    mc.slots = slots;
+    mc.lane = lane;
+    load12(1, in + (warp ? 192 : 0));
+    const bool started = f12_pow_w2(mc, warp ? xinv.w : x.w);
+    if (!started) {  // exponent 0 (the host refuses a zero challenge before it gets here): a^0 = 1
+        if (lane < 12) lp_store(slots, f12_reg_base(0) + lane, lane == 0 ? fq_one() : fq_zero());
+        __syncwarp();
+        F12_OP2(mc, XI6, 0, 0);
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const uint32_t* other = smem + SIPP_GTF_SLOTS * 8 + f12_reg_base(0) * 8;
+    for (int w = lane; w < SIPP_F12_REG_SLOTS * 8; w += 32) slots[f12_reg_base(4) * 8 + w] = other[w];
+    load12(5, in + 96);
+    F12_OP2(mc, XI6, 5, 5);
+    F12_OP3(mc, MUL12Y, 0, 0, 5);
+    F12_OP3(mc, MUL12Y, 0, 0, 4);
+    if (lane < 6) {
+        const Fq2 g = Fq2{lp_load(slots, f12_reg_base(0) + 2 * lane), lp_load(slots, f12_reg_base(0) + 2 * lane + 1)};
+        fq2_encode(out + ((lane & 1) * 3 + (lane >> 1)) * 16, g);
+    }
+}
+int launch_gt_fold_eng(const uint32_t* in, const Scalar256& x, const Scalar256& xinv, uint32_t* out, cudaStream_t s) {
+    k_gt_fold_eng<<<1, 64, 0, s>>>(in, x, xinv, out);
+    return (int)cudaGetLastError();
+}
+
 int launch_reduce_fe_eng(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s) {
     k_reduce_fe_eng<<<nprod, SIPP_RFE_THREADS, 0, s>>>(partials, count, nprod, out, final_exp, ark_norm);
     return (int)cudaGetLastError();

@@ -223,6 +223,56 @@ __global__ void __launch_bounds__(64) k_seeded_inputs(uint64_t seed, size_t n, u
 }
 
 
+// ------------------------------------------------------------------------------------------------ input validation
+// What `G1Affine::new` / `G2Affine::new` assert when the reference's inputs are built (on the curve, in the prime-order
+// subgroup) -- checked here because the folds rely on it: psi is used as [6x^2] and phi as [lambda], which holds only in the
+// r-torsion.  Thread t < n checks A_t: y^2 = x^3 + 3 (G1 has cofactor 1).  Thread n + i checks B_i: y^2 = x^3 + 3/xi and
+//   [x + 1] Q + psi([x] Q) + psi^2([x] Q) == psi^3([2x] Q)     (x the BN parameter: one 63-bit scalar multiplication)
+// which holds exactly for the points of order r (El Housni, Guillevic, Piellard 2022; tests/test_gpu_parity.py checks it on
+// points of the twist outside G2).  The identity (x = y = 0, ark's `infinity`) passes.  flags |= 2: off the curve, |= 4: on
+// the twist but outside G2.  Inputs are Montgomery limbs (after k_codec_decode).
+__device__ __forceinline__ Jac<Fq2> psi_jac(const Jac<Fq2>& p, int j) {  // psi^j on Jacobian coordinates (Z^p = conj(Z))
+    Jac<Fq2> r;
+    r.x = f_mul((j & 1) ? fq2_conj(p.x) : p.x, frob_gamma(j, 2));
+    r.y = f_mul((j & 1) ? fq2_conj(p.y) : p.y, frob_gamma(j, 3));
+    r.z = (j & 1) ? fq2_conj(p.z) : p.z;
+    return r;
+}
+__device__ bool jac_equal(const Jac<Fq2>& p, const Jac<Fq2>& q) {
+    const bool pz = f_is_zero(p.z), qz = f_is_zero(q.z);
+    if (pz || qz) return pz && qz;
+    const Fq2 z1 = f_sqr(p.z), z2 = f_sqr(q.z);
+    if (!fq2_eq(f_mul(p.x, z2), f_mul(q.x, z1))) return false;
+    return fq2_eq(f_mul(p.y, f_mul(z2, q.z)), f_mul(q.y, f_mul(z1, p.z)));
+}
+__global__ void __launch_bounds__(64) k_validate_points(const uint32_t* __restrict__ dA, const uint32_t* __restrict__ dB, size_t n, int* __restrict__ flags) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    if (t < n) {
+        const G1A p{load_fq_words(dA + 16 * t), load_fq_words(dA + 16 * t + 8)};
+        if (affine_is_identity(p)) return;
+        const Fq three = fq_to_mont(Fq{{3, 0, 0, 0, 0, 0, 0, 0}});
+        if (!f_is_zero(f_sub(f_sqr(p.y), f_add(f_mul(f_sqr(p.x), p.x), three)))) atomicOr(flags, 2);
+        return;
+    }
+    const size_t i = t - n;
+    const G2A q{load_fq2_words(dB + 32 * i), load_fq2_words(dB + 32 * i + 16)};
+    if (affine_is_identity(q)) return;
+    if (!fq2_eq(f_sqr(q.y), f_add(f_mul(f_sqr(q.x), q.x), fq2_b_twist()))) { atomicOr(flags, 2); return; }
+    const unsigned long long xb = SIPP_BN_X;
+    const uint32_t k[8] = {(uint32_t)xb, (uint32_t)(xb >> 32), 0, 0, 0, 0, 0, 0};
+    const Jac<Fq2> xq = jac_scalar_mul(q, k);
+    Jac<Fq2> lhs = jac_add_affine(xq, q);
+    lhs = jac_add(lhs, psi_jac(xq, 1));
+    lhs = jac_add(lhs, psi_jac(xq, 2));
+    const Jac<Fq2> rhs = psi_jac(jac_dbl(xq), 3);
+    if (!jac_equal(lhs, rhs)) atomicOr(flags, 4);
+}
+int launch_validate_points(const uint32_t* dA, const uint32_t* dB, size_t n, int* flags, cudaStream_t s) {
+    k_validate_points<<<(unsigned)((2 * n + 63) / 64), 64, 0, s>>>(dA, dB, n, flags);
+    return (int)cudaGetLastError();
+}
+
 int launch_fold(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s) {
     // In-place: an element's partner i + h is only read by the block that owns i, and i < h <= i + h, so no block reads
     // what another block writes.

@@ -215,23 +215,18 @@ int cb_agree(void*, int rc) {
 }
 
 // ------------------------------------------------------------------------------------------------ the protocol loop
-int sharded_protocol(const sipp_shard_backend* be, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof) {
+// `started`: rank 0's absorb job when the caller already started it (before the upload of its shard), else NULL
+int sharded_protocol(const sipp_shard_backend* be, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof, AbsorbJob* started) {
     const int rank = be->rank, world = be->world;
     const size_t np = sipp_proof_len(n);
     std::vector<uint8_t> fwd(rank == 0 ? np * 384 : 0);  // proof in push order; reversed at the end (prover_native.rs:78)
     size_t k = 0;
-    sipp_transcript tr;
-    std::thread absorb;
-    if (rank == 0) {
-        // register A and B (prover_native.rs:36-39): 8n strictly serial permutations that need nothing from the GPUs, so the
-        // chain runs on a host thread while every rank computes Z and the first Z_L, Z_R
-        sipp_transcript_new(&tr);
-        absorb = std::thread([&]() { sipp_transcript_append_pairs(&tr, A_full, B_full, n); });
-    }
-    struct Joiner {
-        std::thread& t;
-        ~Joiner() { if (t.joinable()) t.join(); }
-    } joiner{absorb};
+    AbsorbJob own;
+    AbsorbJob& job = started ? *started : own;
+    // register A and B (prover_native.rs:36-39): 8n strictly serial permutations that need nothing from the GPUs, so the
+    // chain runs on a host thread while every rank computes Z and the first Z_L, Z_R
+    if (rank == 0 && !started) own.start(A_full, B_full, n);
+    sipp_transcript& tr = job.tr;
 
     int rc = be->products(be->user, 0);                                        // let Z = inner_product(A, B);   :29
     if (!rc && rank == 0) rc = be->combine(be->user, 1, &fwd[0]);
@@ -239,9 +234,7 @@ int sharded_protocol(const sipp_shard_backend* be, size_t n, const uint8_t* A_fu
     size_t cur = n;
     bool first = true;
     auto absorb_z = [&]() {
-        auto t1 = std::chrono::steady_clock::now();
-        absorb.join();
-        g_stats.transcript_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        g_stats.transcript_ms += job.join();
         sipp_transcript_append_fq12(&tr, &fwd[0]);                             // proof.push(Z); transcript.append_fq12(Z)  :42-43
         first = false;
     };
@@ -305,7 +298,7 @@ int check_shape(size_t n, int world) {
     return SIPP_OK;
 }
 
-int prove_sharded(sipp_ctx* c, int create_rc, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof) {
+int prove_sharded(sipp_ctx* c, int create_rc, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof, AbsorbJob* job) {
     CudaBackend b;
     b.ctx = c;
     int rc = cb_agree(&b, create_rc);
@@ -314,7 +307,7 @@ int prove_sharded(sipp_ctx* c, int create_rc, size_t n, const uint8_t* A_full, c
         be.user = &b; be.rank = g_comm.rank; be.world = g_comm.world;
         be.local_len = cb_local_len; be.products = cb_products; be.combine = cb_combine; be.broadcast = cb_broadcast;
         be.fold = cb_fold; be.collapse = cb_collapse;
-        rc = sharded_protocol(&be, n, A_full, B_full, proof);
+        rc = sharded_protocol(&be, n, A_full, B_full, proof, job);
     }
     if (b.ctx) {
         cudaStreamSynchronize(g_stream);
@@ -401,17 +394,21 @@ int sipp_comm_nccl_version(void) {
 int sipp_prove_native_sharded(const uint8_t* A_local, const uint8_t* B_local, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof) {
     int rc = sharded_args(n, A_full, B_full, proof);
     if (rc) return rc;
+    AbsorbJob job;  // rank 0: the hash chain starts before the upload of the shard
+    if (g_comm.rank == 0) job.start(A_full, B_full, n);
     sipp_ctx* c = nullptr;
     rc = (A_local && B_local) ? sipp_ctx_create(A_local, B_local, n / (size_t)g_comm.world, &c) : fail(SIPP_ERR_ARG, "null shard");
-    return prove_sharded(c, rc, n, A_full, B_full, proof);
+    return prove_sharded(c, rc, n, A_full, B_full, proof, g_comm.rank == 0 ? &job : nullptr);
 }
 
 int sipp_prove_native_sharded_device(const void* dA_local, const void* dB_local, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof) {
     int rc = sharded_args(n, A_full, B_full, proof);
     if (rc) return rc;
+    AbsorbJob job;
+    if (g_comm.rank == 0) job.start(A_full, B_full, n);
     sipp_ctx* c = nullptr;
     rc = (dA_local && dB_local) ? sipp_ctx_create_from_device(dA_local, dB_local, n / (size_t)g_comm.world, &c) : fail(SIPP_ERR_ARG, "null shard");
-    return prove_sharded(c, rc, n, A_full, B_full, proof);
+    return prove_sharded(c, rc, n, A_full, B_full, proof, g_comm.rank == 0 ? &job : nullptr);
 }
 
 int sipp_prove_native_sharded_backend(const sipp_shard_backend* be, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof) {
@@ -420,7 +417,7 @@ int sipp_prove_native_sharded_backend(const sipp_shard_backend* be, size_t n, co
     int rc = check_shape(n, be->world);
     if (rc) return rc;
     if (be->rank == 0 && (!A_full || !B_full || !proof)) return fail(SIPP_ERR_ARG, "rank 0 needs the full A, B (transcript) and the proof buffer");
-    return sharded_protocol(be, n, A_full, B_full, proof);
+    return sharded_protocol(be, n, A_full, B_full, proof, nullptr);
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ int g_opt_fold_straus = 1;     // throughput folds (batched instances, large rou
 int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own streams (0 = choose by batch size)
 int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
+int g_opt_validate = 1;        // every prove / verify entry point checks its points: on the curve, B_i in the order-r subgroup
 
 struct TimedSpan {
     cudaEvent_t a, b;
@@ -80,6 +81,13 @@ void collect_spans() {
         cudaEventDestroy(t.b);
     }
     g_spans.clear();
+}
+
+double AbsorbJob::join() {
+    if (!th.joinable()) return 0.0;
+    auto t0 = std::chrono::steady_clock::now();
+    th.join();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 size_t log2_exact(size_t n) {
@@ -379,6 +387,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_FOLD_STRAUS: g_opt_fold_straus = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_BATCH_STREAMS: g_opt_batch_streams = value < 0 ? 0 : value; return SIPP_OK;
         case SIPP_OPT_BATCH_QLINES: g_opt_batch_qlines = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_VALIDATE_POINTS: g_opt_validate = value ? 1 : 0; return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -396,6 +405,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_FOLD_STRAUS: return g_opt_fold_straus;
         case SIPP_OPT_BATCH_STREAMS: return g_opt_batch_streams;
         case SIPP_OPT_BATCH_QLINES: return g_opt_batch_qlines;
+        case SIPP_OPT_VALIDATE_POINTS: return g_opt_validate;
         default: return -1;
     }
 }
@@ -425,11 +435,22 @@ int sipp_ctx_create_from_device(const void* dA, const void* dB, size_t n, sipp_c
     launch_decode((const uint32_t*)dA, c->dA, n * 2, g_stream, true);
     launch_codec_decode((const uint32_t*)dB, c->dB, n * 4, g_scr.flag, g_stream);
     g_stats.launches++;
+    if (g_opt_validate) {
+        // what G1Affine::new / G2Affine::new assert in the reference: on the curve, in the prime-order subgroup (the folds use
+        // the endomorphisms, which are [lambda] / [6x^2] only there)
+        Span sp(3, g_stream);
+        launch_validate_points(c->dA, c->dB, n, g_scr.flag, g_stream);
+        g_stats.launches++;
+    }
     int flag = 0;
     cudaError_t e = cudaMemcpyAsync(&flag, g_scr.flag, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
     if (e != cudaSuccess) { sipp_ctx_destroy(c); return cuda_fail(e, "decode"); }
-    if (flag) { sipp_ctx_destroy(c); return fail(SIPP_ERR_ENCODING, "input coordinate >= p"); }
+    if (flag) {
+        sipp_ctx_destroy(c);
+        return fail(SIPP_ERR_ENCODING, (flag & 1) ? "input coordinate >= p" : (flag & 2) ? "input point is not on the curve"
+                                                                                         : "input G2 point is not in the prime-order subgroup");
+    }
     *out = c;
     return SIPP_OK;
 }
@@ -595,7 +616,9 @@ int sipp_gt_fold(const uint8_t zl[384], const uint8_t z[384], const uint8_t zr[3
     cudaMemcpyAsync(d_in + 192, zr, 384, cudaMemcpyHostToDevice, g_stream);
     {
         Span sp(3, g_stream);
-        launch_gt_fold(d_in, scalar_from_bytes(x), scalar_from_bytes(x_inv), g_scr.out, g_stream);
+        // two 32-lane Fq12 machines, one power each (k_gt_fold_eng); the one-thread-per-power kernel stays as the engines-off arm
+        if (g_opt_fe_engine) launch_gt_fold_eng(d_in, scalar_from_bytes(x), scalar_from_bytes(x_inv), g_scr.out, g_stream);
+        else launch_gt_fold(d_in, scalar_from_bytes(x), scalar_from_bytes(x_inv), g_scr.out, g_stream);
     }
     g_stats.launches++;
     cudaError_t e = cudaMemcpyAsync(g_scr.h_out, g_scr.out, 384, cudaMemcpyDeviceToHost, g_stream);
@@ -622,21 +645,13 @@ int sipp_fr_inverse(const uint8_t x[32], uint8_t out[32]) {
 // ------------------------------------------------------------------------------------------------ protocol
 size_t sipp_proof_len(size_t n) { return is_pow2(n) ? 2 * log2_exact(n) + 1 : 0; }
 
-int sipp_ctx_prove(sipp_ctx* c, const uint8_t* A, const uint8_t* B, uint8_t* proof) {
-    if (!c || !A || !B || !proof) return fail(SIPP_ERR_ARG, "null argument");
+// the protocol loop on a context whose A, B are being absorbed by `job` (started by the caller as early as possible)
+static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
     size_t n = c->n;
-    if (!is_pow2(n)) return fail(SIPP_ERR_ARG, "n must be a power of two (the reference halves n every round)");
     size_t np = sipp_proof_len(n);
     std::vector<uint8_t> fwd(np * 384);  // proof in push order; reversed at the end (prover_native.rs:78)
     size_t k = 0;
-
-    // register A and B (prover_native.rs:36-39): a strictly serial 8n-permutation hash chain.  It does not depend on
-    // anything the GPU computes, so it runs on a host thread while the GPU computes Z and the first Z_L, Z_R.
-    sipp_transcript tr;
-    sipp_transcript_new(&tr);
-    auto t0 = std::chrono::steady_clock::now();
-    std::thread absorb([&]() { sipp_transcript_append_pairs(&tr, A, B, n); });
-
+    sipp_transcript& tr = job.tr;
     int rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                       // let Z = inner_product(A, B);   :29
     k++;
     bool first = true;
@@ -646,11 +661,7 @@ int sipp_ctx_prove(sipp_ctx* c, const uint8_t* A, const uint8_t* B, uint8_t* pro
         rc = sipp_ctx_cross_products(c, zl, zr);                              // :46-49
         if (rc) break;
         if (first) {
-            auto t1 = std::chrono::steady_clock::now();
-            absorb.join();
-            auto t2 = std::chrono::steady_clock::now();
-            (void)t0; (void)t1;
-            g_stats.transcript_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();  // exposed wait only
+            g_stats.transcript_ms += job.join();                              // :36-39 finished? (exposed wait only)
             sipp_transcript_append_fq12(&tr, &fwd[0]);                        // proof.push(Z); transcript.append_fq12(Z)  :42-43
             first = false;
         }
@@ -666,19 +677,34 @@ int sipp_ctx_prove(sipp_ctx* c, const uint8_t* A, const uint8_t* B, uint8_t* pro
         rc = sipp_ctx_fold(c, x, xinv);                                       // :60-74
         n = c->n;
     }
-    if (absorb.joinable()) absorb.join();
     if (rc) return rc;
     for (size_t i = 0; i < np; i++) memcpy(proof + 384 * i, &fwd[384 * (np - 1 - i)], 384);  // proof.reverse()  :78
     return SIPP_OK;
 }
 
+int sipp_ctx_prove(sipp_ctx* c, const uint8_t* A, const uint8_t* B, uint8_t* proof) {
+    if (!c || !A || !B || !proof) return fail(SIPP_ERR_ARG, "null argument");
+    if (!is_pow2(c->n)) return fail(SIPP_ERR_ARG, "n must be a power of two (the reference halves n every round)");
+    // register A and B (prover_native.rs:36-39): a strictly serial 8n-permutation hash chain.  It does not depend on
+    // anything the GPU computes, so it runs on a host thread while the GPU computes Z and the first Z_L, Z_R.
+    AbsorbJob job;
+    job.start(A, B, c->n);
+    return prove_core(c, job, proof);
+}
+
 int sipp_prove_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t b_len, uint8_t* proof) {
     if (a_len != b_len) return fail(SIPP_ERR_LENGTH, "assert_eq!(A.len(), B.len()) failed");  // prover_native.rs:27
     if (!is_pow2(a_len)) return fail(SIPP_ERR_ARG, "n must be a non-zero power of two");
-    sipp_ctx* c;
-    int rc = sipp_ctx_create(A, B, a_len, &c);
+    if (!A || !B || !proof) return fail(SIPP_ERR_ARG, "null argument");
+    int rc = ensure_init();
     if (rc) return rc;
-    rc = sipp_ctx_prove(c, A, B, proof);
+    // the hash chain starts before the upload: the H2D copies, the decode and the point validation run in its shadow
+    AbsorbJob job;
+    job.start(A, B, a_len);
+    sipp_ctx* c;
+    rc = sipp_ctx_create(A, B, a_len, &c);
+    if (rc) return rc;
+    rc = prove_core(c, job, proof);
     sipp_ctx_destroy(c);
     return rc;
 }
@@ -690,12 +716,19 @@ int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t 
     size_t n = a_len;
     if (!is_pow2(n)) return fail(SIPP_ERR_ARG, "n must be a non-zero power of two");
     if (proof_len < sipp_proof_len(n)) return fail(SIPP_ERR_SHORT_PROOF, "proof.pop().unwrap() on an empty proof");  // verifier_native.rs:31,40,42
-    sipp_ctx* c;
-    int rc = sipp_ctx_create(A, B, n, &c);
+    // an Fq12 the reference could not have deserialised (a coordinate >= p) is refused, as for A and B
+    if (!fq_bytes_canonical(proof + 384 * (proof_len - sipp_proof_len(n)), 12 * sipp_proof_len(n))) return fail(SIPP_ERR_ENCODING, "proof coordinate >= p");
+    int rc = ensure_init();
     if (rc) return rc;
-    sipp_transcript tr;
-    sipp_transcript_new(&tr);
-    sipp_transcript_append_pairs(&tr, A, B, n);                               // :25-28
+    // :25-28 on a host thread while the GPU receives, decodes and validates A, B (nothing else can overlap: the first fold needs
+    // the first challenge, which needs the whole chain)
+    AbsorbJob job;
+    job.start(A, B, n);
+    sipp_ctx* c;
+    rc = sipp_ctx_create(A, B, n, &c);
+    if (rc) return rc;
+    g_stats.transcript_ms += job.join();
+    sipp_transcript& tr = job.tr;
     size_t top = proof_len;
     uint8_t Z[384];
     memcpy(Z, proof + 384 * --top, 384);                                      // let original_Z = proof.pop().unwrap();  :31

@@ -305,31 +305,27 @@ def test_error_behaviour(sipp, oracle):
 
 
 def test_partials_and_combine(sipp, oracle):
-    """the multi-GPU building blocks on one GPU: un-exponentiated partial products in device memory, then
-    sipp_combine_partials over two 'ranks' built from a strided split equals the full products"""
+    """the multi-GPU building blocks on one GPU (what a host with its own exchange calls): un-exponentiated partial products in
+    device memory, then sipp_combine_partials over two 'ranks' built from a strided split equals the full products"""
     import torch
-    from sipp_b200.sharded import CudaEngine, shard_points
+    from sipp_b200.sharded import shard_points
     A, B = oracle.seeded_inputs(77, 32, threads=4)
-    eng = CudaEngine()
+    stream = torch.cuda.current_stream().cuda_stream
     parts0, parts1 = [], []
     for r in range(2):
         Al, Bl = shard_points(A, B, r, 2)
-        ctx = eng.create(Al, Bl)
-        parts0.append(ctx.partial_products(0))
-        parts1.append(ctx.partial_products(1))
+        ctx = sipp.ProverContext(Al, Bl)
+        for which, dst in ((0, parts0), (1, parts1)):
+            out = torch.empty((1 + which) * 384, dtype=torch.uint8, device="cuda")
+            ctx.partial_products(which, out.data_ptr(), stream)
+            dst.append(out)
     torch.cuda.synchronize()
-    z = eng.combine(torch.cat(parts0), 2, 1)
+    g0, g1 = torch.cat(parts0), torch.cat(parts1)
+    z = sipp.combine_partials(g0.data_ptr(), 2, 1, stream)
     assert z[0] == oracle.inner_product(A, B, threads=4)
-    zs = eng.combine(torch.cat(parts1), 2, 2)
+    zs = sipp.combine_partials(g1.data_ptr(), 2, 2, stream)
     assert zs[0] == oracle.inner_product(A[64 * 16:], B[:128 * 16], threads=4)
     assert zs[1] == oracle.inner_product(A[:64 * 16], B[128 * 16:], threads=4)
-
-
-def test_sharded_prove_single_rank(sipp, oracle):
-    from sipp_b200.sharded import CudaEngine, sharded_prove
-    A, B = oracle.seeded_inputs(78, 16, threads=4)
-    proof = sharded_prove(CudaEngine(), A, B, 16, A, B, rank=0, world=1)
-    assert b"".join(proof) == oracle.sipp_prove(A, B, threads=4)
 
 
 def test_inner_product_many_pairs_per_group(sipp, oracle):
@@ -407,3 +403,104 @@ def test_fold_large_round_straus_vs_split(sipp, oracle):
     for i in (0, 5, 7, 9, 11, 123, h - 1):
         assert fa[64 * i:64 * i + 64] == oracle.fold_g1(A[64 * i:64 * i + 64] + A[64 * (h + i):64 * (h + i) + 64], x), i
         assert fb[128 * i:128 * i + 128] == oracle.fold_g2(B[128 * i:128 * i + 128] + B[128 * (h + i):128 * (h + i) + 128], xinv), i
+
+
+# twist points (on y^2 = x^3 + 3/xi) that are NOT in the order-r subgroup, made with the pure-Python model (a random twist point, and
+# r times it: a point whose order divides the cofactor 2p - r)
+TWIST_NOT_G2 = H("fbee9e35ab3c0ac619c62937bfe3caf537f37ffb5991752a801d56df83aea70a5de70f4aba744b50f26b23f62869ea32968c0a8a8e5449e0444c86ada8f60b28"
+                 "b220740d239210aa74480d7e4ebe546a6b9f5fa2f8cf8c0a0a4580f18c2e612775f82b46ee8dc7599bf9c136ec784e777e061d68a3c8d110c06b2a0e0d572002")
+TWIST_COFACTOR_ORDER = H("2b66479ac463b5b5f53b9cfd46efe028fe7bea566ff042edbbc48c198673c32a531c699076c6076499d44db1348fa2825f4f0673f09890f44761c3415a3db52e"
+                         "e03c1427e3e064c6723f718785f986642fb9f61a77a8b4fe5d9c49913e5c95273c79ed1afc24de83175a47fc30a1e3aa56e552ca537aba0f361143c88cb49a23")
+
+
+def test_point_validation(sipp, oracle):
+    """what G1Affine::new / G2Affine::new assert when the reference's inputs are built: points off the curve and twist points outside
+    the order-r subgroup are refused by every entry point that takes points (SIPP_ERR_ENCODING); valid points, the identity
+    included, pass; SIPP_OPT_VALIDATE_POINTS = 0 restores trusted-input behaviour"""
+    from sipp_b200 import _lib
+    assert oracle.g2_on_curve(TWIST_NOT_G2) and oracle.g2_on_curve(TWIST_COFACTOR_ORDER)
+    n = 8
+    A, B = oracle.seeded_inputs(91, n)
+    ident = bytearray(A), bytearray(B)
+    ident[0][64:128] = bytes(64)
+    ident[1][128 * 5:128 * 6] = bytes(128)
+    assert b"".join(sipp.sipp_prove_native(bytes(ident[0]), bytes(ident[1]))) == oracle.sipp_prove(bytes(ident[0]), bytes(ident[1]))
+    proof = sipp.sipp_prove_native(A, B)
+
+    def expect_refused(a, b, what):
+        for call in (lambda: sipp.sipp_prove_native(a, b), lambda: sipp.inner_product(a, b), lambda: sipp.sipp_verify_native(a, b, proof),
+                     lambda: sipp.sipp_prove_native_batch(a, b, 4), lambda: sipp.sipp_verify_native_batch(a, b, 8, [proof])):
+            with pytest.raises(sipp.SippError) as ei:
+                call()
+            assert ei.value.code == _lib.ERR_ENCODING and what in str(ei.value), str(ei.value)
+    bad = bytearray(A)
+    bad[64 * 3 + 32] ^= 1                                      # y of A_3: off y^2 = x^3 + 3
+    expect_refused(bytes(bad), B, "not on the curve")
+    bad = bytearray(B)
+    bad[128 * 2 + 64] ^= 1                                     # y.c0 of B_2: off the twist
+    expect_refused(A, bytes(bad), "not on the curve")
+    for pt in (TWIST_NOT_G2, TWIST_COFACTOR_ORDER):
+        bad = bytearray(B)
+        bad[128 * 6:128 * 7] = pt
+        expect_refused(A, bytes(bad), "subgroup")
+    sipp.set_option(_lib.OPT_VALIDATE_POINTS, 0)
+    try:
+        bad = bytearray(B)
+        bad[128 * 6:128 * 7] = TWIST_NOT_G2
+        sipp.inner_product(A, bytes(bad))                      # trusted inputs: no check, no error (value unspecified)
+    finally:
+        sipp.set_option(_lib.OPT_VALIDATE_POINTS, 1)
+    # 3,000 valid points in one launch (every block / warp shape of the kernel), none refused
+    A3, B3 = sipp.seeded_inputs(92, 3000)
+    assert sipp.inner_product(A3, B3) == oracle.inner_product(A3, B3, threads=16)
+
+
+def test_verifier_refuses_non_canonical_proof(sipp, oracle):
+    """a proof element with a coordinate c + p (< 2^256) reduces to the same field element but hashes differently; ark's
+    deserialisation cannot produce it, so the verifier refuses it instead of accepting a malleated proof"""
+    from sipp_b200 import _lib
+    n = 4
+    A, B = oracle.seeded_inputs(93, n)
+    proof = sipp.sipp_prove_native(A, B)
+    z = bytearray(proof[-1])
+    c = int.from_bytes(z[:32], "little")
+    assert c + P < 2**256
+    z[:32] = (c + P).to_bytes(32, "little")
+    bad = proof[:-1] + [bytes(z)]
+    with pytest.raises(sipp.SippError) as ei:
+        sipp.sipp_verify_native(A, B, bad)
+    assert ei.value.code == _lib.ERR_ENCODING
+    res = (ctypes.c_int * 2)()
+    lib = _lib.load()
+    assert lib.sipp_verify_native_batch(A + A, B + B, n, 2, b"".join(proof) + b"".join(bad), len(proof), res, None, None, None) == 0
+    assert list(res) == [0, _lib.ERR_ENCODING]
+
+
+def test_gt_fold_machine_matches_oracle(sipp, lib, oracle):
+    """Z_L^x * Z * Z_R^(x^-1) (verifier_native.rs:59-61) on the two 32-lane machines (k_gt_fold_eng) == the one-thread-per-power
+    kernel == the oracle's generic powers, on arbitrary Fq12 elements (not in the cyclotomic subgroup) and edge exponents"""
+    from sipp_b200 import _lib
+    rng = random.Random(17)
+    for x in (1, 2, 3, R - 1, rng.randrange(1, R), rng.randrange(1, R), 1 << 253):
+        xinv = pow(x, -1, R)
+        zl, z, zr = (b"".join(le(rng.randrange(P)) for _ in range(12)) for _ in range(3))
+        outs = []
+        for eng in (1, 0):
+            sipp.set_option(_lib.OPT_FE_ENGINE, eng)
+            out = ctypes.create_string_buffer(384)
+            try:
+                assert lib.sipp_gt_fold(zl, z, zr, le(x), le(xinv), out) == 0
+            finally:
+                sipp.set_option(_lib.OPT_FE_ENGINE, 1)
+            outs.append(out.raw)
+        assert outs[0] == outs[1]
+
+        def power(base, e):
+            acc = ONE12
+            for bit in bin(e)[2:]:
+                acc = oracle.field_op("FQ12_SQR", acc)
+                if bit == "1":
+                    acc = oracle.field_op("FQ12_MUL", acc, base)
+            return acc
+        want = oracle.field_op("FQ12_MUL", oracle.field_op("FQ12_MUL", power(zl, x), z), power(zr, xinv))
+        assert outs[0] == want

@@ -154,3 +154,24 @@ def test_fq12_machine_final_exp(hc, oracle):
             levels = hc.hc_final_exp(1, f, b, ark)
             assert a.raw == b.raw and levels > 500
     subprocess.check_call([os.environ.get("PYTHON", "python"), os.path.join(ROOT, "tools", "gen_fq12_programs.py"), "--check"], stdout=subprocess.DEVNULL)
+
+
+def test_fq12_machine_generic_power(hc):
+    """the verifier's Z_L^x (verifier_native.rs:59-61) through the MUL12Y chain links (the code k_gt_fold_eng runs) == plain
+    square-and-multiply in the pure-Python model, on elements OUTSIDE the cyclotomic subgroup, incl. edge exponents"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import sipp_model as m
+    hc.hc_pow_machine.restype = ctypes.c_long
+    rng = random.Random(12)
+    for k in (0, 1, 2, 3, 4, R - 1, rng.randrange(R), rng.randrange(R), (1 << 253) + 1, 3 << 200):
+        f = [(rng.randrange(P), rng.randrange(P)) for _ in range(6)]
+        out = _buf(384)
+        levels = hc.hc_pow_machine(m.f12_bytes(f), le(k), out)
+        want = list(m.F12_ONE)
+        for bit in bin(k)[2:] if k else "":
+            want = m.f12_sqr(want)
+            if bit == "1":
+                want = m.f12_mul(want, f)
+        assert out.raw == m.f12_bytes(want), hex(k)
+        assert levels <= 2 * (256 + 128) + 8

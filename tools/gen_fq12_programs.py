@@ -108,7 +108,7 @@ def emit_mul12(p, d, a, b, pre=True, post_xi=False):
     p.dot(6, ops)
     ops = [(val(d, k, c), [(1, H(2 * k + c)), (1, H(12 + 2 * k + c))]) for k in range(6) for c in range(2)]
     if post_xi:
-        for k in range(3, 6):
+        for k in range(0 if post_xi == "all" else 3, 6):
             ops += xi_of_sum(reg2(d, k, True), [(1, (H(2 * k), H(2 * k + 1))), (1, (H(12 + 2 * k), H(12 + 2 * k + 1)))])
     p.lin(ops)
 
@@ -123,6 +123,15 @@ def build_mul12x():
     """link of an exponentiation chain: D = A * B with B's xi slots valid on entry, D's xi slots 3..5 valid on exit"""
     p = Program("MUL12X")
     emit_mul12(p, "D", "A", "B", pre=False, post_xi=True)
+    return p
+
+
+def build_mul12y():
+    """link of a GENERIC power chain (the verifier's Z_L^x, verifier_native.rs:59-61 -- proof elements need not be cyclotomic):
+    D = A * B with all of B's xi slots valid on entry and all of D's valid on exit, so squarings D = D * D and products by a
+    table entry chain without LIN levels of their own"""
+    p = Program("MUL12Y")
+    emit_mul12(p, "D", "A", "B", pre=False, post_xi="all")
     return p
 
 
@@ -349,6 +358,21 @@ def self_check(progs):
             want = m.f12_mul(want, cyc)
             assert mc.get12("R8") == want, step
     assert mc.get12("R7") == cyc
+    # generic power chain: MUL12Y squares in place and multiplies by a table entry prepared once by XI6
+    mc.set12("R1", a)
+    mc.run(progs["XI6"], "R1", "R1")
+    mc.run(progs["COPYX"], "R2", "R1")
+    want = a
+    for step in range(7):
+        mc.run(progs["MUL12Y"], "R2", "R2", "R2")
+        want = m.f12_sqr(want)
+        assert mc.get12("R2") == want, step
+        if step % 2 == 0:
+            mc.run(progs["MUL12Y"], "R2", "R2", "R1")
+            want = m.f12_mul(want, a)
+            assert mc.get12("R2") == want, step
+    mc.run(progs["MUL12Y"], "R3", "R2", "R1")                      # not in place
+    assert mc.get12("R3") == m.f12_mul(want, a) and mc.get12("R1") == a
     return True
 
 
@@ -362,7 +386,7 @@ def enc_slot(s):
 
 
 def emit(progs, path):
-    order = ["MUL12", "CSQR", "FROB1", "FROB2", "FROB3", "CONJ", "COPY", "INV12", "SPARSE", "MUL12X", "CSQRX", "XI6", "COPYX"]
+    order = ["MUL12", "CSQR", "FROB1", "FROB2", "FROB3", "CONJ", "COPY", "INV12", "SPARSE", "MUL12X", "CSQRX", "XI6", "COPYX", "MUL12Y"]
     code, types, index = [], [], {}
     dump = ("G", 63)  # idle lanes write X(2), which no program reads
     for name in order:
@@ -422,7 +446,7 @@ def emit(progs, path):
 def main():
     progs = {"MUL12": build_mul12(), "CSQR": build_csqr(), "FROB1": build_frob(1), "FROB2": build_frob(2), "FROB3": build_frob(3),
              "CONJ": build_conj(), "COPY": build_copy(), "INV12": build_inv12(), "SPARSE": build_sparse(),
-             "MUL12X": build_mul12x(), "CSQRX": build_csqr(fused=True), "XI6": build_xi6(), "COPYX": build_copyx()}
+             "MUL12X": build_mul12x(), "CSQRX": build_csqr(fused=True), "XI6": build_xi6(), "COPYX": build_copyx(), "MUL12Y": build_mul12y()}
     if "--check" in sys.argv:
         self_check(progs)
         print("self-check against the model: ok")
