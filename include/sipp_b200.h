@@ -220,9 +220,27 @@ int sipp_verify_native_batch(const uint8_t *A, const uint8_t *B, size_t n, size_
 /* same with DEVICE buffers in boundary format (inputs resident in HBM, proofs left in HBM) */
 int sipp_prove_native_batch_device(const void *dA, const void *dB, size_t n, size_t count, void *d_proofs);
 
+/* ---- input producers of the BLS-aggregation demo (bin/bls_aggregation.rs:95-117) ---------------------------- */
+/* Scalars are 32-byte little-endian integers < r.  The `_device` forms take DEVICE pointers in the same formats.
+ * `map_to_g2_without_cofactor_mul(u).mul_by_cofactor()` (:100-104) is not provided: it lives in the un-vendored starky-bn254
+ * crate and has no specification offline. */
+/* public_keys[i] = (G1Affine::generator() * sk_i).into()                  :96-99   -> out: count x 64 B */
+int sipp_g1_generator_mul_batch(const uint8_t *scalars, size_t count, uint8_t *out);
+int sipp_g1_generator_mul_batch_device(const void *d_scalars, size_t count, void *d_out);
+/* signatures[i] = (m_i * sk_i).into()                                     :105-109 -> out: count x 128 B
+ * point_count = count: one point per scalar; point_count = 1: every scalar multiplies points[0] (window table, no doublings) */
+int sipp_g2_mul_batch(const uint8_t *points, size_t point_count, const uint8_t *scalars, size_t count, uint8_t *out);
+int sipp_g2_mul_batch_device(const void *d_points, size_t point_count, const void *d_scalars, size_t count, void *d_out);
+/* signatures.iter().fold(G2Projective::zero(), |acc, &s| acc + s).into()  :110-113 -> out: 128 B (count = 0: the identity) */
+int sipp_g2_sum(const uint8_t *points, size_t count, uint8_t out[128]);
+int sipp_g2_sum_device(const void *d_points, size_t count, void *d_out);
+/* -G1Affine::generator()                                                  :116 (host only) */
+int sipp_g1_neg_generator(uint8_t out[64]);
+
 /* ---- synthetic inputs and instrumentation --------------------------------------------------------------- */
-/* A_i = [a_i]G1, B_i = [b_i]G2 with the documented SplitMix64 scalar stream (same as oracle_seeded_inputs);
- * generated on the GPU into DEVICE buffers dA (n x 64 B), dB (n x 128 B) in boundary format */
+/* A_i = [a_i]G1, B_i = [b_i]G2 with the documented SplitMix64 scalar stream (same as oracle_seeded_inputs), generated on the
+ * GPU by the producers above (keygen over the window tables of the two generators) into DEVICE buffers dA (n x 64 B),
+ * dB (n x 128 B) in boundary format */
 int sipp_seeded_inputs_device(uint64_t seed, size_t n, void *dA, void *dB);
 int sipp_seeded_inputs(uint64_t seed, size_t n, uint8_t *A, uint8_t *B);
 

@@ -5,6 +5,6 @@ mirror of the reference interface used by the tests and bench.py.  Nothing here 
 Poseidon transcript, which the reference also keeps on the host.
 """
 from .api import (ProverContext, SIPPStatement, Transcript, VerificationError, combine_partials, fr_inverse,  # noqa: F401
-                  inner_product, pairing, seeded_inputs, set_option, sipp_prove_native, sipp_prove_native_batch,
+                  g1_generator_mul_batch, g1_neg_generator, g2_mul_batch, g2_sum, inner_product, pairing, seeded_inputs, set_option, sipp_prove_native, sipp_prove_native_batch,
                   sipp_verify_native, sipp_verify_native_batch, stats)
 from ._lib import SippError  # noqa: F401

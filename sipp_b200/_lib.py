@@ -110,6 +110,13 @@ def load():
     lib.sipp_statement_u32_len.restype = sz
     lib.sipp_statement_to_u32.argtypes = [u8p, u8p, sz, u8p, u8p, u8p, u8p, u32p, sz]
     lib.sipp_statement_from_u32.argtypes = [sz, u32p, sz, u8p, u8p, u8p, u8p, u8p, u8p]
+    lib.sipp_g1_generator_mul_batch.argtypes = [u8p, sz, u8p]
+    lib.sipp_g1_generator_mul_batch_device.argtypes = [vp, sz, vp]
+    lib.sipp_g2_mul_batch.argtypes = [u8p, sz, u8p, sz, u8p]
+    lib.sipp_g2_mul_batch_device.argtypes = [vp, sz, vp, sz, vp]
+    lib.sipp_g2_sum.argtypes = [u8p, sz, u8p]
+    lib.sipp_g2_sum_device.argtypes = [vp, sz, vp]
+    lib.sipp_g1_neg_generator.argtypes = [u8p]
     lib.sipp_comm_get_unique_id.argtypes = [u8p]
     lib.sipp_comm_init.argtypes = [u8p, i, i]
     lib.sipp_comm_init_host.argtypes = [i, i, ALLGATHER_FN, BROADCAST_FN, vp]

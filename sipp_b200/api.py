@@ -300,6 +300,42 @@ def fr_inverse(x: bytes) -> bytes:
     return out.raw
 
 
+# ---- input producers of the BLS-aggregation demo (bin/bls_aggregation.rs:95-117) ---------------------------------------------
+def g1_generator_mul_batch(scalars: Points) -> List[bytes]:
+    """public_keys[i] = (G1Affine::generator() * sk_i).into()   (bls_aggregation.rs:96-99)"""
+    k = _flat(scalars, FR_BYTES)
+    _lib.require_gpu_once()
+    out = ctypes.create_string_buffer(G1_BYTES * (len(k) // FR_BYTES))
+    _lib.check(_lib.load().sipp_g1_generator_mul_batch(k, len(k) // FR_BYTES, out))
+    return _split(out.raw, G1_BYTES)
+
+
+def g2_mul_batch(points: Points, scalars: Points) -> List[bytes]:
+    """signatures[i] = (m_i * sk_i).into()   (bls_aggregation.rs:105-109); a single point multiplies every scalar"""
+    p, k = _flat(points, G2_BYTES), _flat(scalars, FR_BYTES)
+    _lib.require_gpu_once()
+    count = len(k) // FR_BYTES
+    out = ctypes.create_string_buffer(G2_BYTES * count)
+    _lib.check(_lib.load().sipp_g2_mul_batch(p, len(p) // G2_BYTES, k, count, out))
+    return _split(out.raw, G2_BYTES)
+
+
+def g2_sum(points: Points) -> bytes:
+    """signatures.iter().fold(G2Projective::zero(), |acc, &s| acc + s).into()   (bls_aggregation.rs:110-113)"""
+    p = _flat(points, G2_BYTES)
+    _lib.require_gpu_once()
+    out = ctypes.create_string_buffer(G2_BYTES)
+    _lib.check(_lib.load().sipp_g2_sum(p, len(p) // G2_BYTES, out))
+    return out.raw
+
+
+def g1_neg_generator() -> bytes:
+    """-G1Affine::generator()   (bls_aggregation.rs:116)"""
+    out = ctypes.create_string_buffer(G1_BYTES)
+    _lib.check(_lib.load().sipp_g1_neg_generator(out))
+    return out.raw
+
+
 def seeded_inputs(seed: int, n: int):
     """A_i = [a_i]G1, B_i = [b_i]G2 with the documented SplitMix64 scalar stream, generated on the GPU."""
     _lib.require_gpu_once()

@@ -40,7 +40,6 @@ int launch_fold(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaSt
 int launch_fold_wide(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s);
 // on-curve + G2 subgroup check of decoded points: flags |= 2 (off the curve), |= 4 (outside the prime-order subgroup)
 int launch_validate_points(const uint32_t* dA, const uint32_t* dB, size_t n, int* flags, cudaStream_t s);
-int launch_seeded_inputs(uint64_t seed, size_t n, uint32_t* dA, uint32_t* dB, cudaStream_t s);
 int launch_test_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s);
 int launch_test_fq12_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s);
 int launch_microbench(int which, int blocks, int threads, void* out, int iters, uint32_t seed, double* ops_per_thread, cudaStream_t s);
@@ -78,5 +77,15 @@ int launch_tr_round(uint64_t* states, const uint32_t* proofs, size_t np, int slo
 int launch_test_poseidon(uint64_t* states, size_t count, cudaStream_t s);
 int launch_gt_fold_batch(const uint32_t* proofs, size_t stride, int slot_l, int slot_r, const uint64_t* challenges, uint32_t* z, size_t count,
                          cudaStream_t s);
+
+// BLS input producers (k_bls.cu): group 1 = G1 (16 words per point), 2 = G2 (32 words)
+size_t window_table_bytes(int group);
+int launch_window_table(int group, const uint32_t* base, uint32_t* table, cudaStream_t s);
+int launch_fixed_base_mul(int group, const uint32_t* table, const uint32_t* scalars, size_t count, uint32_t* out, cudaStream_t s);
+int launch_g2_mul_var(const uint32_t* points, const uint32_t* scalars, size_t count, uint32_t* out, cudaStream_t s);
+int g2_sum_blocks(size_t count, int sm_count);
+int launch_g2_sum(const uint32_t* points, size_t count, uint32_t* partials, int blocks, uint32_t* out, cudaStream_t s);
+int launch_seeded_scalars(uint64_t seed, size_t n, uint32_t* sa, uint32_t* sb, cudaStream_t s);
+int launch_generators(uint32_t* gens, cudaStream_t s);
 
 }  // namespace sipp

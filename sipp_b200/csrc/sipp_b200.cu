@@ -762,41 +762,6 @@ int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t 
     return SIPP_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ inputs
-int sipp_seeded_inputs_device(uint64_t seed, size_t n, void* dA, void* dB) {
-    int rc = ensure_init();
-    if (rc) return rc;
-    if (!dA || !dB || n == 0) return fail(SIPP_ERR_ARG, "bad argument");
-    {
-        Span sp(3, g_stream);
-        launch_seeded_inputs(seed, n, (uint32_t*)dA, (uint32_t*)dB, g_stream);
-    }
-    g_stats.launches++;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(g_stream));
-    return SIPP_OK;
-}
-
-int sipp_seeded_inputs(uint64_t seed, size_t n, uint8_t* A, uint8_t* B) {
-    int rc = ensure_init();
-    if (rc) return rc;
-    if (!A || !B || n == 0) return fail(SIPP_ERR_ARG, "bad argument");
-    uint8_t *dA, *dB;
-    CK(cudaMalloc(&dA, n * 64));
-    cudaError_t e = cudaMalloc(&dB, n * 128);
-    if (e != cudaSuccess) { cudaFree(dA); return cuda_fail(e, "cudaMalloc"); }
-    rc = sipp_seeded_inputs_device(seed, n, dA, dB);
-    if (!rc) {
-        e = cudaMemcpyAsync(A, dA, n * 64, cudaMemcpyDeviceToHost, g_stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(B, dB, n * 128, cudaMemcpyDeviceToHost, g_stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "D2H");
-    }
-    cudaFree(dA);
-    cudaFree(dB);
-    return rc;
-}
-
 // ------------------------------------------------------------------------------------------------ test hooks
 int sipp_test_fq_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t count) {
     int rc = ensure_init();

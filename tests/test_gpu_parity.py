@@ -347,30 +347,91 @@ def test_roundtrip_property_large(sipp):
     sipp.sipp_verify_native(A, B, proof)
 
 
-def test_bls_aggregation_shape(sipp, oracle, golden):
-    """The demo's instance shape (bin/bls_aggregation.rs:95-122): 127 (pk_i, H(m_i)) pairs and (-G1, sigma_agg); the product of
-    a valid aggregate signature is 1, and that 128-pair statement proves and verifies.  pk_i = [a_i]G1 and H_i = [b_i]G2 come from
-    the seeded generator (the demo's hash-to-G2 lives in an un-vendored crate), sigma_agg = [sum a_i b_i]G2 is built on the GPU
-    with the fold kernel (B1 + s B2 with B1 = identity)."""
-    n = 127
-    A, B = sipp.seeded_inputs(21, n)
-    sc = oracle.seeded_scalars(21, n)                       # a_0, b_0, a_1, b_1, ...
-    ks = [int.from_bytes(sc[32 * i:32 * i + 32], "little") for i in range(2 * n)]
-    s = sum(ks[2 * i] * ks[2 * i + 1] for i in range(n)) % R
+def test_bls_producers_against_oracle(sipp, oracle, golden):
+    """the demo's input producers (bin/bls_aggregation.rs:95-117) one by one against the oracle's double-and-add: keygen over the
+    generator's window table, variable-base signing, fixed-base G2 over a table built on the fly, the sum as a tree; edge scalars
+    (0 -> identity, 1, r - 1, single bytes set), identity points, empty and ragged sizes"""
+    from sipp_b200 import _lib
+    rng = random.Random(23)
+    g1, g2 = H(golden["pairing_gen"]["a"]), H(golden["pairing_gen"]["b"])
+    ks = [0, 1, 2, R - 1, 255, 256, 1 << 248, (1 << 253) + 5] + [rng.randrange(R) for _ in range(200)]
+    kb = b"".join(le(k) for k in ks)
+    pks = sipp.g1_generator_mul_batch(kb)
+    assert pks[0] == bytes(64) and pks[1] == g1
+    assert pks == [oracle.g1_mul(g1, le(k)) for k in ks]
+    # signing: one message point per key (variable base), messages = multiples of the generator with a few identities
+    ms = [oracle.g2_mul(g2, le(rng.randrange(1, R))) for _ in range(37)]
+    ms[5] = bytes(128)
+    sk = [le(k) for k in ks[:37]]
+    sigs = sipp.g2_mul_batch(ms, sk)
+    assert sigs == [oracle.g2_mul(m, k) for m, k in zip(ms, sk)]
+    # one base for every scalar: small counts walk the base, larger ones build its window table
+    for cnt in (3, 208):
+        got = sipp.g2_mul_batch(ms[7], kb[:32 * cnt])
+        assert got == [oracle.g2_mul(ms[7], le(k)) for k in ks[:cnt]]
+    # sum: sizes around the block / thread shape of the tree, identities inside, P + (-P)
+    pts = sipp.g2_mul_batch(g2, b"".join(le(rng.randrange(1, R)) for _ in range(700)))
+
+    def neg2(q):
+        x, y0, y1 = q[:64], int.from_bytes(q[64:96], "little"), int.from_bytes(q[96:], "little")
+        return x + le((P - y0) % P) + le((P - y1) % P)
+    for cnt in (0, 1, 2, 127, 128, 129, 513, 700):
+        sel = list(pts[:cnt])
+        if cnt >= 129:
+            sel[3] = bytes(128)
+            sel[100] = neg2(sel[99])
+        acc = None
+        want = bytes(128)
+        if sel:
+            # oracle sum through fold_g2 with scalar 1: (B1 + 1 * B2) pairwise tree
+            cur = list(sel)
+            while len(cur) > 1:
+                if len(cur) % 2:
+                    cur.append(bytes(128))
+                hlen = len(cur) // 2
+                folded = oracle.fold_g2(b"".join(cur), le(1))
+                cur = [folded[128 * i:128 * i + 128] for i in range(hlen)]
+            want = cur[0]
+        assert sipp.g2_sum(sel) == want, cnt
+    assert sipp.g1_neg_generator() == le(1) + le(P - 2)
+    # error behaviour: a scalar >= r, a coordinate >= p
+    with pytest.raises(sipp.SippError) as ei:
+        sipp.g1_generator_mul_batch(le(R))
+    assert ei.value.code == _lib.ERR_ENCODING
+    with pytest.raises(sipp.SippError) as ei:
+        sipp.g2_sum(le(P) + bytes(96))
+    assert ei.value.code == _lib.ERR_ENCODING
+
+
+def test_bls_aggregation_demo(sipp, oracle, golden):
+    """bin/bls_aggregation.rs:93-122 with the library's producers: 127 key pairs, 127 messages in G2, signatures, the aggregate,
+    the 128-pair instance (pk_i, m_i) + (-G1, sigma): inner product == 1, prove, verify -- every step against the oracle.
+    (The demo's messages come from hash-to-G2, which lives in an un-vendored crate; here m_i = [h_i] G2 for seeded h_i.)"""
+    n = 128
+    rng = random.Random(24)
     g2 = H(golden["pairing_gen"]["b"])
-    ctx = sipp.ProverContext(bytes(64) + le(1) + le(2), bytes(128) + g2)
-    ctx.fold(le(1), le(s))                                  # B' = identity + s G2  (x^-1 slot carries the scalar)
-    _, sigma = ctx.read()
-    assert sigma == oracle.g2_mul(g2, le(s))
-    neg_g1 = le(1) + le(P - 2)
-    A2, B2 = A + neg_g1, B + sigma
-    assert sipp.inner_product(A2, B2) == ONE12              # assert!(inner_product(&A, &B) == Fq12::one())  :119
-    proof = sipp.sipp_prove_native(A2, B2)                  # :120-122
-    st = sipp.sipp_verify_native(A2, B2, proof)
+    sks = [le(rng.randrange(1, R)) for _ in range(n - 1)]                         # private_keys  :95
+    pks = sipp.g1_generator_mul_batch(sks)                                        # public_keys   :96-99
+    ms = sipp.g2_mul_batch(g2, [le(rng.randrange(1, R)) for _ in range(n - 1)])   # messages in G2 (stand-in for :100-104)
+    sigs = sipp.g2_mul_batch(ms, sks)                                             # signatures    :105-109
+    sigma = sipp.g2_sum(sigs)                                                     # aggregated    :110-113
+    assert all(oracle.g2_on_curve(s) for s in sigs[:5]) and sigs[0] == oracle.g2_mul(ms[0], sks[0])
+    A2 = b"".join(pks) + sipp.g1_neg_generator()                                  # a.push(-G1)   :116
+    B2 = b"".join(ms) + sigma                                                     # b.push(sigma) :117
+    assert sipp.inner_product(A2, B2) == ONE12                                    # assert_eq!(inner_product(&a, &b), Fq12::one())  :119
+    proof = sipp.sipp_prove_native(A2, B2)                                        # :120
+    st = sipp.sipp_verify_native(A2, B2, proof)                                   # :121
+    assert sipp.pairing(st.final_A, st.final_B) == st.final_Z                     # :122
     assert proof[-1] == ONE12 and st.Z == ONE12
     assert b"".join(proof) == oracle.sipp_prove(A2, B2, threads=8)
-    # a forged aggregate (one message signed with the wrong key) is not the identity
-    assert sipp.inner_product(A2, B + oracle.g2_mul(g2, le((s + 1) % R))) != ONE12
+    # a forged aggregate (one signature dropped) does not give the identity
+    assert sipp.inner_product(A2, b"".join(ms) + sipp.g2_sum(sigs[1:])) != ONE12
+
+
+def test_seeded_inputs_match_oracle_generator(sipp, oracle):
+    """the synthetic inputs of every benchmark are keygen over the two generators' window tables: same bytes as the oracle's"""
+    for seed, n in ((1, 1), (2, 77), (9, 1500)):
+        assert sipp.seeded_inputs(seed, n) == oracle.seeded_inputs(seed, n, threads=8)
 
 
 def test_fold_large_round_straus_vs_split(sipp, oracle):
