@@ -279,6 +279,8 @@ int sipp_test_transcript_round_device(uint64_t *states, const uint8_t *fq12s, in
 /* host copy of the binary Fr inversion used by the device transcript (glv_core.h): 0 ok, -1 x >= r, -2 x == 0; no GPU needed */
 int sipp_test_fr_inverse_binary(const uint8_t x[32], uint8_t out[32]);
 int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);
+/* the derived tables of the host Poseidon (sipp::PoseidonFastTables, poseidon_fast.h), for tools/probe/poseidon_lab.cc */
+const void *sipp_test_poseidon_tables(void);
 
 #ifdef __cplusplus
 }

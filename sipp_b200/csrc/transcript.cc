@@ -273,6 +273,7 @@ void sipp_poseidon_permute(uint64_t s[12]) {
     else sipp_poseidon_permute_portable(s);
 }
 int sipp_poseidon_backend(void) { return g_use_avx512 ? 1 : 0; }
+const void* sipp_test_poseidon_tables(void) { return &g_tab; }  // benchmark hook: tools/probe/poseidon_lab.cc times the layers
 
 void sipp_transcript_new(sipp_transcript* t) { memset(t, 0, sizeof *t); }
 

@@ -1,0 +1,163 @@
+// poseidon_lab.cc -- measurements on the GPU box's host CPU behind the Poseidon design (tools/probe/README.md).
+// Build: g++ -O3 -march=x86-64-v3 -std=c++17 -o /tmp/poseidon_lab tools/probe/poseidon_lab.cc sipp_b200/csrc/transcript.o \
+//        (transcript.o from the library build; the AVX-512 file is included as source)
+// Prints: core clock estimate, latency / throughput of the scalar and vector modular products, of the MDS layer, per-permutation time.
+#include <immintrin.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <x86intrin.h>
+
+#include <chrono>
+
+extern "C" void sipp_poseidon_permute(uint64_t s[12]);
+extern "C" void sipp_poseidon_permute_portable(uint64_t s[12]);
+extern "C" int sipp_poseidon_backend(void);
+extern "C" int sipp_get_option(int) { return 0; }  // transcript.o asks for the Fq12 order switch (lives in the CUDA TU)
+
+#define T512 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
+
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// the implementation file itself: its internal helpers (anonymous namespace) are visible in this translation unit
+#include "../../sipp_b200/csrc/poseidon_avx512.cc"
+using namespace sipp;
+extern "C" const void* sipp_test_poseidon_tables(void);
+#define T256 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
+T256 static inline __m256i w_reduce(__m256i lo, __m256i hi) {
+    const __m256i eps = _mm256_set1_epi64x((long long)EPS);
+    __m256i hh = _mm256_srli_epi64(hi, 32);
+    __m256i t = _mm256_sub_epi64(lo, hh);
+    __mmask8 b = _mm256_cmplt_epu64_mask(lo, hh);
+    t = _mm256_mask_sub_epi64(t, b, t, eps);
+    __m256i m = _mm256_mul_epu32(hi, eps);
+    __m256i r = _mm256_add_epi64(t, m);
+    __mmask8 c = _mm256_cmplt_epu64_mask(r, m);
+    return _mm256_mask_add_epi64(r, c, r, eps);
+}
+T256 static inline __m256i w_mul(__m256i x, __m256i y) {
+    const __m256i lo32 = _mm256_set1_epi64x((long long)EPS);
+    __m256i xh = _mm256_srli_epi64(x, 32), yh = _mm256_srli_epi64(y, 32);
+    __m256i ll = _mm256_mul_epu32(x, y), lh = _mm256_mul_epu32(x, yh), hl = _mm256_mul_epu32(xh, y), hh = _mm256_mul_epu32(xh, yh);
+    __m256i t0 = _mm256_add_epi64(hl, _mm256_srli_epi64(ll, 32));
+    __m256i t1 = _mm256_add_epi64(lh, _mm256_and_si256(t0, lo32));
+    __m256i hi = _mm256_add_epi64(hh, _mm256_add_epi64(_mm256_srli_epi64(t0, 32), _mm256_srli_epi64(t1, 32)));
+    __m256i lo = _mm256_or_si256(_mm256_and_si256(ll, lo32), _mm256_slli_epi64(t1, 32));
+    return w_reduce(lo, hi);
+}
+
+T512 int main() {
+    const int N = 20000000;
+    // core clock: dependent 64-bit adds retire one per cycle
+    double ghz;
+    {
+        uint64_t a = 1, b = 3;
+        double t0 = now();
+        for (int i = 0; i < N; i++) {
+            asm volatile("add %1, %0\n\tadd %1, %0\n\tadd %1, %0\n\tadd %1, %0\n\tadd %1, %0\n\tadd %1, %0\n\tadd %1, %0\n\tadd %1, %0" : "+r"(a) : "r"(b));
+        }
+        double dt = now() - t0;
+        ghz = 8.0 * N / dt / 1e9;
+        printf("core clock estimate: %.2f GHz (dependent add chain)  [%llu]\n", ghz, (unsigned long long)a);
+    }
+    auto report = [&](const char* name, double dt, double ops) { printf("%-46s %7.2f ns = %6.1f cycles\n", name, dt / ops * 1e9, dt / ops * 1e9 * ghz); };
+    {   // scalar modular product: latency
+        uint64_t x = 0x123456789abcdef1ull, y = 0xfedcba9876543211ull;
+        double t0 = now();
+        for (int i = 0; i < N; i++) x = s_mul(x, y);
+        report("scalar modmul, dependent chain", now() - t0, N);
+        uint64_t a[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+        t0 = now();
+        for (int i = 0; i < N / 8; i++)
+            for (int k = 0; k < 8; k++) a[k] = s_mul(a[k], y);
+        report("scalar modmul, 8 independent chains (per op)", now() - t0, N / 8 * 8);
+        printf("  [%llu %llu]\n", (unsigned long long)x, (unsigned long long)a[3]);
+    }
+    {   // vector modular product
+        __m512i x = _mm512_set1_epi64(0x123456789abcdef1ll), y = _mm512_set1_epi64(0x7edcba9876543211ll);
+        double t0 = now();
+        for (int i = 0; i < N / 4; i++) x = v_mul(x, y);
+        report("zmm modmul, dependent chain", now() - t0, N / 4);
+        __m512i a = x, b = y, c = _mm512_add_epi64(x, y), d = _mm512_sub_epi64(x, y);
+        t0 = now();
+        for (int i = 0; i < N / 4; i++) { a = v_mul(a, y); b = v_mul(b, y); c = v_mul(c, y); d = v_mul(d, y); }
+        report("zmm modmul, 4 independent chains (per op)", now() - t0, N / 4 * 4);
+        __m256i p = _mm256_set1_epi64x(0x123456789abcdef1ll), q = _mm256_set1_epi64x(0x7edcba9876543211ll);
+        t0 = now();
+        for (int i = 0; i < N / 4; i++) p = w_mul(p, q);
+        report("ymm modmul, dependent chain", now() - t0, N / 4);
+        __m256i e = p, f = q, g = _mm256_add_epi64(p, q), h = _mm256_sub_epi64(p, q), e2 = _mm256_add_epi64(g, q), f2 = _mm256_sub_epi64(h, q);
+        t0 = now();
+        for (int i = 0; i < N / 4; i++) { e = w_mul(e, q); f = w_mul(f, q); g = w_mul(g, q); h = w_mul(h, q); e2 = w_mul(e2, q); f2 = w_mul(f2, q); }
+        report("ymm modmul, 6 independent chains (per op)", now() - t0, N / 4 * 6);
+        alignas(64) uint64_t out[8], out2[4];
+        _mm512_store_si512(out, _mm512_add_epi64(_mm512_add_epi64(a, b), _mm512_add_epi64(c, _mm512_add_epi64(d, x))));
+        _mm256_store_si256((__m256i*)out2, _mm256_add_epi64(_mm256_add_epi64(e, f), _mm256_add_epi64(_mm256_add_epi64(g, h), _mm256_add_epi64(e2, f2))));
+        printf("  [%llu %llu %llu]\n", (unsigned long long)out[0], (unsigned long long)out2[1], (unsigned long long)_mm256_extract_epi64(p, 0));
+    }
+    {   // mixed: one zmm chain + 4 scalar chains side by side (do the scalar ports run under the 512-bit work?)
+        __m512i x = _mm512_set1_epi64(0x123456789abcdef1ll), y = _mm512_set1_epi64(0x7edcba9876543211ll);
+        uint64_t a[4] = {1, 2, 3, 4}, ys = 0xfedcba9876543211ull;
+        double t0 = now();
+        for (int i = 0; i < N / 4; i++) {
+            x = v_mul(x, y);
+            for (int k = 0; k < 4; k++) a[k] = s_mul(a[k], ys);
+        }
+        report("zmm modmul chain + 4 scalar chains (per step)", now() - t0, N / 4);
+        alignas(64) uint64_t out[8];
+        _mm512_store_si512(out, x);
+        printf("  [%llu %llu]\n", (unsigned long long)out[0], (unsigned long long)a[2]);
+    }
+    {   // the layers of a full round, each as a dependent chain over (s0, s1)
+        const PoseidonFastTables& T = *(const PoseidonFastTables*)sipp_test_poseidon_tables();
+        __m512i s0 = _mm512_set_epi64(8, 7, 6, 5, 4, 3, 2, 1), s1 = _mm512_set_epi64(0, 0, 0, 0, 12, 11, 10, 9);
+        const int R = 2000000;
+        double t0 = now();
+        for (int i = 0; i < R; i++) { s0 = v_pow7(s0); s1 = v_pow7(s1); }
+        report("S-box layer (2 zmm x^7), chained", now() - t0, R);
+        t0 = now();
+        for (int i = 0; i < R; i++) s0 = v_pow7(s0);
+        report("S-box, one zmm x^7, chained", now() - t0, R);
+        t0 = now();
+        for (int i = 0; i < R; i++) v_mds(s0, s1, T);
+        report("MDS layer, chained", now() - t0, R);
+        t0 = now();
+        for (int i = 0; i < R; i++) v_full_round(s0, s1, T.rc_full[i & 7], T);
+        report("full round, chained", now() - t0, R);
+        uint64_t u = 12345;
+        t0 = now();
+        for (int i = 0; i < R; i++) u = s_pow7(u);
+        report("scalar x^7, chained", now() - t0, R);
+        uint64_t q[4] = {1, 2, 3, 4};
+        t0 = now();
+        for (int i = 0; i < R; i++) { s0 = v_pow7(s0); for (int k = 0; k < 4; k++) q[k] = s_pow7(q[k]); }
+        report("one zmm x^7 + 4 scalar x^7 side by side", now() - t0, R);
+        alignas(64) uint64_t out[8];
+        _mm512_store_si512(out, _mm512_add_epi64(s0, s1));
+        printf("  [%llu %llu %llu]\n", (unsigned long long)out[0], (unsigned long long)u, (unsigned long long)q[1]);
+    }
+    {   // whole permutation, chained
+        uint64_t s[12];
+        for (int i = 0; i < 12; i++) s[i] = i;
+        const int P = 400000;
+        double best = 1e9;
+        for (int rep = 0; rep < 5; rep++) {
+            double t0 = now();
+            for (int i = 0; i < P; i++) sipp_poseidon_permute(s);
+            double dt = now() - t0;
+            if (dt < best) best = dt;
+        }
+        printf("backend %d\n", sipp_poseidon_backend());
+        report("Poseidon permutation (library), chained", best, P);
+        best = 1e9;
+        for (int rep = 0; rep < 3; rep++) {
+            double t0 = now();
+            for (int i = 0; i < P / 4; i++) sipp_poseidon_permute_portable(s);
+            double dt = now() - t0;
+            if (dt < best) best = dt;
+        }
+        report("Poseidon permutation (portable), chained", best, P / 4);
+        printf("  [%llu]\n", (unsigned long long)s[0]);
+    }
+    return 0;
+}
