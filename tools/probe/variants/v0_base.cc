@@ -1,0 +1,316 @@
+// poseidon_avx512.cc -- AVX-512 implementation of the plonky2 Poseidon permutation over Goldilocks (width 12).
+//
+// The Fiat-Shamir transcript of the SIPP native protocol (/root/reference/src/transcript_native.rs:25-30) is a strictly
+// sequential chain of 8n + 13 + 27 log2(n) permutations (prover_native.rs:36-39 absorbs every A_i, B_i) that must stay on
+// the host; at the sizes the GPU finishes in milliseconds this chain IS the prove time, so one permutation has to be as
+// short as the machine allows.  This file computes exactly the same function as the portable code in transcript.cc
+// (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2):
+//   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products and the
+//                  2^64 = 2^32 - 1, 2^96 = -1 reduction; the circulant MDS layer as 36 FP64 FMAs on the 32-bit halves
+//                  (sums < 2^43 are exact in double), the rotations built in registers (valignq / two-source permutes:
+//                  a store-and-reload of the state cannot be forwarded and cost 60 ns of the 119 ns round)
+//   partial rounds sparse form (tables derived in transcript.cc): the lane-0 S-box and the 11-term dot product run on the
+//                  scalar ports (mulx / adc, 192-bit lazy accumulation in two carry chains) while the rank-1 update of
+//                  lanes 1..11 runs on the vector ports.  The 11-term sum of round r reads the state of round r - 1 (one
+//                  extra product restores the missing rank-1 term) and the constant of the S-box output is folded in, so
+//                  the dependent chain of a round is the S-box, one multiply-add and one reduction.
+// Measured on the GPU box's Xeon: 1.506 -> 1.385 (dot order) -> 1.223 (register MDS) -> 1.18 -> 1.153 us per permutation
+// (scalar reduction on the carry flag of its own addition instead of a compare).
+#include <immintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../../sipp_b200/csrc/poseidon_fast.h"
+
+#if defined(__x86_64__)
+#define SIPP_AVX512 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
+
+namespace sipp {
+namespace {
+
+typedef unsigned __int128 u128;
+const uint64_t EPS = 0xFFFFFFFFull;
+const uint64_t GL_P = 0xFFFFFFFF00000001ull;
+
+// ------------------------------------------------------------------------------------------------ scalar helpers
+SIPP_AVX512 inline uint64_t s_red128(uint64_t lo, uint64_t hi) {
+    uint64_t hh = hi >> 32, hl = hi & EPS;
+    unsigned long long t, r;
+    unsigned char b = _subborrow_u64(0, lo, hh, &t);
+    if (__builtin_expect(b, 0)) t -= EPS;
+    uint64_t m = (hl << 32) - hl;
+    unsigned char c = _addcarry_u64(0, t, m, &r);   // the carry flag of the addition itself, no separate compare
+    r += (0 - (uint64_t)c) & EPS;
+    return r;
+}
+SIPP_AVX512 inline uint64_t s_mul(uint64_t a, uint64_t b) {
+    unsigned long long hi;
+    uint64_t lo = _mulx_u64(a, b, &hi);
+    return s_red128(lo, hi);
+}
+SIPP_AVX512 inline uint64_t s_add(uint64_t a, uint64_t b) {  // any a, b
+    uint64_t r = a + b;
+    uint64_t t = r + ((0 - (uint64_t)(r < a)) & EPS);
+    return t + ((0 - (uint64_t)(t < r)) & EPS);
+}
+SIPP_AVX512 inline uint64_t s_pow7(uint64_t x) {
+    uint64_t x2 = s_mul(x, x), x3 = s_mul(x2, x), x4 = s_mul(x2, x2);
+    return s_mul(x3, x4);
+}
+// sum_{i<11} a[i] * b[i] + extra_a * extra_b, reduced once (three-limb lazy accumulation; 2^128 = -2^32 mod p)
+SIPP_AVX512 inline uint64_t s_dot11p(const uint64_t* a, const uint64_t* b, uint64_t ea, uint64_t eb) {
+    unsigned long long lo = 0, hi = 0, top = 0, pl, ph;
+#pragma GCC unroll 11
+    for (int i = 0; i < 11; i++) {
+        pl = _mulx_u64(a[i], b[i], &ph);
+        unsigned char c = _addcarry_u64(0, lo, pl, &lo);
+        c = _addcarry_u64(c, hi, ph, &hi);
+        top += c;
+    }
+    // the term that depends on the S-box output of this round enters last: it is the only one on the dependent chain
+    pl = _mulx_u64(ea, eb, &ph);
+    unsigned char c = _addcarry_u64(0, lo, pl, &lo);
+    c = _addcarry_u64(c, hi, ph, &hi);
+    top += c;
+    uint64_t r = s_red128(lo, hi);
+    uint64_t t = (uint64_t)top << 32;  // top <= 12
+    uint64_t d = r - t;
+    if (__builtin_expect(r < t, 0)) d -= EPS;  // borrowed 2^64 = EPS
+    return d;
+}
+
+
+// 192-bit lazy sum of 11 products in two independent carry chains (even / odd terms)
+struct Acc192 { unsigned long long lo, hi, top; };
+SIPP_AVX512 inline Acc192 s_dot11_raw(const uint64_t* a, const uint64_t* b) {
+    unsigned long long lo0 = 0, hi0 = 0, top0 = 0, lo1 = 0, hi1 = 0, top1 = 0, pl, ph;
+    unsigned char c;
+#pragma GCC unroll 6
+    for (int i = 0; i < 11; i += 2) {
+        pl = _mulx_u64(a[i], b[i], &ph);
+        c = _addcarry_u64(0, lo0, pl, &lo0);
+        c = _addcarry_u64(c, hi0, ph, &hi0);
+        top0 += c;
+        if (i + 1 < 11) {
+            pl = _mulx_u64(a[i + 1], b[i + 1], &ph);
+            c = _addcarry_u64(0, lo1, pl, &lo1);
+            c = _addcarry_u64(c, hi1, ph, &hi1);
+            top1 += c;
+        }
+    }
+    c = _addcarry_u64(0, lo0, lo1, &lo0);
+    c = _addcarry_u64(c, hi0, hi1, &hi0);
+    return Acc192{lo0, hi0, top0 + top1 + c};
+}
+SIPP_AVX512 inline void acc_mul(Acc192& s, uint64_t a, uint64_t b) {
+    unsigned long long ph, pl = _mulx_u64(a, b, &ph);
+    unsigned char c = _addcarry_u64(0, s.lo, pl, &s.lo);
+    c = _addcarry_u64(c, s.hi, ph, &s.hi);
+    s.top += c;
+}
+SIPP_AVX512 inline uint64_t acc_reduce(const Acc192& s) {
+    uint64_t r = s_red128(s.lo, s.hi);
+    uint64_t t = (uint64_t)s.top << 32;  // top <= 13; 2^128 = -2^32
+    uint64_t d = r - t;
+    if (__builtin_expect(r < t, 0)) d -= EPS;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------ vector helpers
+SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
+    const __m512i eps = _mm512_set1_epi64((long long)EPS);
+    __m512i hh = _mm512_srli_epi64(hi, 32);
+    __m512i t = _mm512_sub_epi64(lo, hh);
+    __mmask8 b = _mm512_cmplt_epu64_mask(lo, hh);
+    t = _mm512_mask_sub_epi64(t, b, t, eps);
+    __m512i m = _mm512_mul_epu32(hi, eps);  // (hi & 0xffffffff) * (2^32 - 1)
+    __m512i r = _mm512_add_epi64(t, m);
+    __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
+    return _mm512_mask_add_epi64(r, c, r, eps);
+}
+SIPP_AVX512 inline __m512i v_mul(__m512i x, __m512i y) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
+    __m512i xh = _mm512_srli_epi64(x, 32), yh = _mm512_srli_epi64(y, 32);
+    __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
+    __m512i t0 = _mm512_add_epi64(hl, _mm512_srli_epi64(ll, 32));
+    __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
+    __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
+    __m512i lo = _mm512_or_si512(_mm512_and_si512(ll, lo32), _mm512_slli_epi64(t1, 32));
+    return v_reduce(lo, hi);
+}
+SIPP_AVX512 inline __m512i v_sqr(__m512i x) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
+    __m512i xh = _mm512_srli_epi64(x, 32);
+    __m512i ll = _mm512_mul_epu32(x, x), lh = _mm512_mul_epu32(x, xh), hh = _mm512_mul_epu32(xh, xh);
+    __m512i t0 = _mm512_add_epi64(lh, _mm512_srli_epi64(ll, 32));
+    __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
+    __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
+    __m512i lo = _mm512_or_si512(_mm512_and_si512(ll, lo32), _mm512_slli_epi64(t1, 32));
+    return v_reduce(lo, hi);
+}
+SIPP_AVX512 inline __m512i v_pow7(__m512i x) {
+    __m512i x2 = v_sqr(x), x4 = v_sqr(x2), x3 = v_mul(x2, x);
+    return v_mul(x3, x4);
+}
+// a + b with b canonical (< p): a single wrap correction suffices
+SIPP_AVX512 inline __m512i v_add_canon(__m512i a, __m512i b) {
+    const __m512i eps = _mm512_set1_epi64((long long)EPS);
+    __m512i r = _mm512_add_epi64(a, b);
+    __mmask8 c = _mm512_cmplt_epu64_mask(r, a);
+    return _mm512_mask_add_epi64(r, c, r, eps);
+}
+SIPP_AVX512 inline __m512i v_canon(__m512i a) {
+    const __m512i p = _mm512_set1_epi64((long long)GL_P);
+    return _mm512_min_epu64(a, _mm512_sub_epi64(a, p));
+}
+
+// out[r] = sum_i s[(i + r) mod 12] * CIRC[i] + 8 s[0] [r == 0] on the 32-bit halves, in FP64 (sums < 2^43 are exact).
+// The twelve rotations of the state are built in registers: with E0 = s[0..7], E1 = s[8..11, 0..3], E2 = s[4..11] the window
+// s[i..i+7] is one valignq of two neighbours.  Rows 8..11 only fill half a vector, so their low and high halves share one:
+// F_k = lo[4k..4k+3] | hi[4k..4k+3], and the window s[8+i..11+i] is a two-source permute of two neighbouring F's.
+template <int I>
+SIPP_AVX512 inline __m512d win8(__m512d e0, __m512d e1, __m512d e2) {
+    if (I == 0) return e0;
+    if (I == 8) return e1;
+    if (I < 8) return _mm512_castsi512_pd(_mm512_alignr_epi64(_mm512_castpd_si512(e1), _mm512_castpd_si512(e0), I & 7));
+    return _mm512_castsi512_pd(_mm512_alignr_epi64(_mm512_castpd_si512(e2), _mm512_castpd_si512(e1), I & 7));
+}
+SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables& T) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
+    const __m512d l0 = _mm512_cvtepu64_pd(_mm512_and_si512(s0, lo32)), l1 = _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32));
+    const __m512d h0 = _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)), h1 = _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32));
+    // rows 0..7
+    const __m512d le1 = _mm512_shuffle_f64x2(l1, l0, 0x44), le2 = _mm512_shuffle_f64x2(l0, l1, 0x4E);
+    const __m512d he1 = _mm512_shuffle_f64x2(h1, h0, 0x44), he2 = _mm512_shuffle_f64x2(h0, h1, 0x4E);
+    __m512d al0 = _mm512_mul_pd(l0, _mm512_load_pd(T.mds_c0a)), ah0 = _mm512_mul_pd(h0, _mm512_load_pd(T.mds_c0a));
+    __m512d al1, ah1, al2, ah2, al3, ah3;
+#define SIPP_MDS_A(I, ACCL, ACCH, FIRST)                                                              \
+    {                                                                                                 \
+        const __m512d c = _mm512_set1_pd(T.mds_circ[I]);                                              \
+        const __m512d wl = win8<I>(l0, le1, le2), wh = win8<I>(h0, he1, he2);                         \
+        ACCL = FIRST ? _mm512_mul_pd(wl, c) : _mm512_fmadd_pd(wl, c, ACCL);                           \
+        ACCH = FIRST ? _mm512_mul_pd(wh, c) : _mm512_fmadd_pd(wh, c, ACCH);                           \
+    }
+    SIPP_MDS_A(1, al1, ah1, true)
+    SIPP_MDS_A(2, al2, ah2, true)
+    SIPP_MDS_A(3, al3, ah3, true)
+    SIPP_MDS_A(4, al0, ah0, false)
+    SIPP_MDS_A(5, al1, ah1, false)
+    SIPP_MDS_A(6, al2, ah2, false)
+    SIPP_MDS_A(7, al3, ah3, false)
+    SIPP_MDS_A(8, al0, ah0, false)
+    SIPP_MDS_A(9, al1, ah1, false)
+    SIPP_MDS_A(10, al2, ah2, false)
+    SIPP_MDS_A(11, al3, ah3, false)
+#undef SIPP_MDS_A
+    // rows 8..11: ring of half-vectors F2, F0, F1, F2, ... starting at s[8]
+    const __m512d f0 = _mm512_shuffle_f64x2(l0, h0, 0x44), f1 = _mm512_shuffle_f64x2(l0, h0, 0xEE), f2 = _mm512_shuffle_f64x2(l1, h1, 0x44);
+    const __m512i ix1 = _mm512_load_si512(T.mds_ix[0]), ix2 = _mm512_load_si512(T.mds_ix[1]), ix3 = _mm512_load_si512(T.mds_ix[2]);
+    __m512d b0 = _mm512_mul_pd(f2, _mm512_set1_pd(T.mds_circ[0]));
+    __m512d b1 = _mm512_mul_pd(_mm512_permutex2var_pd(f2, ix1, f0), _mm512_set1_pd(T.mds_circ[1]));
+    b0 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f2, ix2, f0), _mm512_set1_pd(T.mds_circ[2]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f2, ix3, f0), _mm512_set1_pd(T.mds_circ[3]), b1);
+    b0 = _mm512_fmadd_pd(f0, _mm512_set1_pd(T.mds_circ[4]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f0, ix1, f1), _mm512_set1_pd(T.mds_circ[5]), b1);
+    b0 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f0, ix2, f1), _mm512_set1_pd(T.mds_circ[6]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f0, ix3, f1), _mm512_set1_pd(T.mds_circ[7]), b1);
+    b0 = _mm512_fmadd_pd(f1, _mm512_set1_pd(T.mds_circ[8]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f1, ix1, f2), _mm512_set1_pd(T.mds_circ[9]), b1);
+    b0 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f1, ix2, f2), _mm512_set1_pd(T.mds_circ[10]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f1, ix3, f2), _mm512_set1_pd(T.mds_circ[11]), b1);
+    const __m512i eps = lo32;
+    auto combine = [&](__m512i alo, __m512i ahi) SIPP_AVX512 {  // < 2^43 each; value = alo + 2^32 ahi
+        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
+        __mmask8 c = _mm512_cmplt_epu64_mask(lo, alo);
+        __m512i hi = _mm512_srli_epi64(ahi, 32);
+        hi = _mm512_mask_add_epi64(hi, c, hi, _mm512_set1_epi64(1));
+        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);  // hi * (2^32 - 1), hi < 2^12
+        __m512i r = _mm512_add_epi64(lo, m);
+        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
+        return _mm512_mask_add_epi64(r, c2, r, eps);
+    };
+    s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al0, al1), _mm512_add_pd(al2, al3))),
+                 _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah0, ah1), _mm512_add_pd(ah2, ah3))));
+    const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(b0, b1));  // lanes 0..3: low sums, lanes 4..7: high sums of rows 8..11
+    s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));              // lanes 4..7 of s1 are don't-care
+}
+
+SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonFastTables& T) {
+    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
+    s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
+    v_mds(s0, s1, T);
+}
+
+}  // namespace
+
+SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T) {
+    alignas(64) uint64_t buf[16];
+    memcpy(buf, s, 96);
+    buf[12] = buf[13] = buf[14] = buf[15] = 0;
+    __m512i s0 = _mm512_load_si512(buf), s1 = _mm512_load_si512(buf + 8);
+    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[k], T);
+
+    // ---- 22 partial rounds, sparse form ----
+    s0 = v_add_canon(s0, _mm512_load_si512(T.first));
+    s1 = v_add_canon(s1, _mm512_load_si512(T.first + 8));
+    _mm512_store_si512(buf, s0);
+    _mm512_store_si512(buf + 8, s1);
+    uint64_t u0 = buf[0];
+    alignas(64) uint64_t ub[16];  // ub[i] = lane i (1..11); ub[0] unused
+    {
+        uint64_t zero = 0;
+        for (int i = 0; i < 11; i++) ub[i + 1] = s_dot11p(T.init[i], buf + 1, zero, zero);
+        ub[0] = 0; ub[12] = ub[13] = ub[14] = ub[15] = 0;
+    }
+    // d_r = vhat_r . U_r + m00 x_r with U_r = U_{r-1} + x_{r-1} w_{r-1}, so d_r = vhat_r . U_{r-1} + x_{r-1} (vhat_r . w_{r-1}) + m00 x_r:
+    // the 11-term sum reads the state of ONE ROUND EARLIER (in memory long before it is needed), and the dependent chain of a
+    // round is the S-box plus two multiply-adds.  Two buffers alternate: round r reads U_{r-1}, writes U_{r+1}.
+    alignas(64) uint64_t um[2][16];
+    memcpy(um[0], ub, sizeof ub);
+    __m512i v0 = _mm512_load_si512(ub), v1 = _mm512_load_si512(ub + 8);
+    uint64_t x_prev = 0;
+    for (int r = 0; r < 22; r++) {
+        Acc192 acc = s_dot11_raw(T.vhat[r], um[r == 0 ? 0 : (r + 1) & 1] + 1);
+        acc_mul(acc, x_prev, T.kprev[r]);
+        {   // + m00 post[r] (constant), off the chain
+            unsigned char c = _addcarry_u64(0, acc.lo, T.mpost[r], &acc.lo);
+            c = _addcarry_u64(c, acc.hi, 0, &acc.hi);
+            acc.top += c;
+        }
+        const uint64_t p7 = s_pow7(u0);
+        uint64_t x = s_add(p7, T.post[r]);
+        acc_mul(acc, p7, T.m00);
+        uint64_t d = acc_reduce(acc);
+        __m512i xb = _mm512_set1_epi64((long long)x);
+        v0 = v_add_canon(v0, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r]))));
+        v1 = v_add_canon(v1, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r] + 8))));
+        _mm512_store_si512(um[(r + 1) & 1], v0);
+        _mm512_store_si512(um[(r + 1) & 1] + 8, v1);
+        x_prev = x;
+        u0 = d;
+    }
+    _mm512_store_si512(ub, v0);
+    _mm512_store_si512(ub + 8, v1);
+    ub[0] = u0;
+    s0 = _mm512_load_si512(ub);
+    s1 = _mm512_load_si512(ub + 8);
+    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[4 + k], T);
+    s0 = v_canon(s0);
+    s1 = v_canon(s1);
+    _mm512_store_si512(buf, s0);
+    _mm512_store_si512(buf + 8, s1);
+    memcpy(s, buf, 96);
+}
+
+bool poseidon_avx512_supported() {
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vl") &&
+           __builtin_cpu_supports("bmi2");
+}
+
+}  // namespace sipp
+#else
+namespace sipp {
+void poseidon_permute_avx512(uint64_t*, const PoseidonFastTables&) {}
+bool poseidon_avx512_supported() { return false; }
+}  // namespace sipp
+#endif
