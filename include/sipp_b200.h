@@ -73,6 +73,11 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          inputs are built); failure = SIPP_ERR_ENCODING.  0 = trusted inputs: the caller guarantees it (the folds
                                          use the GLV / GLS endomorphisms, which act as scalars only on the r-torsion -- results for other points
                                          are unspecified) */
+#define SIPP_OPT_MATRIX_TAIL 14       /* single proof: once at most this many points are left (default 32, 0 = off, max 64) the prover
+                                         computes E[i][j] = e(A_i, B_j) for all pairs and the remaining rounds fold that MATRIX in GT
+                                         (E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(1/x), k_mat.cu) instead of the points:
+                                         same Z_L, Z_R bit for bit, one short kernel per round.  The context's points are then left
+                                         as they were when the tail began (only its length keeps halving) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

@@ -104,6 +104,32 @@ SIPP_HD bool f12_pow_w2(M& mc, const uint32_t* k) {
     return started;
 }
 
+// register 0 <- (+-frob^comp(register 1))^k for one recoded sub-scalar k (fold_plan.h GtPlan: NAF digits, sign), register 1 a
+// CYCLOTOMIC element (a pairing value); registers 1, 2 are overwritten.  The pairing-matrix tail's GT exponentiation
+// e(A_i + x A_j, .) = e(A_i, .) e(A_j, .)^x  (/root/reference/src/prover_native.rs:60-69 carried over to GT): Frobenius images are
+// one DOT2 level, inverses are conjugates, squarings / products are CSQRX / MUL12X chain links.  Returns false when k == 0
+// (register 0 untouched: the caller writes 1).
+template <class M>
+SIPP_HD bool f12_gt_pow_comp(M& mc, int comp, const FoldComp& c, int bits) {
+    const FoldDigits d = fold_digits(c, bits);
+    if (d.top < 0) return false;
+    if (comp == 1) F12_OP2(mc, FROB1, 1, 1);
+    else if (comp == 2) F12_OP2(mc, FROB2, 1, 1);
+    else if (comp == 3) F12_OP2(mc, FROB3, 1, 1);
+    if ((c.neg != 0) != d.flip) F12_OP2(mc, CONJ, 1, 1);
+    F12_OP2(mc, XI6, 1, 1);
+    F12_OP2(mc, CONJ, 2, 1);
+    F12_OP2(mc, XI6, 2, 2);
+    F12_OP2(mc, COPYX, 0, 1);
+    for (int i = d.top - 1; i >= 0; i--) {
+        F12_OP2(mc, CSQRX, 0, 0);
+        const uint32_t bit = 1u << (i & 31);
+        if (d.plus[i >> 5] & bit) F12_OP3(mc, MUL12X, 0, 0, 1);
+        else if (d.minus[i >> 5] & bit) F12_OP3(mc, MUL12X, 0, 0, 2);
+    }
+    return true;
+}
+
 #define SIPP_F12_FE_REGS 11
 // register 0 holds f on entry; returns the register that holds f^((p^12-1)/r) (+ the arkworks multiple if ark_norm).
 // Same formulas, in the same order, as coop_final_exp (coop.cuh) / final_exponentiation (pairing.cuh).

@@ -23,8 +23,16 @@ struct FoldPlan {
     int g1_bits, g2_bits;  // NAF length (max over the components)
 };
 
+// Pairing-matrix tail (k_mat.cu): the same four-dimensional recoding applied to BOTH x and x^-1, used as exponents in GT, where the
+// p-power Frobenius acts as [L] exactly as psi does on G2 (p = 6x^2 mod r).  c[0..3]: x, c[4..7]: x^-1.
+struct GtPlan {
+    FoldComp c[8];
+    int bits;
+};
+
 int fold_decompose_g1(const uint64_t k[4], FoldSubScalar out[2]);
 int fold_decompose_g2(const uint64_t k[4], FoldSubScalar out[4]);
 int fold_plan_build(const uint8_t x[32], const uint8_t x_inv[32], FoldPlan* plan);
+int gt_plan_build(const uint8_t x[32], const uint8_t x_inv[32], GtPlan* plan);
 
 }  // namespace sipp

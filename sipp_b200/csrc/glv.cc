@@ -27,6 +27,23 @@ int fold_plan_build(const uint8_t x[32], const uint8_t x_inv[32], FoldPlan* plan
     return glv::plan_build(kx, ki, HOST_TABLES, plan);
 }
 
+int gt_plan_build(const uint8_t x[32], const uint8_t x_inv[32], GtPlan* plan) {
+    memset(plan, 0, sizeof *plan);
+    for (int which = 0; which < 2; which++) {
+        uint64_t k[4];
+        memcpy(k, which ? x_inv : x, 32);
+        FoldSubScalar s[4];
+        if (fold_decompose_g2(k, s)) return -1;
+        for (int j = 0; j < 4; j++) {
+            FoldComp& c = plan->c[4 * which + j];
+            const int len = glv::naf(s[j].mag, c.plus, c.minus);
+            c.neg = s[j].neg;
+            if (len > plan->bits) plan->bits = len;
+        }
+    }
+    return plan->bits > 32 * SIPP_FOLD_MASK_WORDS ? -1 : 0;
+}
+
 }  // namespace sipp
 
 // host copy of the inversion the device transcript uses (glv_core.h), for the CPU tests: 0 ok, -1 v >= r, -2 v == 0

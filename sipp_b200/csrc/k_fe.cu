@@ -5,30 +5,8 @@
 // k_reduce_fe_eng: product of the per-block partials (6-lane cooperative tree, as k_reduce_fe_coop) and then ONE final
 // exponentiation per product on the 32-lane Fq12 machine (engine12.cuh).  grid = nprod blocks of 128 threads.
 #include "coop.cuh"
-#include "engine12.cuh"
+#include "machine12.cuh"
 namespace sipp {
-
-static __device__ const F12Ins d_f12_code[SIPP_F12_LEVELS * SIPP_F12_LANES] = SIPP_F12_CODE_INIT;
-static __constant__ unsigned char c_f12_types[SIPP_F12_LEVELS] = SIPP_F12_TYPES_INIT;
-
-struct DevMachine12 {
-    uint32_t* slots;
-    int lane;
-    // a real call: the final exponentiation invokes ~500 programs, inlining the executor into each would explode
-    __device__ __noinline__ void run(int first, int n, int d, int a, int b) {
-        const int base[4] = {0, f12_reg_base(d), f12_reg_base(a), f12_reg_base(b)};
-#pragma unroll 1
-        for (int L = first; L < first + n; L++) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(d_f12_code) + L * SIPP_F12_LANES + lane);
-            const F12Ins ins{{w.x, w.y, w.z, w.w}};
-            Fq r;
-            const bool wr = f12_eval(c_f12_types[L], ins, slots, base, r);
-            __syncwarp();
-            if (wr) lp_store(slots, f12_slot(f12_byte(ins, 0), base), r);
-            __syncwarp();
-        }
-    }
-};
 
 #define SIPP_RFE_THREADS 128
 #define SIPP_RFE_GROUPS 20
@@ -65,8 +43,12 @@ __global__ void __launch_bounds__(SIPP_RFE_THREADS) k_reduce_fe_eng(const uint32
         n = half;
     }
     if (warp != 0) return;
-    if (!final_exp) {
-        if (active_lane && group == 0) store_fq2_words(out + prod * 96 + k * 16, f);
+    if (final_exp != 1) {  // 0: the raw product (a partial for another reduction); 2: the product of values that are already
+                           // exponentiated (pairing-matrix tail), encoded like a final-exponentiation result
+        if (active_lane && group == 0) {
+            if (final_exp == 2) fq2_encode(out + prod * 96 + ((k & 1) * 3 + (k >> 1)) * 16, f);
+            else store_fq2_words(out + prod * 96 + k * 16, f);
+        }
         return;
     }
     // hand f to the machine: register 0, slot 2k + c
@@ -102,7 +84,7 @@ __device__ __forceinline__ void acc_cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
 }
 __global__ void __launch_bounds__(SIPP_ACC_MACHINES * 32) k_accum_eng(const uint32_t* __restrict__ lines, size_t m_chunk, int kpg, uint32_t* __restrict__ partials,
-                                                                     int partial_stride_prod, int block_offset) {
+                                                                     int partial_stride_prod, int block_offset, int tree) {
     __shared__ __align__(16) uint32_t smem[SIPP_ACC_MACHINES * SIPP_ACC_SLOTS * 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int prod = blockIdx.y;
@@ -151,6 +133,14 @@ __global__ void __launch_bounds__(SIPP_ACC_MACHINES * 32) k_accum_eng(const uint
         fold_lines();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!tree) {  // pairing-matrix tail: every group's Miller value on its own (group index = output index)
+        __syncwarp();
+        if (npairs > 0) {
+            uint32_t* o = partials + ((gid + (size_t)block_offset) * partial_stride_prod + prod) * 96;
+            for (int w = lane; w < 96; w += 32) o[w] = slots[f12_reg_base(0) * 8 + w];
+        }
+        return;
+    }
     // tree product over the machines of the block: 2 <- 3 and 0 <- 1 are independent, then 0 <- 2
 #pragma unroll 1
     for (int half = SIPP_ACC_MACHINES / 2; half >= 1; half >>= 1) {
@@ -173,7 +163,13 @@ int accum_eng_blocks(size_t m_chunk, int kpg) {
 }
 int launch_accum_eng(const uint32_t* lines, size_t m_chunk, int nprod, int kpg, uint32_t* partials, int block_offset, cudaStream_t s) {
     dim3 grid((unsigned)accum_eng_blocks(m_chunk, kpg), (unsigned)nprod);
-    k_accum_eng<<<grid, SIPP_ACC_MACHINES * 32, 0, s>>>(lines, m_chunk, kpg, partials, nprod, block_offset);
+    k_accum_eng<<<grid, SIPP_ACC_MACHINES * 32, 0, s>>>(lines, m_chunk, kpg, partials, nprod, block_offset, 1);
+    return (int)cudaGetLastError();
+}
+// one Miller value per pair (no product): out[j] = 96 words, register-shaped (slot 2k + c), j < m
+int launch_accum_eng_each(const uint32_t* lines, size_t m, uint32_t* out, cudaStream_t s) {
+    dim3 grid((unsigned)accum_eng_blocks(m, 1), 1u);
+    k_accum_eng<<<grid, SIPP_ACC_MACHINES * 32, 0, s>>>(lines, m, 1, out, 1, 0, 0);
     return (int)cudaGetLastError();
 }
 

@@ -53,8 +53,15 @@ int launch_reduce_fe_coop(const uint32_t* partials, int count, int nprod, uint32
 int launch_reduce_fe_eng(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s);
 int accum_eng_blocks(size_t m_chunk, int kpg);
 int launch_accum_eng(const uint32_t* lines, size_t m_chunk, int nprod, int kpg, uint32_t* partials, int block_offset, cudaStream_t s);
+int launch_accum_eng_each(const uint32_t* lines, size_t m, uint32_t* out, cudaStream_t s);
 int launch_test_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, cudaStream_t s);
 size_t lines_bytes_per_pair();
+
+// pairing-matrix tail (k_mat.cu): E[i][j] = e(A_i, B_j) for the n points left, then folds of the MATRIX instead of the points
+int launch_mat_gather(const uint32_t* A, const uint32_t* B, size_t n, uint32_t* Aexp, uint32_t* Bexp, cudaStream_t s);
+int launch_mat_fe(const uint32_t* miller, size_t count, uint32_t* E, int ark_norm, cudaStream_t s);
+int launch_mat_diag(const uint32_t* E, size_t n, uint32_t* partials, cudaStream_t s);
+int launch_mat_fold(const uint32_t* E, size_t n, uint32_t* Eout, const GtPlan& plan, cudaStream_t s);
 
 // batched instances (k_coop.cu, k_fold.cu, k_transcript.cu)
 int launch_lines_batch(const uint32_t* A, const uint32_t* B, const BatchJob& job, size_t p0, size_t np, uint32_t* lines, cudaStream_t s);

@@ -32,6 +32,7 @@ int g_opt_fold_straus = 1;     // throughput folds (batched instances, large rou
 int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own streams (0 = choose by batch size)
 int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
+int g_opt_matrix_n = 32;       // pairing-matrix tail (k_mat.cu) once at most this many points are left; 0 = off
 int g_opt_validate = 1;        // every prove / verify entry point checks its points: on the curve, B_i in the order-r subgroup
 
 struct TimedSpan {
@@ -309,6 +310,94 @@ int ctx_products(sipp_ctx* c, int which, uint8_t* out0, uint8_t* out1) {
     return SIPP_OK;
 }
 
+// ---- pairing-matrix tail (k_mat.cu): once n <= SIPP_OPT_MATRIX_TAIL points are left, E[i][j] = e(A_i, B_j) is computed for all
+// n^2 pairs and the remaining rounds fold the MATRIX in GT instead of the points -- one short kernel per round instead of
+// fold + lines + accumulation + final exponentiation (prover_native.rs:45-75; same Z_L, Z_R bit for bit)
+struct MatTail {
+    uint32_t* E[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t n = 0;  // points the matrix stands for; 0 = not built
+    ~MatTail() {
+        pool_free(E[0]);
+        pool_free(E[1]);
+    }
+};
+bool mat_tail_wanted(size_t n) { return g_opt_pipeline && g_opt_fe_engine && n >= 2 && n <= (size_t)g_opt_matrix_n; }
+
+int mat_build(sipp_ctx* c, MatTail& mt) {
+    const size_t n = c->n, m = n * n;
+    uint32_t *aexp = nullptr, *bexp = nullptr, *mil = nullptr;
+    int rc = scratch_reserve(n);
+    if (!rc) rc = lines_reserve(m * lines_bytes_per_pair());
+    if (rc) return rc;
+    cudaError_t e = pool_alloc((void**)&mt.E[0], m * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (m / 4) * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&aexp, m * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&bexp, m * 128);
+    if (e == cudaSuccess) e = pool_alloc((void**)&mil, m * 384);
+    int le = 0;
+    if (e == cudaSuccess) {
+        {
+            Span sp(0, g_stream);
+            MillerJob job;
+            job.a_off[0] = job.b_off[0] = job.a_off[1] = job.b_off[1] = 0;
+            job.m = m;
+            le = launch_mat_gather(c->dA, c->dB, n, aexp, bexp, g_stream);
+            if (!le) le = launch_lines_wide(aexp, bexp, job, 1, 0, m, g_scr.lines, g_stream);
+            if (!le) le = launch_accum_eng_each(g_scr.lines, m, mil, g_stream);
+        }
+        if (!le) {
+            Span sp(1, g_stream);
+            le = launch_mat_fe(mil, m, mt.E[0], g_opt_fe_norm, g_stream);
+        }
+        g_stats.launches += 4;
+        g_stats.miller_launches++;
+    }
+    // the staging blocks are only reused by later work on the same stream
+    pool_free(aexp);
+    pool_free(bexp);
+    pool_free(mil);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(matrix tail)");
+    if (le) return cuda_fail((cudaError_t)le, "pairing matrix");
+    mt.n = n;
+    mt.cur = 0;
+    return SIPP_OK;
+}
+
+// Z_L = prod E[i+h][i], Z_R = prod E[i][i+h]   (prover_native.rs:48-49)
+int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr) {
+    const size_t h = mt.n / 2;
+    {
+        Span sp(1, g_stream);
+        int le = launch_mat_diag(mt.E[mt.cur], mt.n, g_scr.partials, g_stream);
+        if (!le) le = launch_reduce_fe_eng(g_scr.partials, (int)h, 2, g_scr.out, 2, g_opt_fe_norm, g_stream);
+        if (le) return cuda_fail((cudaError_t)le, "matrix products");
+    }
+    g_stats.launches += 2;
+    g_stats.miller_pairs += 2 * h;  // the pairs these two products stand for
+    CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, 2 * 384, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    memcpy(zl, g_scr.h_out, 384);
+    memcpy(zr, g_scr.h_out + 384, 384);
+    return SIPP_OK;
+}
+
+// E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(x^-1)   (prover_native.rs:60-69 in GT)
+int mat_fold(MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]) {
+    if (mt.n > 2) {  // the 1 x 1 matrix after the last round is never read
+        GtPlan plan;
+        if (gt_plan_build(x, xinv, &plan)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
+        Span sp(2, g_stream);
+        int le = launch_mat_fold(mt.E[mt.cur], mt.n, mt.E[mt.cur ^ 1], plan, g_stream);
+        if (le) return cuda_fail((cudaError_t)le, "k_mat_fold");
+        g_stats.launches++;
+        mt.cur ^= 1;
+    }
+    g_stats.fold_points += mt.n / 2;
+    mt.n /= 2;
+    return SIPP_OK;
+}
+
 }  // namespace
 
 namespace sipp_host {
@@ -388,6 +477,7 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_BATCH_STREAMS: g_opt_batch_streams = value < 0 ? 0 : value; return SIPP_OK;
         case SIPP_OPT_BATCH_QLINES: g_opt_batch_qlines = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_VALIDATE_POINTS: g_opt_validate = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_MATRIX_TAIL: g_opt_matrix_n = value < 0 ? 0 : (value > 64 ? 64 : value); return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -406,6 +496,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_BATCH_STREAMS: return g_opt_batch_streams;
         case SIPP_OPT_BATCH_QLINES: return g_opt_batch_qlines;
         case SIPP_OPT_VALIDATE_POINTS: return g_opt_validate;
+        case SIPP_OPT_MATRIX_TAIL: return g_opt_matrix_n;
         default: return -1;
     }
 }
@@ -655,10 +746,13 @@ static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
     int rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                       // let Z = inner_product(A, B);   :29
     k++;
     bool first = true;
+    MatTail mt;
     while (rc == SIPP_OK && n > 1) {                                          // :45
         uint8_t* zl = &fwd[384 * k];
         uint8_t* zr = &fwd[384 * (k + 1)];
-        rc = sipp_ctx_cross_products(c, zl, zr);                              // :46-49
+        if (!mt.n && mat_tail_wanted(n)) rc = mat_build(c, mt);               // from here on the rounds run on the pairing matrix
+        if (rc) break;
+        rc = mt.n ? mat_products(mt, zl, zr) : sipp_ctx_cross_products(c, zl, zr);  // :46-49
         if (rc) break;
         if (first) {
             g_stats.transcript_ms += job.join();                              // :36-39 finished? (exposed wait only)
@@ -674,7 +768,12 @@ static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
         rc = sipp_fr_inverse(x, xinv);                                        // :58
         g_stats.transcript_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         if (rc) break;
-        rc = sipp_ctx_fold(c, x, xinv);                                       // :60-74
+        if (mt.n) {
+            rc = mat_fold(mt, x, xinv);                                       // :60-74 on the matrix; the points stay as they were
+            c->n = n / 2;
+        } else {
+            rc = sipp_ctx_fold(c, x, xinv);                                   // :60-74
+        }
         n = c->n;
     }
     if (rc) return rc;

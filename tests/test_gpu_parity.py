@@ -259,6 +259,32 @@ def test_sipp_native_n64(sipp, oracle):
     assert ok and st.final_A == ost["final_A"] and st.final_B == ost["final_B"] and st.final_Z == ost["final_Z"]
 
 
+def test_matrix_tail_thresholds(sipp, oracle):
+    """the pairing-matrix tail (k_mat.cu: the last rounds fold E[i][j] = e(A_i, B_j) in GT instead of the points) must give the
+    proof of the point-fold route whatever the round it takes over at -- incl. from the very first round (n <= threshold), with
+    identity points on both sides, and under the arkworks final-exponentiation multiple"""
+    from sipp_b200 import _lib
+    A, B = oracle.seeded_inputs(77, 64, threads=4)
+    A = bytearray(A); B = bytearray(B)
+    A[64 * 5:64 * 6] = bytes(64)          # identity in G1
+    B[128 * 41:128 * 42] = bytes(128)     # identity in G2
+    A[64 * 9:64 * 10] = A[64 * 41:64 * 42]  # equal points in the two halves
+    A, B = bytes(A), bytes(B)
+    want = oracle.sipp_prove(A, B, threads=4)
+    try:
+        for thr in (0, 2, 4, 8, 16, 32, 64):
+            sipp.set_option(_lib.OPT_MATRIX_TAIL, thr)
+            assert b"".join(sipp.sipp_prove_native(A, B)) == want, thr
+        sipp.set_option(_lib.OPT_FE_NORMALISATION, 1)
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 0)
+        ref = b"".join(sipp.sipp_prove_native(A[:64 * 16], B[:128 * 16]))
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 8)
+        assert b"".join(sipp.sipp_prove_native(A[:64 * 16], B[:128 * 16])) == ref
+    finally:
+        sipp.set_option(_lib.OPT_FE_NORMALISATION, 0)
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 32)
+
+
 def test_prove_n128_config0(sipp, oracle):
     """BASELINE configs[0]: n = 128, prove + verify, byte-equal to the CPU reference restatement"""
     A, B = oracle.seeded_inputs(1, 128, threads=4)

@@ -175,3 +175,23 @@ def test_fq12_machine_generic_power(hc):
                 want = m.f12_mul(want, f)
         assert out.raw == m.f12_bytes(want), hex(k)
         assert levels <= 2 * (256 + 128) + 8
+
+
+def test_matrix_fold_entry(hc):
+    """k_mat_fold's entry formula on the emulated machines against the Python model: E'[i][j] = e(A_i + x A_{i+h}, B_j + x^-1 B_{j+h})
+    (prover_native.rs:60-69 carried over to GT by bilinearity), incl. x = 1, x = r - 1 and an identity point"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import sipp_model as m
+    hc.hc_mat_fold_entry.restype = ctypes.c_long
+    rng = random.Random(21)
+    A, B = m.seeded_inputs(11, 2)
+    for x in (rng.randrange(1, R), 1, R - 1, rng.randrange(1, R)):
+        xi = pow(x, -1, R)
+        a = [A[0], None if x == 1 else A[1]]
+        e = [[m.pairing(a[i], B[j]) for j in range(2)] for i in range(2)]
+        want = m.pairing(m.g1_add(a[0], m.g1_mul(a[1], x)), m.g2_add(B[0], m.g2_mul(B[1], xi)))
+        out = _buf(384)
+        levels = hc.hc_mat_fold_entry(m.f12_bytes(e[0][0]), m.f12_bytes(e[1][1]), m.f12_bytes(e[1][0]), m.f12_bytes(e[0][1]), le(x), le(xi), out)
+        assert 0 <= levels <= 2 * (67 + 34) + 8
+        assert out.raw == m.f12_bytes(want), hex(x)

@@ -1,0 +1,20 @@
+"""A/B of the pairing-matrix tail (SIPP_OPT_MATRIX_TAIL): prove time of n pairs for several thresholds.  python tools/tail_ab.py [n] [reps]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sipp_b200
+from sipp_b200 import _lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+A, B = sipp_b200.seeded_inputs(2, n)
+ref = None
+for thr in (0, 8, 16, 32, 64, 0, 32):
+    sipp_b200.set_option(_lib.OPT_MATRIX_TAIL, thr)
+    sipp_b200.sipp_prove_native(A, B)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        proof = sipp_b200.sipp_prove_native(A, B)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    p = b"".join(proof)
+    ref = ref or p
+    print("n=%d tail<=%-3d  min %.2f ms  median %.2f ms  same=%s" % (n, thr, min(ts), sorted(ts)[len(ts) // 2], p == ref), flush=True)
