@@ -9,9 +9,8 @@ struct PoseidonFastTables {
     alignas(64) uint64_t rc_full[8][16];   // round constants of the 4 + 4 full rounds, lanes 12..15 = 0
     alignas(64) uint64_t first[16];        // constants added before the first partial round
     alignas(64) uint64_t w16[22][16];      // w16[r][i] = w_r[i - 1] for i = 1..11, 0 elsewhere
-    alignas(64) double mds_c0a[8];         // CIRC[0] + 8 in lane 0, CIRC[0] elsewhere
-    double mds_circ[12];
-    alignas(64) uint64_t mds_ix[3][8];     // permutex2var indices: per 256-bit half, shift the pair (a, b) down by 1, 2, 3 elements
+    alignas(64) double mds_col_a[12][8];   // column form of the MDS layer: coefficient of s[j] in row r (r = 0..7) ...
+    alignas(64) double mds_col_b[12][8];   // ... and in row 8 + (r & 3) (rows 8..11 twice: low sums in lanes 0..3, high sums in 4..7)
     uint64_t post[22];
     uint64_t mpost[22];
     uint64_t kprev[22];                    // kprev[r] = vhat[r] . w[r-1] (0 for r = 0)

@@ -202,14 +202,13 @@ struct FastPartialInit {
         }
         for (int i = 0; i < 11; i++)
             for (int j = 0; j < 11; j++) g_tab.init[i][j] = g_fp.init[i][j];
-        for (int i = 0; i < 12; i++) g_tab.mds_circ[i] = (double)MDS_CIRC[i];
-        for (int i = 0; i < 8; i++) g_tab.mds_c0a[i] = (double)(MDS_CIRC[0] + (i == 0 ? 8 : 0));
-        g_tab.m00 = g_fp.m00;
-        for (int r = 1; r <= 3; r++)
-            for (int j = 0; j < 8; j++) {
-                int half = j >> 2, e = (j & 3) + r;  // element e of the concatenation a.half[0..3], b.half[0..3]
-                g_tab.mds_ix[r - 1][j] = (uint64_t)(e < 4 ? half * 4 + e : 8 + half * 4 + (e - 4));
+        // out[r] = sum_i s[(i + r) mod 12] CIRC[i] + 8 s[0] [r == 0]  =>  the coefficient of s[j] in row r is CIRC[(j - r) mod 12]
+        for (int j = 0; j < 12; j++)
+            for (int r = 0; r < 8; r++) {
+                g_tab.mds_col_a[j][r] = (double)(MDS_CIRC[(j - r + 12) % 12] + ((j == 0 && r == 0) ? 8 : 0));
+                g_tab.mds_col_b[j][r] = (double)MDS_CIRC[(j - 8 - (r & 3) + 24) % 12];
             }
+        g_tab.m00 = g_fp.m00;
         const char* force = getenv("SIPP_POSEIDON");  // "portable" forces the scalar path (tests compare both)
         g_use_avx512 = sipp::poseidon_avx512_supported() && !(force && !strcmp(force, "portable"));
     }

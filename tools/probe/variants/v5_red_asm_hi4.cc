@@ -5,26 +5,22 @@
 // the host; at the sizes the GPU finishes in milliseconds this chain IS the prove time, so one permutation has to be as
 // short as the machine allows.  This file computes exactly the same function as the portable code in transcript.cc
 // (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2):
-//   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products (high halves by
-//                  movehdup, the low word joined by moveldup + blend: port 5 instead of more shifts on port 0) and the
+//   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products and the
 //                  2^64 = 2^32 - 1, 2^96 = -1 reduction; the circulant MDS layer as 36 FP64 FMAs on the 32-bit halves
-//                  (sums < 2^43 are exact in double) in COLUMN form: the halves are stored once as doubles and every s[j]
-//                  comes back as a broadcast load times a constant column -- no permute network on port 5
+//                  (sums < 2^43 are exact in double), the rotations built in registers (valignq / two-source permutes:
+//                  a store-and-reload of the state cannot be forwarded and cost 60 ns of the 119 ns round)
 //   partial rounds sparse form (tables derived in transcript.cc): the lane-0 S-box and the 11-term dot product run on the
 //                  scalar ports (mulx / adc, 192-bit lazy accumulation in two carry chains) while the rank-1 update of
 //                  lanes 1..11 runs on the vector ports.  The 11-term sum of round r reads the state of round r - 1 (one
 //                  extra product restores the missing rank-1 term) and the constant of the S-box output is folded in, so
 //                  the dependent chain of a round is the S-box, one multiply-add and one reduction.
-// Measured on the GPU box's Xeon (3.79 GHz, tools/probe/run_poseidon_lab.sh): 1.506 -> 1.385 (dot order) -> 1.223 (register MDS)
-// -> 1.18 -> 1.153 (reduction on the carry flag) -> 1.116 (192-bit accumulators pinned in registers by asm blocks) -> 1.065 (the
-// scalar 128 -> 64-bit reduction as one 11-instruction asm block: latency 12.2 -> 10.3 cycles) -> 1.027 us per permutation
-// (column-form MDS, port-balanced vector product).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
-// 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
+// Measured on the GPU box's Xeon: 1.506 -> 1.385 (dot order) -> 1.223 (register MDS) -> 1.18 -> 1.153 us per permutation
+// (scalar reduction on the carry flag of its own addition instead of a compare).
 #include <immintrin.h>
 #include <stdint.h>
 #include <string.h>
 
-#include "poseidon_fast.h"
+#include "../../../sipp_b200/csrc/poseidon_fast.h"
 
 #if defined(__x86_64__)
 #define SIPP_AVX512 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
@@ -153,30 +149,24 @@ SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
     __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
     return _mm512_mask_add_epi64(r, c, r, eps);
 }
-// the high 32-bit halves as multiplier operands come from movehdup (port 5) instead of a shift (port 0, where the four
-// multiplies already queue): vpmuludq reads only the low half of each lane; likewise the low word is assembled by moveldup + blend
-SIPP_AVX512 inline __m512i v_hi(__m512i x) { return _mm512_castps_si512(_mm512_movehdup_ps(_mm512_castsi512_ps(x))); }
-SIPP_AVX512 inline __m512i v_join(__m512i ll, __m512i t1) {  // (ll & 0xffffffff) | (t1 << 32)
-    return _mm512_mask_blend_epi32(0xAAAA, ll, _mm512_castps_si512(_mm512_moveldup_ps(_mm512_castsi512_ps(t1))));
-}
 SIPP_AVX512 inline __m512i v_mul(__m512i x, __m512i y) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    __m512i xh = v_hi(x), yh = v_hi(y);
+    __m512i xh = _mm512_srli_epi64(x, 32), yh = _mm512_srli_epi64(y, 32);
     __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
     __m512i t0 = _mm512_add_epi64(hl, _mm512_srli_epi64(ll, 32));
     __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
     __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
-    __m512i lo = v_join(ll, t1);
+    __m512i lo = _mm512_or_si512(_mm512_and_si512(ll, lo32), _mm512_slli_epi64(t1, 32));
     return v_reduce(lo, hi);
 }
 SIPP_AVX512 inline __m512i v_sqr(__m512i x) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    __m512i xh = v_hi(x);
+    __m512i xh = _mm512_srli_epi64(x, 32);
     __m512i ll = _mm512_mul_epu32(x, x), lh = _mm512_mul_epu32(x, xh), hh = _mm512_mul_epu32(xh, xh);
     __m512i t0 = _mm512_add_epi64(lh, _mm512_srli_epi64(ll, 32));
     __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
     __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
-    __m512i lo = v_join(ll, t1);
+    __m512i lo = _mm512_or_si512(_mm512_and_si512(ll, lo32), _mm512_slli_epi64(t1, 32));
     return v_reduce(lo, hi);
 }
 SIPP_AVX512 inline __m512i v_pow7(__m512i x) {
@@ -199,29 +189,56 @@ SIPP_AVX512 inline __m512i v_canon(__m512i a) {
 // The twelve rotations of the state are built in registers: with E0 = s[0..7], E1 = s[8..11, 0..3], E2 = s[4..11] the window
 // s[i..i+7] is one valignq of two neighbours.  Rows 8..11 only fill half a vector, so their low and high halves share one:
 // F_k = lo[4k..4k+3] | hi[4k..4k+3], and the window s[8+i..11+i] is a two-source permute of two neighbouring F's.
-// Column form: out = sum_j s[j] * column_j.  The state halves are stored once as doubles and every s[j] comes back as a
-// broadcast LOAD (load ports; forwarded from the 64-byte stores), multiplied by a constant column vector -- no valignq / permute
-// network on port 5.  Rows 0..7: two accumulator sets (low / high halves); rows 8..11: one register with the low sums in lanes
-// 0..3 and the high sums in lanes 4..7 (the broadcast of the high half is merged into the upper lanes by the load itself).
+template <int I>
+SIPP_AVX512 inline __m512d win8(__m512d e0, __m512d e1, __m512d e2) {
+    if (I == 0) return e0;
+    if (I == 8) return e1;
+    if (I < 8) return _mm512_castsi512_pd(_mm512_alignr_epi64(_mm512_castpd_si512(e1), _mm512_castpd_si512(e0), I & 7));
+    return _mm512_castsi512_pd(_mm512_alignr_epi64(_mm512_castpd_si512(e2), _mm512_castpd_si512(e1), I & 7));
+}
 SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables& T) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    alignas(64) double L[16], H[16];
-    _mm512_store_pd(L, _mm512_cvtepu64_pd(_mm512_and_si512(s0, lo32)));
-    _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
-    _mm512_store_pd(H, _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)));
-    _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
-    __m512d al[4], ah[4], ab[4];
-#pragma GCC unroll 12
-    for (int j = 0; j < 12; j++) {
-        const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
-        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
-        const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
-        if (j < 4) {
-            al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
-        } else {
-            al[j & 3] = _mm512_fmadd_pd(bl, ca, al[j & 3]); ah[j & 3] = _mm512_fmadd_pd(bh, ca, ah[j & 3]); ab[j & 3] = _mm512_fmadd_pd(bb, cb, ab[j & 3]);
-        }
+    const __m512d l0 = _mm512_cvtepu64_pd(_mm512_and_si512(s0, lo32)), l1 = _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32));
+    const __m512d h0 = _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)), h1 = _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32));
+    // rows 0..7
+    const __m512d le1 = _mm512_shuffle_f64x2(l1, l0, 0x44), le2 = _mm512_shuffle_f64x2(l0, l1, 0x4E);
+    const __m512d he1 = _mm512_shuffle_f64x2(h1, h0, 0x44), he2 = _mm512_shuffle_f64x2(h0, h1, 0x4E);
+    __m512d al0 = _mm512_mul_pd(l0, _mm512_load_pd(T.mds_c0a)), ah0 = _mm512_mul_pd(h0, _mm512_load_pd(T.mds_c0a));
+    __m512d al1, ah1, al2, ah2, al3, ah3;
+#define SIPP_MDS_A(I, ACCL, ACCH, FIRST)                                                              \
+    {                                                                                                 \
+        const __m512d c = _mm512_set1_pd(T.mds_circ[I]);                                              \
+        const __m512d wl = win8<I>(l0, le1, le2), wh = win8<I>(h0, he1, he2);                         \
+        ACCL = FIRST ? _mm512_mul_pd(wl, c) : _mm512_fmadd_pd(wl, c, ACCL);                           \
+        ACCH = FIRST ? _mm512_mul_pd(wh, c) : _mm512_fmadd_pd(wh, c, ACCH);                           \
     }
+    SIPP_MDS_A(1, al1, ah1, true)
+    SIPP_MDS_A(2, al2, ah2, true)
+    SIPP_MDS_A(3, al3, ah3, true)
+    SIPP_MDS_A(4, al0, ah0, false)
+    SIPP_MDS_A(5, al1, ah1, false)
+    SIPP_MDS_A(6, al2, ah2, false)
+    SIPP_MDS_A(7, al3, ah3, false)
+    SIPP_MDS_A(8, al0, ah0, false)
+    SIPP_MDS_A(9, al1, ah1, false)
+    SIPP_MDS_A(10, al2, ah2, false)
+    SIPP_MDS_A(11, al3, ah3, false)
+#undef SIPP_MDS_A
+    // rows 8..11: ring of half-vectors F2, F0, F1, F2, ... starting at s[8]
+    const __m512d f0 = _mm512_shuffle_f64x2(l0, h0, 0x44), f1 = _mm512_shuffle_f64x2(l0, h0, 0xEE), f2 = _mm512_shuffle_f64x2(l1, h1, 0x44);
+    const __m512i ix1 = _mm512_load_si512(T.mds_ix[0]), ix2 = _mm512_load_si512(T.mds_ix[1]), ix3 = _mm512_load_si512(T.mds_ix[2]);
+    __m512d b0 = _mm512_mul_pd(f2, _mm512_set1_pd(T.mds_circ[0]));
+    __m512d b1 = _mm512_mul_pd(_mm512_permutex2var_pd(f2, ix1, f0), _mm512_set1_pd(T.mds_circ[1]));
+    b0 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f2, ix2, f0), _mm512_set1_pd(T.mds_circ[2]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f2, ix3, f0), _mm512_set1_pd(T.mds_circ[3]), b1);
+    b0 = _mm512_fmadd_pd(f0, _mm512_set1_pd(T.mds_circ[4]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f0, ix1, f1), _mm512_set1_pd(T.mds_circ[5]), b1);
+    b0 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f0, ix2, f1), _mm512_set1_pd(T.mds_circ[6]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f0, ix3, f1), _mm512_set1_pd(T.mds_circ[7]), b1);
+    b0 = _mm512_fmadd_pd(f1, _mm512_set1_pd(T.mds_circ[8]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f1, ix1, f2), _mm512_set1_pd(T.mds_circ[9]), b1);
+    b0 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f1, ix2, f2), _mm512_set1_pd(T.mds_circ[10]), b0);
+    b1 = _mm512_fmadd_pd(_mm512_permutex2var_pd(f1, ix3, f2), _mm512_set1_pd(T.mds_circ[11]), b1);
     const __m512i eps = lo32;
     auto combine = [&](__m512i alo, __m512i ahi) SIPP_AVX512 {  // < 2^43 each; value = alo + 2^32 ahi
         __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
@@ -233,16 +250,27 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
         __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
         return _mm512_mask_add_epi64(r, c2, r, eps);
     };
-    s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al[0], al[1]), _mm512_add_pd(al[2], al[3]))),
-                 _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah[0], ah[1]), _mm512_add_pd(ah[2], ah[3]))));
-    const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ab[0], ab[1]), _mm512_add_pd(ab[2], ab[3])));
+    s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al0, al1), _mm512_add_pd(al2, al3))),
+                 _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah0, ah1), _mm512_add_pd(ah2, ah3))));
+    const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(b0, b1));  // lanes 0..3: low sums, lanes 4..7: high sums of rows 8..11
     s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));              // lanes 4..7 of s1 are don't-care
 }
 
-SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonFastTables& T) {
+// lanes 8..11 arrive as four scalars: their S-boxes run on the scalar ports (mulx) next to the vector S-box of lanes 0..7 -- the
+// second state register is half empty, its x^7 cost a full register's worth of vector-port slots -- and rejoin for the MDS layer
+SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t a[4], const uint64_t* rc16, const PoseidonFastTables& T) {
+    const uint64_t t0 = s_pow7(s_add(a[0], rc16[8])), t1 = s_pow7(s_add(a[1], rc16[9]));
+    const uint64_t t2 = s_pow7(s_add(a[2], rc16[10])), t3 = s_pow7(s_add(a[3], rc16[11]));
     s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
-    s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
+    s1 = _mm512_zextsi256_si512(_mm256_set_epi64x((long long)t3, (long long)t2, (long long)t1, (long long)t0));
     v_mds(s0, s1, T);
+}
+
+// lab harness entry: the old signature
+SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonFastTables& T) {
+    alignas(32) uint64_t a[4];
+    _mm256_store_si256((__m256i*)a, _mm512_castsi512_si256(s1));
+    v_full_round(s0, s1, a, rc16, T);
 }
 
 }  // namespace
@@ -252,7 +280,11 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
     memcpy(buf, s, 96);
     buf[12] = buf[13] = buf[14] = buf[15] = 0;
     __m512i s0 = _mm512_load_si512(buf), s1 = _mm512_load_si512(buf + 8);
-    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[k], T);
+    alignas(32) uint64_t hi4[4] = {buf[8], buf[9], buf[10], buf[11]};
+    for (int k = 0; k < 4; k++) {
+        v_full_round(s0, s1, hi4, T.rc_full[k], T);
+        if (k < 3) _mm256_store_si256((__m256i*)hi4, _mm512_castsi512_si256(s1));
+    }
 
     // ---- 22 partial rounds, sparse form ----
     s0 = v_add_canon(s0, _mm512_load_si512(T.first));
@@ -293,8 +325,11 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
     _mm512_store_si512(ub + 8, v1);
     ub[0] = u0;
     s0 = _mm512_load_si512(ub);
-    s1 = _mm512_load_si512(ub + 8);
-    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[4 + k], T);
+    hi4[0] = ub[8]; hi4[1] = ub[9]; hi4[2] = ub[10]; hi4[3] = ub[11];
+    for (int k = 0; k < 4; k++) {
+        v_full_round(s0, s1, hi4, T.rc_full[4 + k], T);
+        if (k < 3) _mm256_store_si256((__m256i*)hi4, _mm512_castsi512_si256(s1));
+    }
     s0 = v_canon(s0);
     s1 = v_canon(s1);
     _mm512_store_si512(buf, s0);

@@ -5,26 +5,22 @@
 // the host; at the sizes the GPU finishes in milliseconds this chain IS the prove time, so one permutation has to be as
 // short as the machine allows.  This file computes exactly the same function as the portable code in transcript.cc
 // (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2):
-//   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products (high halves by
-//                  movehdup, the low word joined by moveldup + blend: port 5 instead of more shifts on port 0) and the
+//   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products and the
 //                  2^64 = 2^32 - 1, 2^96 = -1 reduction; the circulant MDS layer as 36 FP64 FMAs on the 32-bit halves
-//                  (sums < 2^43 are exact in double) in COLUMN form: the halves are stored once as doubles and every s[j]
-//                  comes back as a broadcast load times a constant column -- no permute network on port 5
+//                  (sums < 2^43 are exact in double), the rotations built in registers (valignq / two-source permutes:
+//                  a store-and-reload of the state cannot be forwarded and cost 60 ns of the 119 ns round)
 //   partial rounds sparse form (tables derived in transcript.cc): the lane-0 S-box and the 11-term dot product run on the
 //                  scalar ports (mulx / adc, 192-bit lazy accumulation in two carry chains) while the rank-1 update of
 //                  lanes 1..11 runs on the vector ports.  The 11-term sum of round r reads the state of round r - 1 (one
 //                  extra product restores the missing rank-1 term) and the constant of the S-box output is folded in, so
 //                  the dependent chain of a round is the S-box, one multiply-add and one reduction.
-// Measured on the GPU box's Xeon (3.79 GHz, tools/probe/run_poseidon_lab.sh): 1.506 -> 1.385 (dot order) -> 1.223 (register MDS)
-// -> 1.18 -> 1.153 (reduction on the carry flag) -> 1.116 (192-bit accumulators pinned in registers by asm blocks) -> 1.065 (the
-// scalar 128 -> 64-bit reduction as one 11-instruction asm block: latency 12.2 -> 10.3 cycles) -> 1.027 us per permutation
-// (column-form MDS, port-balanced vector product).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
-// 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
+// Measured on the GPU box's Xeon: 1.506 -> 1.385 (dot order) -> 1.223 (register MDS) -> 1.18 -> 1.153 us per permutation
+// (scalar reduction on the carry flag of its own addition instead of a compare).
 #include <immintrin.h>
 #include <stdint.h>
 #include <string.h>
 
-#include "poseidon_fast.h"
+#include "../../../sipp_b200/csrc/poseidon_fast.h"
 
 #if defined(__x86_64__)
 #define SIPP_AVX512 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
@@ -153,30 +149,24 @@ SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
     __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
     return _mm512_mask_add_epi64(r, c, r, eps);
 }
-// the high 32-bit halves as multiplier operands come from movehdup (port 5) instead of a shift (port 0, where the four
-// multiplies already queue): vpmuludq reads only the low half of each lane; likewise the low word is assembled by moveldup + blend
-SIPP_AVX512 inline __m512i v_hi(__m512i x) { return _mm512_castps_si512(_mm512_movehdup_ps(_mm512_castsi512_ps(x))); }
-SIPP_AVX512 inline __m512i v_join(__m512i ll, __m512i t1) {  // (ll & 0xffffffff) | (t1 << 32)
-    return _mm512_mask_blend_epi32(0xAAAA, ll, _mm512_castps_si512(_mm512_moveldup_ps(_mm512_castsi512_ps(t1))));
-}
 SIPP_AVX512 inline __m512i v_mul(__m512i x, __m512i y) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    __m512i xh = v_hi(x), yh = v_hi(y);
+    __m512i xh = _mm512_srli_epi64(x, 32), yh = _mm512_srli_epi64(y, 32);
     __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
     __m512i t0 = _mm512_add_epi64(hl, _mm512_srli_epi64(ll, 32));
     __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
     __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
-    __m512i lo = v_join(ll, t1);
+    __m512i lo = _mm512_or_si512(_mm512_and_si512(ll, lo32), _mm512_slli_epi64(t1, 32));
     return v_reduce(lo, hi);
 }
 SIPP_AVX512 inline __m512i v_sqr(__m512i x) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    __m512i xh = v_hi(x);
+    __m512i xh = _mm512_srli_epi64(x, 32);
     __m512i ll = _mm512_mul_epu32(x, x), lh = _mm512_mul_epu32(x, xh), hh = _mm512_mul_epu32(xh, xh);
     __m512i t0 = _mm512_add_epi64(lh, _mm512_srli_epi64(ll, 32));
     __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
     __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
-    __m512i lo = v_join(ll, t1);
+    __m512i lo = _mm512_or_si512(_mm512_and_si512(ll, lo32), _mm512_slli_epi64(t1, 32));
     return v_reduce(lo, hi);
 }
 SIPP_AVX512 inline __m512i v_pow7(__m512i x) {
@@ -203,7 +193,24 @@ SIPP_AVX512 inline __m512i v_canon(__m512i a) {
 // broadcast LOAD (load ports; forwarded from the 64-byte stores), multiplied by a constant column vector -- no valignq / permute
 // network on port 5.  Rows 0..7: two accumulator sets (low / high halves); rows 8..11: one register with the low sums in lanes
 // 0..3 and the high sums in lanes 4..7 (the broadcast of the high half is merged into the upper lanes by the load itself).
+struct MdsCols {
+    alignas(64) double a[12][8];  // a[j][r] = coefficient of s[j] in row r, r = 0..7
+    alignas(64) double b[12][8];  // b[j][r] = coefficient of s[j] in row 8 + (r & 3)
+};
+inline const MdsCols& mds_cols(const PoseidonFastTables& T) {
+    static const MdsCols C = [&]() {
+        MdsCols c;
+        for (int j = 0; j < 12; j++)
+            for (int r = 0; r < 8; r++) {
+                c.a[j][r] = T.mds_circ[(j - r + 12) % 12] + ((j == 0 && r == 0) ? 8.0 : 0.0);
+                c.b[j][r] = T.mds_circ[(j - 8 - (r & 3) + 24) % 12];
+            }
+        return c;
+    }();
+    return C;
+}
 SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables& T) {
+    const MdsCols& C = mds_cols(T);
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
     alignas(64) double L[16], H[16];
     _mm512_store_pd(L, _mm512_cvtepu64_pd(_mm512_and_si512(s0, lo32)));
@@ -215,7 +222,7 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     for (int j = 0; j < 12; j++) {
         const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
         const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
-        const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
+        const __m512d ca = _mm512_load_pd(C.a[j]), cb = _mm512_load_pd(C.b[j]);
         if (j < 4) {
             al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
         } else {
