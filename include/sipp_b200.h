@@ -78,6 +78,11 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          (E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(1/x), k_mat.cu) instead of the points:
                                          same Z_L, Z_R bit for bit, one short kernel per round.  The context's points are then left
                                          as they were when the tail began (only its length keeps halving) */
+#define SIPP_OPT_MATRIX_BLOCK_N 15    /* look-ahead stages of the same kind BEFORE the tail: when at most this many points are left (default
+                                         256; 0 = off) they are cut into SIPP_OPT_MATRIX_BLOCK_R blocks, E[i][j] = <A_block_i, B_block_j> is
+                                         computed for all block pairs in one launch set, and log2(R) rounds take Z_L, Z_R from that matrix
+                                         while the points are folded on a side stream, off the critical path */
+#define SIPP_OPT_MATRIX_BLOCK_R 16    /* blocks per look-ahead stage: 4, 8 (default), 16 or 32 (capped so that the stage ends where the tail begins) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);
 

@@ -23,7 +23,7 @@ namespace sipp_host {
 extern int g_device;             // CUDA device of this process, -1 before sipp_init
 extern int g_sm_count;
 extern cudaStream_t g_stream;    // the library's non-blocking stream
-extern int g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate;
+extern int g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate, g_opt_matrix_n, g_opt_matrix_block_n, g_opt_matrix_block_r;
 extern sipp_stats g_stats;
 
 int fail(int code, const char* what);             // records the message for sipp_last_error, returns `code`
@@ -79,6 +79,29 @@ struct AbsorbJob {
         if (th.joinable()) th.join();
     }
 };
+
+// Pairing-matrix tail of a single proof (k_mat.cu; SIPP_OPT_MATRIX_TAIL): E[i][j] = e(A_i, B_j) over the points left in a context,
+// then Z_L / Z_R as products of matrix entries and the fold as GT exponentiations of the matrix.  Used by the single-GPU prover and
+// by rank 0's tail of the sharded one.
+struct MatTail {
+    uint32_t* E[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t n = 0;   // virtual points (blocks) the matrix stands for; 0 = no stage in progress
+    size_t m = 1;   // points per block (1: the tail of the proof)
+    int folds = 0;  // point folds issued on the side stream in this stage
+    void reset() {
+        pool_free(E[0]);
+        pool_free(E[1]);
+        E[0] = E[1] = nullptr;
+        n = 0;
+        m = 1;
+    }
+    ~MatTail() { reset(); }
+};
+size_t mat_stage(size_t n);  // number of blocks of the stage that starts with n points left (0: a plain round)
+int mat_build(sipp_ctx* c, MatTail& mt, size_t nr);
+int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr);
+int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]);
 
 // CUDA-event span around a kernel class (SIPP_OPT_PROFILE): kind 0 miller, 1 reduce / final exponentiation, 2 fold, 3 other
 int span_begin(int kind, cudaStream_t s);

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(SIPP_RFE_THREADS) k_reduce_fe_eng(const uint32
         n = half;
     }
     if (warp != 0) return;
-    if (final_exp != 1) {  // 0: the raw product (a partial for another reduction); 2: the product of values that are already
+    if (final_exp != 1 && final_exp != 3) {  // 0: the raw product (a partial for another reduction); 2: the product of values that are already
                            // exponentiated (pairing-matrix tail), encoded like a final-exponentiation result
         if (active_lane && group == 0) {
             if (final_exp == 2) fq2_encode(out + prod * 96 + ((k & 1) * 3 + (k >> 1)) * 16, f);
@@ -62,6 +62,10 @@ __global__ void __launch_bounds__(SIPP_RFE_THREADS) k_reduce_fe_eng(const uint32
     mc.slots = mslots;
     mc.lane = lane;
     const int res = f12_final_exp(mc, ark_norm != 0);
+    if (final_exp == 3) {  // an entry of the pairing matrix (k_mat.cu): stays on the device, register-shaped
+        for (int w = lane; w < 96; w += 32) out[prod * 96 + w] = mslots[f12_reg_base(res) * 8 + w];
+        return;
+    }
     if (lane < 6) {
         const Fq2 g = Fq2{lp_load(mslots, f12_reg_base(res) + 2 * lane), lp_load(mslots, f12_reg_base(res) + 2 * lane + 1)};
         const int slot = (lane & 1) * 3 + (lane >> 1);

@@ -16,19 +16,20 @@
 
 namespace sipp {
 
-// pair q = i * n + j of the expanded launch is (A_i, B_j)
-__global__ void k_mat_gather(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, size_t n, uint32_t* __restrict__ Aexp, uint32_t* __restrict__ Bexp) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 (4 words) per thread: 4 + 8 per pair
-    const size_t q = t / 12;
-    const int w = (int)(t % 12);
-    if (q >= n * n) return;
-    const size_t i = q / n, j = q % n;
-    if (w < 4) reinterpret_cast<uint4*>(Aexp + 16 * q)[w] = __ldg(reinterpret_cast<const uint4*>(A + 16 * i) + w);
-    else reinterpret_cast<uint4*>(Bexp + 32 * q)[w - 4] = __ldg(reinterpret_cast<const uint4*>(B + 32 * j) + (w - 4));
+// pair q = (i * nr + j) * m + t of the expanded launch is (A[i m + t], B[j m + t]): entry (i, j) of the matrix owns m consecutive pairs
+__global__ void k_mat_gather(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, size_t nr, size_t m, uint32_t* __restrict__ Aexp,
+                             uint32_t* __restrict__ Bexp) {
+    const size_t th = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 (4 words) per thread: 4 + 8 per pair
+    const size_t q = th / 12;
+    const int w = (int)(th % 12);
+    if (q >= nr * nr * m) return;
+    const size_t e = q / m, t = q % m, i = e / nr, j = e % nr;
+    if (w < 4) reinterpret_cast<uint4*>(Aexp + 16 * q)[w] = __ldg(reinterpret_cast<const uint4*>(A + 16 * (i * m + t)) + w);
+    else reinterpret_cast<uint4*>(Bexp + 32 * q)[w - 4] = __ldg(reinterpret_cast<const uint4*>(B + 32 * (j * m + t)) + (w - 4));
 }
-int launch_mat_gather(const uint32_t* A, const uint32_t* B, size_t n, uint32_t* Aexp, uint32_t* Bexp, cudaStream_t s) {
-    const size_t threads = n * n * 12;
-    k_mat_gather<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(A, B, n, Aexp, Bexp);
+int launch_mat_gather(const uint32_t* A, const uint32_t* B, size_t nr, size_t m, uint32_t* Aexp, uint32_t* Bexp, cudaStream_t s) {
+    const size_t threads = nr * nr * m * 12;
+    k_mat_gather<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(A, B, nr, m, Aexp, Bexp);
     return (int)cudaGetLastError();
 }
 

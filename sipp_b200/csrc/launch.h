@@ -58,7 +58,7 @@ int launch_test_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* 
 size_t lines_bytes_per_pair();
 
 // pairing-matrix tail (k_mat.cu): E[i][j] = e(A_i, B_j) for the n points left, then folds of the MATRIX instead of the points
-int launch_mat_gather(const uint32_t* A, const uint32_t* B, size_t n, uint32_t* Aexp, uint32_t* Bexp, cudaStream_t s);
+int launch_mat_gather(const uint32_t* A, const uint32_t* B, size_t nr, size_t m, uint32_t* Aexp, uint32_t* Bexp, cudaStream_t s);
 int launch_mat_fe(const uint32_t* miller, size_t count, uint32_t* E, int ark_norm, cudaStream_t s);
 int launch_mat_diag(const uint32_t* E, size_t n, uint32_t* partials, cudaStream_t s);
 int launch_mat_fold(const uint32_t* E, size_t n, uint32_t* Eout, const GtPlan& plan, cudaStream_t s);

@@ -33,6 +33,7 @@ int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own st
 int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
 int g_opt_matrix_n = 32;       // pairing-matrix tail (k_mat.cu) once at most this many points are left; 0 = off
+int g_opt_matrix_block_n = 256, g_opt_matrix_block_r = 8;  // look-ahead stages: from at most this many points, that many blocks
 int g_opt_validate = 1;        // every prove / verify entry point checks its points: on the curve, B_i in the order-r subgroup
 
 struct TimedSpan {
@@ -310,45 +311,59 @@ int ctx_products(sipp_ctx* c, int which, uint8_t* out0, uint8_t* out1) {
     return SIPP_OK;
 }
 
-// ---- pairing-matrix tail (k_mat.cu): once n <= SIPP_OPT_MATRIX_TAIL points are left, E[i][j] = e(A_i, B_j) is computed for all
-// n^2 pairs and the remaining rounds fold the MATRIX in GT instead of the points -- one short kernel per round instead of
-// fold + lines + accumulation + final exponentiation (prover_native.rs:45-75; same Z_L, Z_R bit for bit)
-struct MatTail {
-    uint32_t* E[2] = {nullptr, nullptr};
-    int cur = 0;
-    size_t n = 0;  // points the matrix stands for; 0 = not built
-    ~MatTail() {
-        pool_free(E[0]);
-        pool_free(E[1]);
-    }
-};
-bool mat_tail_wanted(size_t n) { return g_opt_pipeline && g_opt_fe_engine && n >= 2 && n <= (size_t)g_opt_matrix_n; }
+}  // namespace
 
-int mat_build(sipp_ctx* c, MatTail& mt) {
-    const size_t n = c->n, m = n * n;
+namespace sipp_host {
+// ---- pairing-matrix stages (k_mat.cu).  The rounds of prover_native.rs:45-75 are a serial chain fold -> Miller loops -> final
+// exponentiation -> hash; bilinearity cuts it.  Split the n points left into nr blocks of m = n / nr ("virtual points") and let
+//     E[i][j] = <A_block_i, B_block_j> = prod_{t<m} e(A[i m + t], B[j m + t])        (all nr^2 block products, ONE launch set).
+// Then Z_L = prod_{i<nr/2} E[i + nr/2][i], Z_R = prod E[i][i + nr/2] (:48-49), and the fold of the points (:60-69) carries over to
+// the matrix: E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(1/x) -- one short kernel (k_mat_fold) -- for log2(nr) rounds.
+//   m == 1 (n <= SIPP_OPT_MATRIX_TAIL): the tail of the proof; the points are never folded again.
+//   m > 1  (n <= SIPP_OPT_MATRIX_BLOCK_N): a look-ahead stage of log2(nr) rounds; the points are folded with every challenge on a
+//          side stream, off the critical path, and the next stage starts from them.
+// Every Z_L, Z_R is the same field element as on the point-fold route, bit for bit.
+cudaStream_t g_fold_stream = nullptr;
+
+size_t mat_stage(size_t n) {
+    if (!g_opt_pipeline || !g_opt_fe_engine || n < 2) return 0;
+    if (n <= (size_t)g_opt_matrix_n) return n;
+    if (g_opt_matrix_n < 2 || n > (size_t)g_opt_matrix_block_n) return 0;
+    size_t nr = n / (size_t)g_opt_matrix_n;  // the stage ends where the tail begins
+    if (nr > (size_t)g_opt_matrix_block_r) nr = (size_t)g_opt_matrix_block_r;
+    return nr >= 4 ? nr : 0;
+}
+
+int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
+    const size_t n = c->n, m = n / nr, P = nr * nr, pairs = P * m;
     uint32_t *aexp = nullptr, *bexp = nullptr, *mil = nullptr;
-    int rc = scratch_reserve(n);
-    if (!rc) rc = lines_reserve(m * lines_bytes_per_pair());
+    const size_t blocks = (size_t)accum_eng_blocks(m, 1);
+    int rc = scratch_reserve(m == 1 ? nr : (blocks * P + 1) / 2);
+    if (!rc) rc = lines_reserve(pairs * lines_bytes_per_pair());
     if (rc) return rc;
-    cudaError_t e = pool_alloc((void**)&mt.E[0], m * 384);
-    if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (m / 4) * 384);
-    if (e == cudaSuccess) e = pool_alloc((void**)&aexp, m * 64);
-    if (e == cudaSuccess) e = pool_alloc((void**)&bexp, m * 128);
-    if (e == cudaSuccess) e = pool_alloc((void**)&mil, m * 384);
+    cudaError_t e = pool_alloc((void**)&mt.E[0], P * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (P / 4) * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&aexp, pairs * 64);
+    if (e == cudaSuccess) e = pool_alloc((void**)&bexp, pairs * 128);
+    if (e == cudaSuccess && m == 1) e = pool_alloc((void**)&mil, P * 384);
     int le = 0;
     if (e == cudaSuccess) {
         {
             Span sp(0, g_stream);
             MillerJob job;
             job.a_off[0] = job.b_off[0] = job.a_off[1] = job.b_off[1] = 0;
-            job.m = m;
-            le = launch_mat_gather(c->dA, c->dB, n, aexp, bexp, g_stream);
-            if (!le) le = launch_lines_wide(aexp, bexp, job, 1, 0, m, g_scr.lines, g_stream);
-            if (!le) le = launch_accum_eng_each(g_scr.lines, m, mil, g_stream);
+            job.m = pairs;
+            le = launch_mat_gather(c->dA, c->dB, nr, m, aexp, bexp, g_stream);
+            if (!le)
+                le = pairs <= (size_t)g_opt_wide_max ? launch_lines_wide(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream)
+                                                     : launch_lines(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream);
+            // the expanded launch is laid out [entry][pair of the block]: entry = one "product" of m pairs for the accumulation
+            if (!le) le = m == 1 ? launch_accum_eng_each(g_scr.lines, P, mil, g_stream) : launch_accum_eng(g_scr.lines, m, (int)P, 1, g_scr.partials, 0, g_stream);
         }
         if (!le) {
             Span sp(1, g_stream);
-            le = launch_mat_fe(mil, m, mt.E[0], g_opt_fe_norm, g_stream);
+            le = m == 1 ? launch_mat_fe(mil, P, mt.E[0], g_opt_fe_norm, g_stream)
+                        : launch_reduce_fe_eng(g_scr.partials, (int)blocks, (int)P, mt.E[0], 3, g_opt_fe_norm, g_stream);
         }
         g_stats.launches += 4;
         g_stats.miller_launches++;
@@ -357,10 +372,12 @@ int mat_build(sipp_ctx* c, MatTail& mt) {
     pool_free(aexp);
     pool_free(bexp);
     pool_free(mil);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(matrix tail)");
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pairing matrix)");
     if (le) return cuda_fail((cudaError_t)le, "pairing matrix");
-    mt.n = n;
+    mt.n = nr;
+    mt.m = m;
     mt.cur = 0;
+    mt.folds = 0;
     return SIPP_OK;
 }
 
@@ -374,7 +391,7 @@ int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr) {
         if (le) return cuda_fail((cudaError_t)le, "matrix products");
     }
     g_stats.launches += 2;
-    g_stats.miller_pairs += 2 * h;  // the pairs these two products stand for
+    g_stats.miller_pairs += 2 * h * mt.m;  // the pairs these two products stand for
     CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, 2 * 384, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     memcpy(zl, g_scr.h_out, 384);
@@ -382,9 +399,10 @@ int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr) {
     return SIPP_OK;
 }
 
-// E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(x^-1)   (prover_native.rs:60-69 in GT)
-int mat_fold(MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]) {
-    if (mt.n > 2) {  // the 1 x 1 matrix after the last round is never read
+// E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(x^-1)   (prover_native.rs:60-69 in GT); c->n halves.  A look-ahead stage
+// (m > 1) also folds the points themselves, on the side stream; when the matrix is used up the library stream waits for them.
+int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]) {
+    if (mt.n > 2) {  // the 1 x 1 matrix after the last round of a stage is never read
         GtPlan plan;
         if (gt_plan_build(x, xinv, &plan)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
         Span sp(2, g_stream);
@@ -393,14 +411,27 @@ int mat_fold(MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]) {
         g_stats.launches++;
         mt.cur ^= 1;
     }
-    g_stats.fold_points += mt.n / 2;
+    const size_t h = c->n / 2;
+    if (mt.m > 1) {
+        FoldPlan fp;
+        if (fold_plan_build(x, xinv, &fp)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
+        if (!g_fold_stream) CK(cudaStreamCreateWithFlags(&g_fold_stream, cudaStreamNonBlocking));
+        if (mt.folds++ == 0) CK(order_after(g_fold_stream, g_stream));  // the gather of mat_build has read the points
+        Span sp(2, g_fold_stream);
+        int le = h <= (size_t)g_opt_wide_fold_max ? launch_fold_wide(c->dA, c->dB, h, fp, g_fold_stream) : launch_fold(c->dA, c->dB, h, fp, g_fold_stream);
+        if (le) return cuda_fail((cudaError_t)le, "k_fold (look-ahead stage)");
+        g_stats.launches++;
+    }
+    g_stats.fold_points += h;
+    c->n = h;
     mt.n /= 2;
+    if (mt.n == 1) {  // stage over
+        if (mt.m > 1) CK(order_after(g_stream, g_fold_stream));
+        mt.reset();
+    }
     return SIPP_OK;
 }
 
-}  // namespace
-
-namespace sipp_host {
 int ctx_alloc(size_t n, sipp_ctx** out) {
     sipp_ctx* c = new sipp_ctx();
     c->n = c->cap = n;
@@ -458,6 +489,8 @@ int sipp_shutdown(void) {
     pool_release_all();
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
+    if (g_fold_stream) cudaStreamDestroy(g_fold_stream);
+    g_fold_stream = nullptr;
     g_device = -1;
     return SIPP_OK;
 }
@@ -477,7 +510,15 @@ int sipp_set_option(int option, int value) {
         case SIPP_OPT_BATCH_STREAMS: g_opt_batch_streams = value < 0 ? 0 : value; return SIPP_OK;
         case SIPP_OPT_BATCH_QLINES: g_opt_batch_qlines = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_VALIDATE_POINTS: g_opt_validate = value ? 1 : 0; return SIPP_OK;
-        case SIPP_OPT_MATRIX_TAIL: g_opt_matrix_n = value < 0 ? 0 : (value > 64 ? 64 : value); return SIPP_OK;
+        case SIPP_OPT_MATRIX_TAIL:
+            if (value < 0 || value > 64 || (value & (value - 1))) return fail(SIPP_ERR_ARG, "SIPP_OPT_MATRIX_TAIL: 0 or a power of two <= 64");
+            g_opt_matrix_n = value;
+            return SIPP_OK;
+        case SIPP_OPT_MATRIX_BLOCK_N: g_opt_matrix_block_n = value < 0 ? 0 : (value > 4096 ? 4096 : value); return SIPP_OK;
+        case SIPP_OPT_MATRIX_BLOCK_R:
+            if (value < 4 || value > 32 || (value & (value - 1))) return fail(SIPP_ERR_ARG, "SIPP_OPT_MATRIX_BLOCK_R: 4, 8, 16 or 32");
+            g_opt_matrix_block_r = value;
+            return SIPP_OK;
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
@@ -497,6 +538,8 @@ int sipp_get_option(int option) {
         case SIPP_OPT_BATCH_QLINES: return g_opt_batch_qlines;
         case SIPP_OPT_VALIDATE_POINTS: return g_opt_validate;
         case SIPP_OPT_MATRIX_TAIL: return g_opt_matrix_n;
+        case SIPP_OPT_MATRIX_BLOCK_N: return g_opt_matrix_block_n;
+        case SIPP_OPT_MATRIX_BLOCK_R: return g_opt_matrix_block_r;
         default: return -1;
     }
 }
@@ -750,8 +793,11 @@ static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
     while (rc == SIPP_OK && n > 1) {                                          // :45
         uint8_t* zl = &fwd[384 * k];
         uint8_t* zr = &fwd[384 * (k + 1)];
-        if (!mt.n && mat_tail_wanted(n)) rc = mat_build(c, mt);               // from here on the rounds run on the pairing matrix
-        if (rc) break;
+        if (!mt.n) {
+            const size_t nr = mat_stage(n);                                   // a pairing-matrix stage starts here?
+            if (nr) rc = mat_build(c, mt, nr);
+            if (rc) break;
+        }
         rc = mt.n ? mat_products(mt, zl, zr) : sipp_ctx_cross_products(c, zl, zr);  // :46-49
         if (rc) break;
         if (first) {
@@ -769,8 +815,7 @@ static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
         g_stats.transcript_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         if (rc) break;
         if (mt.n) {
-            rc = mat_fold(mt, x, xinv);                                       // :60-74 on the matrix; the points stay as they were
-            c->n = n / 2;
+            rc = mat_fold(c, mt, x, xinv);                                    // :60-74 on the matrix
         } else {
             rc = sipp_ctx_fold(c, x, xinv);                                   // :60-74
         }

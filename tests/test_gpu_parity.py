@@ -275,6 +275,14 @@ def test_matrix_tail_thresholds(sipp, oracle):
         for thr in (0, 2, 4, 8, 16, 32, 64):
             sipp.set_option(_lib.OPT_MATRIX_TAIL, thr)
             assert b"".join(sipp.sipp_prove_native(A, B)) == want, thr
+        # look-ahead stages: blocks of points as "virtual points" for log2(R) rounds, the points folded on a side stream
+        for thr, bn, br in ((32, 64, 4), (8, 64, 8), (4, 64, 4), (2, 64, 32), (16, 32, 8), (0, 64, 8), (4, 16, 4)):
+            sipp.set_option(_lib.OPT_MATRIX_TAIL, thr)
+            sipp.set_option(_lib.OPT_MATRIX_BLOCK_N, bn)
+            sipp.set_option(_lib.OPT_MATRIX_BLOCK_R, br)
+            assert b"".join(sipp.sipp_prove_native(A, B)) == want, (thr, bn, br)
+        sipp.set_option(_lib.OPT_MATRIX_BLOCK_N, 256)
+        sipp.set_option(_lib.OPT_MATRIX_BLOCK_R, 8)
         sipp.set_option(_lib.OPT_FE_NORMALISATION, 1)
         sipp.set_option(_lib.OPT_MATRIX_TAIL, 0)
         ref = b"".join(sipp.sipp_prove_native(A[:64 * 16], B[:128 * 16]))
@@ -283,6 +291,8 @@ def test_matrix_tail_thresholds(sipp, oracle):
     finally:
         sipp.set_option(_lib.OPT_FE_NORMALISATION, 0)
         sipp.set_option(_lib.OPT_MATRIX_TAIL, 32)
+        sipp.set_option(_lib.OPT_MATRIX_BLOCK_N, 256)
+        sipp.set_option(_lib.OPT_MATRIX_BLOCK_R, 8)
 
 
 def test_prove_n128_config0(sipp, oracle):

@@ -199,36 +199,29 @@ SIPP_AVX512 inline __m512i v_canon(__m512i a) {
 // broadcast LOAD (load ports; forwarded from the 64-byte stores), multiplied by a constant column vector -- no valignq / permute
 // network on port 5.  Rows 0..7: two accumulator sets (low / high halves); rows 8..11: one register with the low sums in lanes
 // 0..3 and the high sums in lanes 4..7 (the broadcast of the high half is merged into the upper lanes by the load itself).
-struct MdsCols {
-    alignas(64) double a[12][8];  // a[j][r] = coefficient of s[j] in row r, r = 0..7
-    alignas(64) double b[12][8];  // b[j][r] = coefficient of s[j] in row 8 + (r & 3)
-};
-inline const MdsCols& mds_cols(const PoseidonFastTables& T) {
-    static const MdsCols C = [&]() {
-        MdsCols c;
-        for (int j = 0; j < 12; j++)
-            for (int r = 0; r < 8; r++) {
-                c.a[j][r] = T.mds_circ[(j - r + 12) % 12] + ((j == 0 && r == 0) ? 8.0 : 0.0);
-                c.b[j][r] = T.mds_circ[(j - 8 - (r & 3) + 24) % 12];
-            }
-        return c;
-    }();
-    return C;
-}
-SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables& T) {
-    const MdsCols& C = mds_cols(T);
+// lanes 8..11 arrive as scalars t[0..3] (their S-boxes ran on the scalar ports) and enter the column sums through memory
+template <bool HYBRID>
+SIPP_AVX512 inline void v_mds_t(__m512i& s0, __m512i& s1, const uint64_t* t, const PoseidonFastTables& T) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
     alignas(64) double L[16], H[16];
     _mm512_store_pd(L, _mm512_cvtepu64_pd(_mm512_and_si512(s0, lo32)));
-    _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
     _mm512_store_pd(H, _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)));
-    _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
+    if (HYBRID) {
+#pragma GCC unroll 4
+        for (int k = 0; k < 4; k++) {
+            L[8 + k] = (double)(uint32_t)t[k];
+            H[8 + k] = (double)(uint32_t)(t[k] >> 32);
+        }
+    } else {
+        _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
+        _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
+    }
     __m512d al[4], ah[4], ab[4];
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
         const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
         const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
-        const __m512d ca = _mm512_load_pd(C.a[j]), cb = _mm512_load_pd(C.b[j]);
+        const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
         if (j < 4) {
             al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
         } else {
@@ -251,7 +244,15 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ab[0], ab[1]), _mm512_add_pd(ab[2], ab[3])));
     s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));              // lanes 4..7 of s1 are don't-care
 }
+SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables& T) { v_mds_t<false>(s0, s1, nullptr, T); }
 
+SIPP_AVX512 inline void v_full_round_h(__m512i& s0, __m512i& s1, const uint64_t a[4], const uint64_t* rc16, const PoseidonFastTables& T) {
+    uint64_t t[4];
+#pragma GCC unroll 4
+    for (int k = 0; k < 4; k++) t[k] = s_pow7(s_add(a[k], rc16[8 + k]));
+    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
+    v_mds_t<true>(s0, s1, t, T);
+}
 SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonFastTables& T) {
     s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
     s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
@@ -265,7 +266,11 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
     memcpy(buf, s, 96);
     buf[12] = buf[13] = buf[14] = buf[15] = 0;
     __m512i s0 = _mm512_load_si512(buf), s1 = _mm512_load_si512(buf + 8);
-    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[k], T);
+    alignas(32) uint64_t hi4[4] = {buf[8], buf[9], buf[10], buf[11]};
+    for (int k = 0; k < 4; k++) {
+        v_full_round_h(s0, s1, hi4, T.rc_full[k], T);
+        if (k < 3) _mm256_store_si256((__m256i*)hi4, _mm512_castsi512_si256(s1));
+    }
 
     // ---- 22 partial rounds, sparse form ----
     s0 = v_add_canon(s0, _mm512_load_si512(T.first));
@@ -306,8 +311,11 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
     _mm512_store_si512(ub + 8, v1);
     ub[0] = u0;
     s0 = _mm512_load_si512(ub);
-    s1 = _mm512_load_si512(ub + 8);
-    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[4 + k], T);
+    hi4[0] = ub[8]; hi4[1] = ub[9]; hi4[2] = ub[10]; hi4[3] = ub[11];
+    for (int k = 0; k < 4; k++) {
+        v_full_round_h(s0, s1, hi4, T.rc_full[4 + k], T);
+        if (k < 3) _mm256_store_si256((__m256i*)hi4, _mm512_castsi512_si256(s1));
+    }
     s0 = v_canon(s0);
     s1 = v_canon(s1);
     _mm512_store_si512(buf, s0);

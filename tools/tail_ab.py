@@ -7,8 +7,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 A, B = sipp_b200.seeded_inputs(2, n)
 ref = None
-for thr in (0, 8, 16, 32, 64, 0, 32):
+for thr, bn, br in ((0, 0, 8), (32, 0, 8), (32, 128, 4), (32, 256, 8), (32, 512, 16), (32, 1024, 32), (32, 1024, 8), (32, 2048, 8), (16, 256, 16), (32, 256, 8)):
     sipp_b200.set_option(_lib.OPT_MATRIX_TAIL, thr)
+    sipp_b200.set_option(_lib.OPT_MATRIX_BLOCK_N, bn)
+    sipp_b200.set_option(_lib.OPT_MATRIX_BLOCK_R, br)
     sipp_b200.sipp_prove_native(A, B)
     ts = []
     for _ in range(reps):
@@ -17,4 +19,4 @@ for thr in (0, 8, 16, 32, 64, 0, 32):
         ts.append((time.perf_counter() - t0) * 1e3)
     p = b"".join(proof)
     ref = ref or p
-    print("n=%d tail<=%-3d  min %.2f ms  median %.2f ms  same=%s" % (n, thr, min(ts), sorted(ts)[len(ts) // 2], p == ref), flush=True)
+    print("n=%d tail<=%-3d block<=%-4d R=%-2d  min %.2f ms  median %.2f ms  same=%s" % (n, thr, bn, br, min(ts), sorted(ts)[len(ts) // 2], p == ref), flush=True)
