@@ -1,0 +1,358 @@
+// poseidon_avx512.cc -- AVX-512 implementation of the plonky2 Poseidon permutation over Goldilocks (width 12).
+//
+// The Fiat-Shamir transcript of the SIPP native protocol (/root/reference/src/transcript_native.rs:25-30) is a strictly
+// sequential chain of 8n + 13 + 27 log2(n) permutations (prover_native.rs:36-39 absorbs every A_i, B_i) that must stay on
+// the host; at the sizes the GPU finishes in milliseconds this chain IS the prove time, so one permutation has to be as
+// short as the machine allows.  This file computes exactly the same function as the portable code in transcript.cc
+// (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2):
+//   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products (high halves by
+//                  movehdup, the low word joined by moveldup + blend: port 5 instead of more shifts on port 0) and the
+//                  2^64 = 2^32 - 1, 2^96 = -1 reduction; the circulant MDS layer as 36 FP64 FMAs on the 32-bit halves
+//                  (sums < 2^43 are exact in double) in COLUMN form: the halves are stored once as doubles and every s[j]
+//                  comes back as a broadcast load times a constant column -- no permute network on port 5
+//   partial rounds sparse form (tables derived in transcript.cc): the lane-0 S-box and the 11-term dot product run on the
+//                  scalar ports (mulx / adc, 192-bit lazy accumulation in two carry chains) while the rank-1 update of
+//                  lanes 1..11 runs on the vector ports.  The 11-term sum of round r reads the state of round r - 1 (one
+//                  extra product restores the missing rank-1 term) and the constant of the S-box output is folded in, so
+//                  the dependent chain of a round is the S-box, one multiply-add and one reduction.
+// Measured on the GPU box's Xeon (3.79 GHz, tools/probe/run_poseidon_lab.sh): 1.506 -> 1.385 (dot order) -> 1.223 (register MDS)
+// -> 1.18 -> 1.153 (reduction on the carry flag) -> 1.116 (192-bit accumulators pinned in registers by asm blocks) -> 1.065 (the
+// scalar 128 -> 64-bit reduction as one 11-instruction asm block: latency 12.2 -> 10.3 cycles) -> 1.027 us per permutation
+// (column-form MDS, port-balanced vector product).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
+// 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
+#include <immintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../../sipp_b200/csrc/poseidon_fast.h"
+
+#if defined(__x86_64__)
+#define SIPP_AVX512 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
+
+namespace sipp {
+namespace {
+
+typedef unsigned __int128 u128;
+const uint64_t EPS = 0xFFFFFFFFull;
+const uint64_t GL_P = 0xFFFFFFFF00000001ull;
+
+// ------------------------------------------------------------------------------------------------ scalar helpers
+// (lo + 2^64 hi) mod p, result < 2^64: 2^64 = 2^32 - 1 and 2^96 = -1 (mod p).  One asm block, everything in registers: with the
+// _subborrow_u64 / _addcarry_u64 intrinsics GCC spilled the intermediate through the stack (their result is a pointer argument)
+// and every reduction on the S-box chain paid a store-to-load forward.  The borrow of lo - (hi >> 32) has probability 2^-32:
+// a forward branch that is never taken; the carry of the final addition is a coin flip: branch-free (sbb mask).
+// (lo + 2^64 hi) mod p as ONE asm block of 10 instructions: 2^64 = 2^32 - 1, 2^96 = -1 (mod p).  The borrow of lo - (hi >> 32) has
+// probability 2^-32 per call: a forward branch to a cold fix-up (sub + jc fuse) instead of the four-instruction cmov sequence GCC
+// makes of it; the carry of the final addition is a coin flip: lea + cmovc on the flags of the addition itself.
+SIPP_AVX512 inline uint64_t s_red128(uint64_t lo, uint64_t hi) {
+    uint64_t t, m = hi;
+    const uint64_t eps = EPS;
+    asm("mov %[m], %[t]\n\t"
+        "shr $32, %[t]\n\t"            // hh
+        "mov %k[m], %k[m]\n\t"          // hl
+        "sub %[t], %[lo]\n\t"
+        "jc 2f\n"
+        "1:\n\t"
+        "mov %[m], %[t]\n\t"
+        "shl $32, %[t]\n\t"
+        "sub %[m], %[t]\n\t"            // hl (2^32 - 1)
+        "add %[t], %[lo]\n\t"
+        "lea (%[lo],%[eps]), %[t]\n\t"
+        "cmovc %[t], %[lo]\n\t"
+        ".subsection 1\n"
+        "2:\n\t"
+        "sub %[eps], %[lo]\n\t"
+        "jmp 1b\n\t"
+        ".previous"
+        : [lo] "+r"(lo), [m] "+r"(m), [t] "=&r"(t)
+        : [eps] "r"(eps)
+        : "cc");
+    return lo;
+}
+SIPP_AVX512 inline uint64_t s_mul(uint64_t a, uint64_t b) {
+    unsigned long long hi;
+    uint64_t lo = _mulx_u64(a, b, &hi);
+    return s_red128(lo, hi);
+}
+SIPP_AVX512 inline uint64_t s_add(uint64_t a, uint64_t b) {  // any a, b
+    uint64_t r = a + b;
+    uint64_t t = r + ((0 - (uint64_t)(r < a)) & EPS);
+    return t + ((0 - (uint64_t)(t < r)) & EPS);
+}
+SIPP_AVX512 inline uint64_t s_pow7(uint64_t x) {
+    uint64_t x2 = s_mul(x, x), x3 = s_mul(x2, x), x4 = s_mul(x2, x2);
+    return s_mul(x3, x4);
+}
+// (lo, hi, top) += a * b as ONE asm block: mulx + add / adc / adc with the three limbs pinned in registers.  Written with the
+// _addcarry_u64 intrinsics (which take the address of their result) GCC kept the accumulator in memory and every term went
+// through a store-to-load forward -- 109 cycles per partial round on the GPU box's Xeon for a 55-cycle dependent chain.
+SIPP_AVX512 inline void mac192(unsigned long long& lo, unsigned long long& hi, unsigned long long& top, uint64_t a, uint64_t b) {
+    unsigned long long pl, ph;
+    asm("mulx %3, %0, %1\n\t"
+        "add %0, %4\n\t"
+        "adc %1, %5\n\t"
+        "adc $0, %6"
+        : "=&r"(pl), "=&r"(ph), "+d"(a), "+rm"(b), "+r"(lo), "+r"(hi), "+r"(top)
+        :
+        : "cc");
+}
+// sum_{i<11} a[i] * b[i] + extra_a * extra_b, reduced once (three-limb lazy accumulation; 2^128 = -2^32 mod p)
+SIPP_AVX512 inline uint64_t s_dot11p(const uint64_t* a, const uint64_t* b, uint64_t ea, uint64_t eb) {
+    unsigned long long lo = 0, hi = 0, top = 0;
+#pragma GCC unroll 11
+    for (int i = 0; i < 11; i++) mac192(lo, hi, top, a[i], b[i]);
+    // the term that depends on the S-box output of this round enters last: it is the only one on the dependent chain
+    mac192(lo, hi, top, ea, eb);
+    uint64_t r = s_red128(lo, hi);
+    uint64_t t = (uint64_t)top << 32;  // top <= 12
+    uint64_t d = r - t;
+    if (__builtin_expect(r < t, 0)) d -= EPS;  // borrowed 2^64 = EPS
+    return d;
+}
+
+
+// 192-bit lazy sum of 11 products in two independent chains (even / odd terms)
+struct Acc192 { unsigned long long lo, hi, top; };
+SIPP_AVX512 inline Acc192 s_dot11_raw(const uint64_t* a, const uint64_t* b) {
+    unsigned long long lo0 = 0, hi0 = 0, top0 = 0, lo1 = 0, hi1 = 0, top1 = 0;
+#pragma GCC unroll 6
+    for (int i = 0; i < 11; i += 2) {
+        mac192(lo0, hi0, top0, a[i], b[i]);
+        if (i + 1 < 11) mac192(lo1, hi1, top1, a[i + 1], b[i + 1]);
+    }
+    asm("add %3, %0\n\tadc %4, %1\n\tadc %5, %2" : "+r"(lo0), "+r"(hi0), "+r"(top0) : "r"(lo1), "r"(hi1), "r"(top1) : "cc");
+    return Acc192{lo0, hi0, top0};
+}
+SIPP_AVX512 inline void acc_mul(Acc192& s, uint64_t a, uint64_t b) {
+    unsigned long long lo = s.lo, hi = s.hi, top = s.top;
+    mac192(lo, hi, top, a, b);
+    s.lo = lo; s.hi = hi; s.top = top;
+}
+SIPP_AVX512 inline void acc_add(Acc192& s, uint64_t v) {
+    unsigned long long lo = s.lo, hi = s.hi, top = s.top;
+    asm("add %3, %0\n\tadc $0, %1\n\tadc $0, %2" : "+r"(lo), "+r"(hi), "+r"(top) : "r"(v) : "cc");
+    s.lo = lo; s.hi = hi; s.top = top;
+}
+SIPP_AVX512 inline uint64_t acc_reduce(const Acc192& s) {
+    uint64_t r = s_red128(s.lo, s.hi);
+    uint64_t t = (uint64_t)s.top << 32;  // top <= 13; 2^128 = -2^32
+    uint64_t d = r - t;
+    if (__builtin_expect(r < t, 0)) d -= EPS;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------ vector helpers
+SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
+    const __m512i eps = _mm512_set1_epi64((long long)EPS);
+    __m512i hh = _mm512_srli_epi64(hi, 32);
+    __m512i t = _mm512_sub_epi64(lo, hh);
+    __mmask8 b = _mm512_cmplt_epu64_mask(lo, hh);
+    t = _mm512_mask_sub_epi64(t, b, t, eps);
+    __m512i m = _mm512_mul_epu32(hi, eps);  // (hi & 0xffffffff) * (2^32 - 1)
+    __m512i r = _mm512_add_epi64(t, m);
+    __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
+    return _mm512_mask_add_epi64(r, c, r, eps);
+}
+// the high 32-bit halves as multiplier operands come from movehdup (port 5) instead of a shift (port 0, where the four
+// multiplies already queue): vpmuludq reads only the low half of each lane; likewise the low word is assembled by moveldup + blend
+SIPP_AVX512 inline __m512i v_hi(__m512i x) { return _mm512_castps_si512(_mm512_movehdup_ps(_mm512_castsi512_ps(x))); }
+SIPP_AVX512 inline __m512i v_join(__m512i ll, __m512i t1) {  // (ll & 0xffffffff) | (t1 << 32)
+    return _mm512_mask_blend_epi32(0xAAAA, ll, _mm512_castps_si512(_mm512_moveldup_ps(_mm512_castsi512_ps(t1))));
+}
+SIPP_AVX512 inline __m512i v_mul(__m512i x, __m512i y) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
+    __m512i xh = v_hi(x), yh = v_hi(y);
+    __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
+    __m512i t0 = _mm512_add_epi64(hl, _mm512_srli_epi64(ll, 32));
+    __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
+    __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
+    __m512i lo = v_join(ll, t1);
+    return v_reduce(lo, hi);
+}
+SIPP_AVX512 inline __m512i v_sqr(__m512i x) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
+    __m512i xh = v_hi(x);
+    __m512i ll = _mm512_mul_epu32(x, x), lh = _mm512_mul_epu32(x, xh), hh = _mm512_mul_epu32(xh, xh);
+    __m512i t0 = _mm512_add_epi64(lh, _mm512_srli_epi64(ll, 32));
+    __m512i t1 = _mm512_add_epi64(lh, _mm512_and_si512(t0, lo32));
+    __m512i hi = _mm512_add_epi64(hh, _mm512_add_epi64(_mm512_srli_epi64(t0, 32), _mm512_srli_epi64(t1, 32)));
+    __m512i lo = v_join(ll, t1);
+    return v_reduce(lo, hi);
+}
+SIPP_AVX512 inline __m512i v_pow7(__m512i x) {
+    __m512i x2 = v_sqr(x), x4 = v_sqr(x2), x3 = v_mul(x2, x);
+    return v_mul(x3, x4);
+}
+// a + b with b canonical (< p): a single wrap correction suffices
+SIPP_AVX512 inline __m512i v_add_canon(__m512i a, __m512i b) {
+    const __m512i eps = _mm512_set1_epi64((long long)EPS);
+    __m512i r = _mm512_add_epi64(a, b);
+    __mmask8 c = _mm512_cmplt_epu64_mask(r, a);
+    return _mm512_mask_add_epi64(r, c, r, eps);
+}
+SIPP_AVX512 inline __m512i v_canon(__m512i a) {
+    const __m512i p = _mm512_set1_epi64((long long)GL_P);
+    return _mm512_min_epu64(a, _mm512_sub_epi64(a, p));
+}
+
+// out[r] = sum_i s[(i + r) mod 12] * CIRC[i] + 8 s[0] [r == 0] on the 32-bit halves, in FP64 (sums < 2^43 are exact).
+// The twelve rotations of the state are built in registers: with E0 = s[0..7], E1 = s[8..11, 0..3], E2 = s[4..11] the window
+// s[i..i+7] is one valignq of two neighbours.  Rows 8..11 only fill half a vector, so their low and high halves share one:
+// F_k = lo[4k..4k+3] | hi[4k..4k+3], and the window s[8+i..11+i] is a two-source permute of two neighbouring F's.
+// Column form: out = sum_j s[j] * column_j.  The state halves are stored once as doubles and every s[j] comes back as a
+// broadcast LOAD (load ports; forwarded from the 64-byte stores), multiplied by a constant column vector -- no valignq / permute
+// network on port 5.  Rows 0..7: two accumulator sets (low / high halves); rows 8..11: one register with the low sums in lanes
+// 0..3 and the high sums in lanes 4..7 (the broadcast of the high half is merged into the upper lanes by the load itself).
+SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables& T) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
+    alignas(64) double L[16], H[16];
+    _mm512_store_pd(L, _mm512_cvtepu64_pd(_mm512_and_si512(s0, lo32)));
+    _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
+    _mm512_store_pd(H, _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)));
+    _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
+    __m512d al[4], ah[4], ab[4];
+#pragma GCC unroll 12
+    for (int j = 0; j < 12; j++) {
+        const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
+        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
+        const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
+        if (j < 4) {
+            al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
+        } else {
+            al[j & 3] = _mm512_fmadd_pd(bl, ca, al[j & 3]); ah[j & 3] = _mm512_fmadd_pd(bh, ca, ah[j & 3]); ab[j & 3] = _mm512_fmadd_pd(bb, cb, ab[j & 3]);
+        }
+    }
+    const __m512i eps = lo32;
+    auto combine = [&](__m512i alo, __m512i ahi) SIPP_AVX512 {  // < 2^43 each; value = alo + 2^32 ahi
+        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
+        __mmask8 c = _mm512_cmplt_epu64_mask(lo, alo);
+        __m512i hi = _mm512_srli_epi64(ahi, 32);
+        hi = _mm512_mask_add_epi64(hi, c, hi, _mm512_set1_epi64(1));
+        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);  // hi * (2^32 - 1), hi < 2^12
+        __m512i r = _mm512_add_epi64(lo, m);
+        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
+        return _mm512_mask_add_epi64(r, c2, r, eps);
+    };
+    s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al[0], al[1]), _mm512_add_pd(al[2], al[3]))),
+                 _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah[0], ah[1]), _mm512_add_pd(ah[2], ah[3]))));
+    const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ab[0], ab[1]), _mm512_add_pd(ab[2], ab[3])));
+    s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));              // lanes 4..7 of s1 are don't-care
+}
+
+// Full round with the S-boxes of ALL twelve lanes on the scalar ports: a scalar product has 10 cycles of latency against 36 for the
+// vector one, and twelve independent x^7 chains keep the multiplier busy, so the layer is throughput- instead of latency-bound.
+// The results go to memory as the doubles of their 32-bit halves -- exactly what the column-form MDS layer reads back as
+// broadcast loads -- and the MDS output returns through one 64-byte + one 32-byte store.
+SIPP_AVX512 inline void s_full_round(uint64_t* st, const uint64_t* rc16, const PoseidonFastTables& T) {
+    alignas(64) double L[16], H[16];
+#pragma GCC unroll 12
+    for (int j = 0; j < 12; j++) {
+        const uint64_t t = s_pow7(s_add(st[j], rc16[j]));
+        L[j] = (double)(uint32_t)t;
+        H[j] = (double)(uint32_t)(t >> 32);
+    }
+    __m512d al[4], ah[4], ab[4];
+#pragma GCC unroll 12
+    for (int j = 0; j < 12; j++) {
+        const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
+        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
+        const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
+        if (j < 4) {
+            al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
+        } else {
+            al[j & 3] = _mm512_fmadd_pd(bl, ca, al[j & 3]); ah[j & 3] = _mm512_fmadd_pd(bh, ca, ah[j & 3]); ab[j & 3] = _mm512_fmadd_pd(bb, cb, ab[j & 3]);
+        }
+    }
+    const __m512i eps = _mm512_set1_epi64((long long)EPS);
+    auto combine = [&](__m512i alo, __m512i ahi) SIPP_AVX512 {  // < 2^43 each; value = alo + 2^32 ahi
+        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
+        __mmask8 c = _mm512_cmplt_epu64_mask(lo, alo);
+        __m512i hi = _mm512_srli_epi64(ahi, 32);
+        hi = _mm512_mask_add_epi64(hi, c, hi, _mm512_set1_epi64(1));
+        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);  // hi * (2^32 - 1), hi < 2^12
+        __m512i r = _mm512_add_epi64(lo, m);
+        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
+        return _mm512_mask_add_epi64(r, c2, r, eps);
+    };
+    const __m512i s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al[0], al[1]), _mm512_add_pd(al[2], al[3]))),
+                               _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah[0], ah[1]), _mm512_add_pd(ah[2], ah[3]))));
+    const __m512i bi = _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ab[0], ab[1]), _mm512_add_pd(ab[2], ab[3])));
+    const __m512i s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));
+    _mm512_store_si512(st, s0);
+    _mm256_store_si256((__m256i*)(st + 8), _mm512_castsi512_si256(s1));
+}
+SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonFastTables& T) {
+    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
+    s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
+    v_mds(s0, s1, T);
+}
+
+}  // namespace
+
+SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T) {
+    alignas(64) uint64_t buf[16];
+    memcpy(buf, s, 96);
+    buf[12] = buf[13] = buf[14] = buf[15] = 0;
+    for (int k = 0; k < 4; k++) s_full_round(buf, T.rc_full[k], T);
+    __m512i s0 = _mm512_load_si512(buf), s1 = _mm512_load_si512(buf + 8);
+
+    // ---- 22 partial rounds, sparse form ----
+    s0 = v_add_canon(s0, _mm512_load_si512(T.first));
+    s1 = v_add_canon(s1, _mm512_load_si512(T.first + 8));
+    _mm512_store_si512(buf, s0);
+    _mm512_store_si512(buf + 8, s1);
+    uint64_t u0 = buf[0];
+    alignas(64) uint64_t ub[16];  // ub[i] = lane i (1..11); ub[0] unused
+    {
+        uint64_t zero = 0;
+        for (int i = 0; i < 11; i++) ub[i + 1] = s_dot11p(T.init[i], buf + 1, zero, zero);
+        ub[0] = 0; ub[12] = ub[13] = ub[14] = ub[15] = 0;
+    }
+    // d_r = vhat_r . U_r + m00 x_r with U_r = U_{r-1} + x_{r-1} w_{r-1}, so d_r = vhat_r . U_{r-1} + x_{r-1} (vhat_r . w_{r-1}) + m00 x_r:
+    // the 11-term sum reads the state of ONE ROUND EARLIER (in memory long before it is needed), and the dependent chain of a
+    // round is the S-box plus two multiply-adds.  Two buffers alternate: round r reads U_{r-1}, writes U_{r+1}.
+    alignas(64) uint64_t um[2][16];
+    memcpy(um[0], ub, sizeof ub);
+    __m512i v0 = _mm512_load_si512(ub), v1 = _mm512_load_si512(ub + 8);
+    uint64_t x_prev = 0;
+    for (int r = 0; r < 22; r++) {
+        Acc192 acc = s_dot11_raw(T.vhat[r], um[r == 0 ? 0 : (r + 1) & 1] + 1);
+        acc_mul(acc, x_prev, T.kprev[r]);
+        acc_add(acc, T.mpost[r]);  // + m00 post[r] (constant), off the chain
+        const uint64_t p7 = s_pow7(u0);
+        uint64_t x = s_add(p7, T.post[r]);
+        acc_mul(acc, p7, T.m00);
+        uint64_t d = acc_reduce(acc);
+        __m512i xb = _mm512_set1_epi64((long long)x);
+        v0 = v_add_canon(v0, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r]))));
+        v1 = v_add_canon(v1, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r] + 8))));
+        _mm512_store_si512(um[(r + 1) & 1], v0);
+        _mm512_store_si512(um[(r + 1) & 1] + 8, v1);
+        x_prev = x;
+        u0 = d;
+    }
+    _mm512_store_si512(ub, v0);
+    _mm512_store_si512(ub + 8, v1);
+    ub[0] = u0;
+    for (int k = 0; k < 4; k++) s_full_round(ub, T.rc_full[4 + k], T);
+    s0 = _mm512_load_si512(ub);
+    s1 = _mm512_load_si512(ub + 8);
+    s0 = v_canon(s0);
+    s1 = v_canon(s1);
+    _mm512_store_si512(buf, s0);
+    _mm512_store_si512(buf + 8, s1);
+    memcpy(s, buf, 96);
+}
+
+bool poseidon_avx512_supported() {
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vl") &&
+           __builtin_cpu_supports("bmi2");
+}
+
+}  // namespace sipp
+#else
+namespace sipp {
+void poseidon_permute_avx512(uint64_t*, const PoseidonFastTables&) {}
+bool poseidon_avx512_supported() { return false; }
+}  // namespace sipp
+#endif
