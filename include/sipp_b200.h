@@ -137,7 +137,9 @@ int sipp_comm_nccl_version(void);     /* ncclGetVersion of the libnccl bound at 
 /* pub fn sipp_prove_native(A, B) -> Vec<Fq12>   prover_native.rs:26-80, collectively: every rank passes its strided shard
  * (n / world pairs: A_local[j] = A[j * world + rank]) and the TOTAL n; rank 0 also passes the full A, B (the transcript
  * absorbs every input point, :36-39) and receives the proof ((2 log2 n + 1) x 384 B, returned order); the other ranks may
- * pass NULL for A_full, B_full and proof.  Without a communicator this is sipp_prove_native on one GPU. */
+ * pass NULL for A_full, B_full and proof.  Without a communicator this is sipp_prove_native on one GPU.
+ * Folds stay local (index i and its partner i + n/2 share a rank) until the tail moves to rank 0 -- by default where rank 0's
+ * look-ahead stages begin (SIPP_OPT_MATRIX_BLOCK_N points left, 256), at the latest at one pair per rank. */
 int sipp_prove_native_sharded(const uint8_t *A_local, const uint8_t *B_local, size_t n, const uint8_t *A_full, const uint8_t *B_full,
                               uint8_t *proof);
 /* same with the shard already resident in HBM (DEVICE pointers, boundary format) */

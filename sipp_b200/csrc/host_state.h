@@ -23,7 +23,7 @@ namespace sipp_host {
 extern int g_device;             // CUDA device of this process, -1 before sipp_init
 extern int g_sm_count;
 extern cudaStream_t g_stream;    // the library's non-blocking stream
-extern int g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate, g_opt_matrix_n, g_opt_matrix_block_n, g_opt_matrix_block_r;
+extern int g_opt_pipeline, g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate, g_opt_matrix_n, g_opt_matrix_block_n, g_opt_matrix_block_r;
 extern sipp_stats g_stats;
 
 int fail(int code, const char* what);             // records the message for sipp_last_error, returns `code`

@@ -79,7 +79,8 @@ int nccl_fail(int rc, const char* what) {
 
 // ------------------------------------------------------------------------------------------------ communicator of this process
 enum { COMM_NONE = 0, COMM_NCCL = 1, COMM_HOST = 2 };
-const size_t SLOT = 2 * SIPP_PARTIAL_BYTES;  // bytes per rank in the gather buffer: two partials, or one (A, B) pair (192 B)
+const size_t SLOT = 2 * SIPP_PARTIAL_BYTES;  // bytes per rank in the gather buffer per round: two partials
+const size_t COLLAPSE_MAX = 4096;            // the collapse gathers at most this many points (192 B each) through the same buffer
 const size_t XS = 72;                        // x || x^-1 || status word (+ padding)
 
 struct Comm {
@@ -88,15 +89,18 @@ struct Comm {
     sipp_allgather_fn h_allgather = nullptr;
     sipp_broadcast_fn h_broadcast = nullptr;
     void* user = nullptr;
-    uint8_t* d_gather = nullptr;  // [world][SLOT]
+    uint8_t* d_gather = nullptr;  // [world][SLOT], or the points of the collapse
     uint8_t* d_xs = nullptr;      // XS bytes
-    uint8_t* h_stage = nullptr;   // pinned: [world][SLOT] + XS
+    uint8_t* h_stage = nullptr;   // pinned: gather bytes + XS
+    size_t gather_bytes = 0;
 } g_comm;
 
 int comm_buffers() {
-    CK(cudaMalloc(&g_comm.d_gather, (size_t)g_comm.world * SLOT));
+    g_comm.gather_bytes = (size_t)g_comm.world * SLOT;
+    if (g_comm.gather_bytes < COLLAPSE_MAX * 192) g_comm.gather_bytes = COLLAPSE_MAX * 192;
+    CK(cudaMalloc(&g_comm.d_gather, g_comm.gather_bytes));
     CK(cudaMalloc(&g_comm.d_xs, XS));
-    CK(cudaMallocHost(&g_comm.h_stage, (size_t)g_comm.world * SLOT + XS));
+    CK(cudaMallocHost(&g_comm.h_stage, g_comm.gather_bytes + XS));
     return SIPP_OK;
 }
 
@@ -124,7 +128,7 @@ int comm_broadcast_xs(uint8_t* xs) {
     Comm& c = g_comm;
     if (c.world == 1) return SIPP_OK;
     if (c.kind == COMM_NCCL) {
-        uint8_t* h = c.h_stage + (size_t)c.world * SLOT;
+        uint8_t* h = c.h_stage + c.gather_bytes;
         if (c.rank == 0) {
             memcpy(h, xs, XS);
             CK(cudaMemcpyAsync(c.d_xs, h, XS, cudaMemcpyHostToDevice, g_stream));
@@ -196,23 +200,30 @@ int cb_fold(void* u, const uint8_t* x, const uint8_t* xinv) {
     return mat_fold(b->ctx, b->mt, x, xinv);
 }
 
-// every rank holds exactly one pair: gather the `world` pairs (device format, 64 + 128 B each) to rank 0
+// The tail moves to rank 0: every rank holds L = (points left) / world of them (strided: local element l is global l world + rank).
+// Each rank ships [A_local (64 L) | B_local (128 L)], rank 0 interleaves them back into global order.
 int cb_collapse(void* u) {
     CudaBackend* b = (CudaBackend*)u;
     Comm& c = g_comm;
-    const size_t rec = 64 + 128;
+    const size_t L = b->ctx->n, rec = 192 * L;
+    if ((size_t)c.world * rec > c.gather_bytes) return fail(SIPP_ERR_ARG, "collapse: more points than the gather buffer holds");
     uint8_t* mine = c.d_gather + (size_t)c.rank * rec;
-    CK(cudaMemcpyAsync(mine, b->ctx->dA, 64, cudaMemcpyDeviceToDevice, g_stream));
-    CK(cudaMemcpyAsync(mine + 64, b->ctx->dB, 128, cudaMemcpyDeviceToDevice, g_stream));
+    CK(cudaMemcpyAsync(mine, b->ctx->dA, 64 * L, cudaMemcpyDeviceToDevice, g_stream));
+    CK(cudaMemcpyAsync(mine + 64 * L, b->ctx->dB, 128 * L, cudaMemcpyDeviceToDevice, g_stream));
     int rc = comm_allgather(rec);
     if (rc) return rc;
     b->collapsed = true;
     if (c.rank != 0) return SIPP_OK;
     sipp_ctx* tail;
-    rc = ctx_alloc((size_t)c.world, &tail);
+    rc = ctx_alloc((size_t)c.world * L, &tail);
     if (rc) return rc;
-    cudaError_t e = cudaMemcpy2DAsync(tail->dA, 64, c.d_gather, rec, 64, (size_t)c.world, cudaMemcpyDeviceToDevice, g_stream);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(tail->dB, 128, c.d_gather + 64, rec, 128, (size_t)c.world, cudaMemcpyDeviceToDevice, g_stream);
+    cudaError_t e = cudaSuccess;
+    for (int r = 0; r < c.world && e == cudaSuccess; r++) {
+        const uint8_t* src = c.d_gather + (size_t)r * rec;
+        e = cudaMemcpy2DAsync((uint8_t*)tail->dA + 64 * (size_t)r, 64 * (size_t)c.world, src, 64, 64, L, cudaMemcpyDeviceToDevice, g_stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync((uint8_t*)tail->dB + 128 * (size_t)r, 128 * (size_t)c.world, src + 64 * L, 128, 128, L, cudaMemcpyDeviceToDevice, g_stream);
+    }
     if (e != cudaSuccess) { sipp_ctx_destroy(tail); return cuda_fail(e, "tail gather"); }
     sipp_ctx_destroy(b->ctx);  // pool block: recycled only by later work on the same stream
     b->ctx = tail;
@@ -240,7 +251,9 @@ int cb_agree(void*, int rc) {
 
 // ------------------------------------------------------------------------------------------------ the protocol loop
 // `started`: rank 0's absorb job when the caller already started it (before the upload of its shard), else NULL
-int sharded_protocol(const sipp_shard_backend* be, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof, AbsorbJob* started) {
+// `collapse_at`: the tail moves to rank 0 as soon as at most this many points are left in all (never later than one pair per rank)
+int sharded_protocol(const sipp_shard_backend* be, size_t n, const uint8_t* A_full, const uint8_t* B_full, uint8_t* proof, AbsorbJob* started,
+                     size_t collapse_at) {
     const int rank = be->rank, world = be->world;
     const size_t np = sipp_proof_len(n);
     std::vector<uint8_t> fwd(rank == 0 ? np * 384 : 0);  // proof in push order; reversed at the end (prover_native.rs:78)
@@ -295,14 +308,14 @@ int sharded_protocol(const sipp_shard_backend* be, size_t n, const uint8_t* A_fu
         if (r) return r;
         return be->fold(be->user, xs, xs + 32);                                // :60-74 on the local shard
     };
-    while (!rc && cur > 1 && cur / (size_t)world >= 2) {                       // folds stay local while n >= 2 world
+    while (!rc && cur > 1 && cur / (size_t)world >= 2 && cur > collapse_at) {  // folds stay local while n >= 2 world
         rc = round(true);
         cur /= 2;
     }
     if (rc) return rc;
     if (rank == 0 && first) absorb_z();                                        // no local round ran (n == world, or n == 1)
     if (cur > 1) {
-        rc = be->collapse(be->user);                                           // one pair per rank: the tail moves to rank 0
+        rc = be->collapse(be->user);                                           // the tail moves to rank 0
         if (rc) return rc;
         while (rank == 0 && cur > 1) {
             rc = round(false);
@@ -331,7 +344,10 @@ int prove_sharded(sipp_ctx* c, int create_rc, size_t n, const uint8_t* A_full, c
         be.user = &b; be.rank = g_comm.rank; be.world = g_comm.world;
         be.local_len = cb_local_len; be.products = cb_products; be.combine = cb_combine; be.broadcast = cb_broadcast;
         be.fold = cb_fold; be.collapse = cb_collapse;
-        rc = sharded_protocol(&be, n, A_full, B_full, proof, job);
+        // rank 0 runs the look-ahead stages and the pairing-matrix tail (k_mat.cu) alone: collapse where they begin
+        size_t at = g_opt_pipeline && g_opt_fe_engine ? (size_t)(g_opt_matrix_block_n > g_opt_matrix_n ? g_opt_matrix_block_n : g_opt_matrix_n) : 0;
+        if (at > COLLAPSE_MAX) at = COLLAPSE_MAX;
+        rc = sharded_protocol(&be, n, A_full, B_full, proof, job, at);
     }
     if (b.ctx) {
         cudaStreamSynchronize(g_stream);
@@ -441,7 +457,7 @@ int sipp_prove_native_sharded_backend(const sipp_shard_backend* be, size_t n, co
     int rc = check_shape(n, be->world);
     if (rc) return rc;
     if (be->rank == 0 && (!A_full || !B_full || !proof)) return fail(SIPP_ERR_ARG, "rank 0 needs the full A, B (transcript) and the proof buffer");
-    return sharded_protocol(be, n, A_full, B_full, proof, nullptr);
+    return sharded_protocol(be, n, A_full, B_full, proof, nullptr, 0);  // a caller's backend: one pair per rank, as documented
 }
 
 }  // extern "C"
