@@ -23,7 +23,7 @@ namespace sipp_host {
 extern int g_device;             // CUDA device of this process, -1 before sipp_init
 extern int g_sm_count;
 extern cudaStream_t g_stream;    // the library's non-blocking stream
-extern int g_opt_pipeline, g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate, g_opt_matrix_n, g_opt_matrix_block_n, g_opt_matrix_block_r;
+extern int g_opt_pipeline, g_opt_fe_norm, g_opt_fq12_order, g_opt_profile, g_opt_fold_straus, g_opt_batch_kpg_max, g_opt_batch_streams, g_opt_batch_qlines, g_opt_wide_max, g_opt_wide_fold_max, g_opt_fe_engine, g_opt_validate, g_opt_matrix_n, g_opt_matrix_first, g_opt_matrix_block_n, g_opt_matrix_block_r;
 extern sipp_stats g_stats;
 
 int fail(int code, const char* what);             // records the message for sipp_last_error, returns `code`
@@ -98,10 +98,15 @@ struct MatTail {
     }
     ~MatTail() { reset(); }
 };
+size_t mat_stage_first(size_t n);  // blocks of the stage built from the inputs themselves (0: none)
+int mat_diag_product(MatTail& mt, uint8_t* z);
 size_t mat_stage(size_t n);  // number of blocks of the stage that starts with n points left (0: a plain round)
 int mat_build(sipp_ctx* c, MatTail& mt, size_t nr);
 int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr);
 int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]);
+
+// the protocol loop of a single GPU on a context whose A, B are being absorbed by `job` (sipp_b200.cu)
+int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof);
 
 // CUDA-event span around a kernel class (SIPP_OPT_PROFILE): kind 0 miller, 1 reduce / final exponentiation, 2 fold, 3 other
 int span_begin(int kind, cudaStream_t s);

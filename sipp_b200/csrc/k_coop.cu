@@ -134,6 +134,37 @@ __global__ void __launch_bounds__(128) k_eval_lines_batch(const uint32_t* __rest
     store_fq2_words(o + 64, fq2_mul_xi(l3));
 }
 
+// pairing-matrix stages (k_mat.cu) with many pairs per entry: entry (i, j) of an nr x nr matrix pairs A[i m + t] with B[j m + t],
+// t < m, so every B point meets nr different A points -- its line coefficients are computed once (k_qlines_batch) and evaluated
+// here.  Pair index q = (i nr + j) m + t, one thread per (pair, step), output layout as k_lines.
+__global__ void __launch_bounds__(128) k_eval_lines_mat(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, size_t nr, size_t m,
+                                                        const uint32_t* __restrict__ qlines, uint32_t* __restrict__ lines) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nr * nr * m * SIPP_LINES_PER_PAIR) return;
+    const size_t pair = t / SIPP_LINES_PER_PAIR;
+    const int step = (int)(t - pair * SIPP_LINES_PER_PAIR);
+    const size_t e = pair / m, u = pair % m;
+    const size_t ia = (e / nr) * m + u, ib = (e % nr) * m + u;
+    const G1A p = load_g1(A, ia);
+    uint32_t* o = lines + t * SIPP_LINE_WORDS;
+    const G2A q = load_g2(B, ib);
+    if (affine_is_identity(p) || affine_is_identity(q)) {
+        store_fq2_words(o, fq2_one());
+        store_fq2_words(o + 16, fq2_zero());
+        store_fq2_words(o + 32, fq2_zero());
+        store_fq2_words(o + 48, fq2_zero());
+        store_fq2_words(o + 64, fq2_zero());
+        return;
+    }
+    const uint32_t* src = qlines + (ib * SIPP_LINES_PER_PAIR + step) * SIPP_QLINE_WORDS;
+    const Fq2 l0 = fq2_scale(load_fq2_words(src), p.y), l1 = fq2_scale(load_fq2_words(src + 16), p.x), l3 = load_fq2_words(src + 32);
+    store_fq2_words(o, l0);
+    store_fq2_words(o + 16, l1);
+    store_fq2_words(o + 32, fq2_mul_xi(l1));
+    store_fq2_words(o + 48, l3);
+    store_fq2_words(o + 64, fq2_mul_xi(l3));
+}
+
 // ------------------------------------------------------------------------------------------------ A: accumulation
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -416,6 +447,11 @@ int launch_eval_lines_batch(const uint32_t* A, const uint32_t* B, const BatchJob
                             cudaStream_t s) {
     size_t threads = np * job.h * SIPP_LINES_PER_PAIR;
     k_eval_lines_batch<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(A, B, job, p0, np, qlines, lines);
+    return (int)cudaGetLastError();
+}
+int launch_eval_lines_mat(const uint32_t* A, const uint32_t* B, size_t nr, size_t m, const uint32_t* qlines, uint32_t* lines, cudaStream_t s) {
+    const size_t threads = nr * nr * m * SIPP_LINES_PER_PAIR;
+    k_eval_lines_mat<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(A, B, nr, m, qlines, lines);
     return (int)cudaGetLastError();
 }
 size_t qlines_bytes_per_point() { return (size_t)SIPP_LINES_PER_PAIR * SIPP_QLINE_WORDS * sizeof(uint32_t); }

@@ -60,21 +60,22 @@ int launch_mat_fe(const uint32_t* miller, size_t count, uint32_t* E, int ark_nor
 }
 
 // the factors of Z_L, Z_R in the layout the reduction kernels read: partials[i][y][96], y = 0: E[i+h][i]  (inner_product(A2, B1),
-// prover_native.rs:48), y = 1: E[i][i+h]  (inner_product(A1, B2), :49)
-__global__ void k_mat_diag(const uint32_t* __restrict__ E, size_t n, uint32_t* __restrict__ partials) {
+// prover_native.rs:48), y = 1: E[i][i+h]  (inner_product(A1, B2), :49); main_diagonal: partials[i][96] = E[i][i], the factors of
+// Z = inner_product(A, B)  (:29) when the first matrix is built from the inputs themselves
+__global__ void k_mat_diag(const uint32_t* __restrict__ E, size_t n, int main_diagonal, uint32_t* __restrict__ partials) {
     const size_t h = n / 2;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t e = t / 24;  // 24 uint4 per entry
     const int w = (int)(t % 24);
-    if (e >= 2 * h) return;
+    if (e >= (main_diagonal ? n : 2 * h)) return;
     const size_t i = e >> 1;
     const int y = (int)(e & 1);
-    const size_t src = y == 0 ? (i + h) * n + i : i * n + (i + h);
+    const size_t src = main_diagonal ? e * n + e : (y == 0 ? (i + h) * n + i : i * n + (i + h));
     reinterpret_cast<uint4*>(partials + e * 96)[w] = __ldg(reinterpret_cast<const uint4*>(E + src * 96) + w);
 }
-int launch_mat_diag(const uint32_t* E, size_t n, uint32_t* partials, cudaStream_t s) {
+int launch_mat_diag(const uint32_t* E, size_t n, int main_diagonal, uint32_t* partials, cudaStream_t s) {
     const size_t threads = n * 24;
-    k_mat_diag<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(E, n, partials);
+    k_mat_diag<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(E, n, main_diagonal, partials);
     return (int)cudaGetLastError();
 }
 

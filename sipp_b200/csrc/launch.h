@@ -60,7 +60,7 @@ size_t lines_bytes_per_pair();
 // pairing-matrix tail (k_mat.cu): E[i][j] = e(A_i, B_j) for the n points left, then folds of the MATRIX instead of the points
 int launch_mat_gather(const uint32_t* A, const uint32_t* B, size_t nr, size_t m, uint32_t* Aexp, uint32_t* Bexp, cudaStream_t s);
 int launch_mat_fe(const uint32_t* miller, size_t count, uint32_t* E, int ark_norm, cudaStream_t s);
-int launch_mat_diag(const uint32_t* E, size_t n, uint32_t* partials, cudaStream_t s);
+int launch_mat_diag(const uint32_t* E, size_t n, int main_diagonal, uint32_t* partials, cudaStream_t s);
 int launch_mat_fold(const uint32_t* E, size_t n, uint32_t* Eout, const GtPlan& plan, cudaStream_t s);
 
 // batched instances (k_coop.cu, k_fold.cu, k_transcript.cu)
@@ -73,6 +73,7 @@ int launch_qlines_batch(const uint32_t* B, size_t npoints, uint32_t* qlines, cud
 int launch_eval_lines_batch(const uint32_t* A, const uint32_t* B, const BatchJob& job, size_t p0, size_t np, const uint32_t* qlines, uint32_t* lines,
                             cudaStream_t s);
 size_t qlines_bytes_per_point();
+int launch_eval_lines_mat(const uint32_t* A, const uint32_t* B, size_t nr, size_t m, const uint32_t* qlines, uint32_t* lines, cudaStream_t s);
 int launch_fe_batch_eng(const uint32_t* partials, size_t nproducts, int gpp, int nprod, uint32_t* out, size_t out_stride, int slot0, int slot1, int ark_norm,
                         cudaStream_t s);
 int launch_fold_batch(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t count, const FoldPlan* plans, cudaStream_t s);

@@ -32,7 +32,8 @@ int g_opt_fold_straus = 1;     // throughput folds (batched instances, large rou
 int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own streams (0 = choose by batch size)
 int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
-int g_opt_matrix_n = 32;       // pairing-matrix tail (k_mat.cu) once at most this many points are left; 0 = off
+int g_opt_matrix_n = 16;       // pairing-matrix tail (k_mat.cu) once at most this many points are left; 0 = off
+int g_opt_matrix_first = 1;     // the first matrix is built from the inputs, under the host's absorb chain
 int g_opt_matrix_block_n = 256, g_opt_matrix_block_r = 8;  // look-ahead stages: from at most this many points, that many blocks
 int g_opt_validate = 1;        // every prove / verify entry point checks its points: on the curve, B_i in the order-r subgroup
 
@@ -334,31 +335,58 @@ size_t mat_stage(size_t n) {
     return nr >= 4 ? nr : 0;
 }
 
+// The FIRST stage of a proof starts from the inputs themselves, before any challenge exists: it runs in the shadow of the host's
+// 8n-permutation absorb chain, gives Z as the product of its diagonal, and the first log2(nr) rounds cost one matrix fold each.
+// As many blocks as keep the launch under 2^17 pairs (the matrix needs n nr Miller loops), at most 32.
+size_t mat_stage_first(size_t n) {
+    if (!g_opt_matrix_first || !g_opt_pipeline || !g_opt_fe_engine || n < 8 || g_opt_matrix_n < 2) return 0;
+    if (n <= (size_t)g_opt_matrix_n) return n;               // the whole proof on the matrix of its inputs
+    size_t nr = n / (size_t)g_opt_matrix_n;                  // ideally the stage ends where the tail begins
+    if (nr > 32) nr = 32;
+    while (nr > 1 && nr * n > ((size_t)1 << 17)) nr >>= 1;   // n nr Miller loops
+    if (nr < 4) nr = 4;
+    return (nr * n <= ((size_t)1 << 17) && n / nr >= 2) ? nr : 0;
+}
+
 int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
     const size_t n = c->n, m = n / nr, P = nr * nr, pairs = P * m;
-    uint32_t *aexp = nullptr, *bexp = nullptr, *mil = nullptr;
-    const size_t blocks = (size_t)accum_eng_blocks(m, 1);
+    // small launches: the lane engines (latency); large ones (a first stage): line coefficients of every B point once + the
+    // throughput accumulation kernel
+    const bool big = pairs > (size_t)g_opt_wide_max;
+    int kpg = 1;
+    if (big) {
+        const size_t by_block = (m + 19) / 20, by_fill = (pairs + 11839) / 11840;
+        kpg = (int)(by_block < by_fill ? by_block : by_fill);
+        if (kpg < 1) kpg = 1;
+    }
+    const size_t blocks = big ? (size_t)accum_blocks(m, kpg) : (size_t)accum_eng_blocks(m, 1);
+    uint32_t *aexp = nullptr, *bexp = nullptr, *mil = nullptr, *ql = nullptr;
     int rc = scratch_reserve(m == 1 ? nr : (blocks * P + 1) / 2);
     if (!rc) rc = lines_reserve(pairs * lines_bytes_per_pair());
     if (rc) return rc;
     cudaError_t e = pool_alloc((void**)&mt.E[0], P * 384);
     if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (P / 4) * 384);
-    if (e == cudaSuccess) e = pool_alloc((void**)&aexp, pairs * 64);
-    if (e == cudaSuccess) e = pool_alloc((void**)&bexp, pairs * 128);
+    if (e == cudaSuccess && !big) e = pool_alloc((void**)&aexp, pairs * 64);
+    if (e == cudaSuccess && !big) e = pool_alloc((void**)&bexp, pairs * 128);
+    if (e == cudaSuccess && big) e = pool_alloc((void**)&ql, n * qlines_bytes_per_point());
     if (e == cudaSuccess && m == 1) e = pool_alloc((void**)&mil, P * 384);
     int le = 0;
     if (e == cudaSuccess) {
         {
             Span sp(0, g_stream);
-            MillerJob job;
-            job.a_off[0] = job.b_off[0] = job.a_off[1] = job.b_off[1] = 0;
-            job.m = pairs;
-            le = launch_mat_gather(c->dA, c->dB, nr, m, aexp, bexp, g_stream);
-            if (!le)
-                le = pairs <= (size_t)g_opt_wide_max ? launch_lines_wide(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream)
-                                                     : launch_lines(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream);
-            // the expanded launch is laid out [entry][pair of the block]: entry = one "product" of m pairs for the accumulation
-            if (!le) le = m == 1 ? launch_accum_eng_each(g_scr.lines, P, mil, g_stream) : launch_accum_eng(g_scr.lines, m, (int)P, 1, g_scr.partials, 0, g_stream);
+            if (big) {
+                le = launch_qlines_batch(c->dB, n, ql, g_stream);
+                if (!le) le = launch_eval_lines_mat(c->dA, c->dB, nr, m, ql, g_scr.lines, g_stream);
+                // the expanded launch is laid out [entry][pair of the block]: an entry is one "product" of m pairs
+                if (!le) le = launch_accum(g_scr.lines, m, (int)P, kpg, g_scr.partials, 0, g_stream);
+            } else {
+                MillerJob job;
+                job.a_off[0] = job.b_off[0] = job.a_off[1] = job.b_off[1] = 0;
+                job.m = pairs;
+                le = launch_mat_gather(c->dA, c->dB, nr, m, aexp, bexp, g_stream);
+                if (!le) le = launch_lines_wide(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream);
+                if (!le) le = m == 1 ? launch_accum_eng_each(g_scr.lines, P, mil, g_stream) : launch_accum_eng(g_scr.lines, m, (int)P, 1, g_scr.partials, 0, g_stream);
+            }
         }
         if (!le) {
             Span sp(1, g_stream);
@@ -372,6 +400,7 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
     pool_free(aexp);
     pool_free(bexp);
     pool_free(mil);
+    pool_free(ql);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pairing matrix)");
     if (le) return cuda_fail((cudaError_t)le, "pairing matrix");
     mt.n = nr;
@@ -381,12 +410,28 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
     return SIPP_OK;
 }
 
+// Z = prod E[i][i]   (prover_native.rs:29) from a matrix built over the inputs
+int mat_diag_product(MatTail& mt, uint8_t* z) {
+    {
+        Span sp(1, g_stream);
+        int le = launch_mat_diag(mt.E[mt.cur], mt.n, 1, g_scr.partials, g_stream);
+        if (!le) le = launch_reduce_fe_eng(g_scr.partials, (int)mt.n, 1, g_scr.out, 2, g_opt_fe_norm, g_stream);
+        if (le) return cuda_fail((cudaError_t)le, "matrix diagonal");
+    }
+    g_stats.launches += 2;
+    g_stats.miller_pairs += mt.n * mt.m;
+    CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, 384, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    memcpy(z, g_scr.h_out, 384);
+    return SIPP_OK;
+}
+
 // Z_L = prod E[i+h][i], Z_R = prod E[i][i+h]   (prover_native.rs:48-49)
 int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr) {
     const size_t h = mt.n / 2;
     {
         Span sp(1, g_stream);
-        int le = launch_mat_diag(mt.E[mt.cur], mt.n, g_scr.partials, g_stream);
+        int le = launch_mat_diag(mt.E[mt.cur], mt.n, 0, g_scr.partials, g_stream);
         if (!le) le = launch_reduce_fe_eng(g_scr.partials, (int)h, 2, g_scr.out, 2, g_opt_fe_norm, g_stream);
         if (le) return cuda_fail((cudaError_t)le, "matrix products");
     }
@@ -514,6 +559,7 @@ int sipp_set_option(int option, int value) {
             if (value < 0 || value > 64 || (value & (value - 1))) return fail(SIPP_ERR_ARG, "SIPP_OPT_MATRIX_TAIL: 0 or a power of two <= 64");
             g_opt_matrix_n = value;
             return SIPP_OK;
+        case SIPP_OPT_MATRIX_FIRST: g_opt_matrix_first = value ? 1 : 0; return SIPP_OK;
         case SIPP_OPT_MATRIX_BLOCK_N: g_opt_matrix_block_n = value < 0 ? 0 : (value > 4096 ? 4096 : value); return SIPP_OK;
         case SIPP_OPT_MATRIX_BLOCK_R:
             if (value < 4 || value > 32 || (value & (value - 1))) return fail(SIPP_ERR_ARG, "SIPP_OPT_MATRIX_BLOCK_R: 4, 8, 16 or 32");
@@ -538,6 +584,7 @@ int sipp_get_option(int option) {
         case SIPP_OPT_BATCH_QLINES: return g_opt_batch_qlines;
         case SIPP_OPT_VALIDATE_POINTS: return g_opt_validate;
         case SIPP_OPT_MATRIX_TAIL: return g_opt_matrix_n;
+        case SIPP_OPT_MATRIX_FIRST: return g_opt_matrix_first;
         case SIPP_OPT_MATRIX_BLOCK_N: return g_opt_matrix_block_n;
         case SIPP_OPT_MATRIX_BLOCK_R: return g_opt_matrix_block_r;
         default: return -1;
@@ -780,16 +827,24 @@ int sipp_fr_inverse(const uint8_t x[32], uint8_t out[32]) {
 size_t sipp_proof_len(size_t n) { return is_pow2(n) ? 2 * log2_exact(n) + 1 : 0; }
 
 // the protocol loop on a context whose A, B are being absorbed by `job` (started by the caller as early as possible)
-static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
+}  // extern "C"
+namespace sipp_host {
+int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
     size_t n = c->n;
     size_t np = sipp_proof_len(n);
     std::vector<uint8_t> fwd(np * 384);  // proof in push order; reversed at the end (prover_native.rs:78)
     size_t k = 0;
     sipp_transcript& tr = job.tr;
-    int rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                       // let Z = inner_product(A, B);   :29
+    MatTail mt;
+    int rc;
+    if (const size_t nr0 = mat_stage_first(n)) {                              // Z and the first rounds from ONE matrix over the inputs
+        rc = mat_build(c, mt, nr0);
+        if (!rc) rc = mat_diag_product(mt, &fwd[384 * k]);                    // let Z = inner_product(A, B);   :29
+    } else {
+        rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                        // let Z = inner_product(A, B);   :29
+    }
     k++;
     bool first = true;
-    MatTail mt;
     while (rc == SIPP_OK && n > 1) {                                          // :45
         uint8_t* zl = &fwd[384 * k];
         uint8_t* zr = &fwd[384 * (k + 1)];
@@ -825,6 +880,8 @@ static int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
     for (size_t i = 0; i < np; i++) memcpy(proof + 384 * i, &fwd[384 * (np - 1 - i)], 384);  // proof.reverse()  :78
     return SIPP_OK;
 }
+}  // namespace sipp_host
+extern "C" {
 
 int sipp_ctx_prove(sipp_ctx* c, const uint8_t* A, const uint8_t* B, uint8_t* proof) {
     if (!c || !A || !B || !proof) return fail(SIPP_ERR_ARG, "null argument");

@@ -283,6 +283,16 @@ def test_matrix_tail_thresholds(sipp, oracle):
             assert b"".join(sipp.sipp_prove_native(A, B)) == want, (thr, bn, br)
         sipp.set_option(_lib.OPT_MATRIX_BLOCK_N, 256)
         sipp.set_option(_lib.OPT_MATRIX_BLOCK_R, 8)
+        # first stage (matrix over the inputs, Z from its diagonal) on / off, for sizes on both sides of every branch of its rule
+        for first in (0, 1):
+            sipp.set_option(_lib.OPT_MATRIX_FIRST, first)
+            for thr in (32, 8, 2):
+                sipp.set_option(_lib.OPT_MATRIX_TAIL, thr)
+                for m in (64, 32, 16, 8, 4):
+                    got = b"".join(sipp.sipp_prove_native(A[:64 * m], B[:128 * m]))
+                    assert got == (want if m == 64 else oracle.sipp_prove(A[:64 * m], B[:128 * m], threads=4)), (first, thr, m)
+        sipp.set_option(_lib.OPT_MATRIX_FIRST, 1)
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 16)
         sipp.set_option(_lib.OPT_FE_NORMALISATION, 1)
         sipp.set_option(_lib.OPT_MATRIX_TAIL, 0)
         ref = b"".join(sipp.sipp_prove_native(A[:64 * 16], B[:128 * 16]))
@@ -290,9 +300,10 @@ def test_matrix_tail_thresholds(sipp, oracle):
         assert b"".join(sipp.sipp_prove_native(A[:64 * 16], B[:128 * 16])) == ref
     finally:
         sipp.set_option(_lib.OPT_FE_NORMALISATION, 0)
-        sipp.set_option(_lib.OPT_MATRIX_TAIL, 32)
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 16)
         sipp.set_option(_lib.OPT_MATRIX_BLOCK_N, 256)
         sipp.set_option(_lib.OPT_MATRIX_BLOCK_R, 8)
+        sipp.set_option(_lib.OPT_MATRIX_FIRST, 1)
 
 
 def test_prove_n128_config0(sipp, oracle):
