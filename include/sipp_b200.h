@@ -102,6 +102,11 @@ int sipp_ctx_inner_product(sipp_ctx *ctx, uint8_t out[384]);
 int sipp_ctx_cross_products(sipp_ctx *ctx, uint8_t zl[384], uint8_t zr[384]);
 /* A <- A1 + x A2, B <- B1 + x^-1 B2, n <- n/2                   prover_native.rs:60-74 */
 int sipp_ctx_fold(sipp_ctx *ctx, const uint8_t x[32], const uint8_t x_inv[32]);
+/* Opt-in for a host that keeps its own transcript: with stages on, sipp_ctx_inner_product / _cross_products / _fold may run on
+ * pairing-matrix stages (SIPP_OPT_MATRIX_*: same Z, Z_L, Z_R bit for bit, several times shorter rounds) exactly as the library's
+ * own sipp_prove_native does.  The price: once the tail stage has begun the points are not folded any more, and sipp_ctx_read
+ * returns SIPP_ERR_ARG.  Off by default: every call then does literally what its reference line does. */
+int sipp_ctx_set_stages(sipp_ctx *ctx, int on);
 /* current A, B back to the host (final_A / final_B: verifier_native.rs:74-75; every round in tests) */
 int sipp_ctx_read(sipp_ctx *ctx, uint8_t *A_out, uint8_t *B_out);
 

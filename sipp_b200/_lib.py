@@ -70,6 +70,7 @@ def load():
     lib.sipp_ctx_cross_products.argtypes = [vp, u8p, u8p]
     lib.sipp_ctx_fold.argtypes = [vp, u8p, u8p]
     lib.sipp_ctx_read.argtypes = [vp, u8p, u8p]
+    lib.sipp_ctx_set_stages.argtypes = [vp, ctypes.c_int]
     lib.sipp_ctx_partial_products.argtypes = [vp, i, vp, vp]
     lib.sipp_combine_partials.argtypes = [vp, i, i, u8p, vp]
     lib.sipp_pairing.argtypes = [u8p, u8p, u8p]

@@ -259,6 +259,11 @@ class ProverContext:
     def fold(self, x: bytes, x_inv: bytes) -> None:
         _lib.check(_lib.load().sipp_ctx_fold(self._h, bytes(x), bytes(x_inv)))
 
+    def set_stages(self, on: bool = True) -> None:
+        """opt in to the pairing-matrix stages for inner_product / cross_products / fold (sipp_ctx_set_stages): same values,
+        shorter rounds; read() is refused once the tail stage has begun"""
+        _lib.check(_lib.load().sipp_ctx_set_stages(self._h, 1 if on else 0))
+
     def read(self):
         n = len(self)
         a, b = ctypes.create_string_buffer(G1_BYTES * n), ctypes.create_string_buffer(G2_BYTES * n)

@@ -11,11 +11,35 @@
 #include "../../include/sipp_b200.h"
 #include "launch.h"
 
+namespace sipp_host {
+void pool_free(void* p);
+// A pairing-matrix stage of a single proof (k_mat.cu; SIPP_OPT_MATRIX_*): E[i][j] = <A_block_i, B_block_j> over the points of a
+// context, then Z_L / Z_R as products of matrix entries and the fold as GT exponentiations of the matrix.
+struct MatTail {
+    uint32_t* E[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t n = 0;   // virtual points (blocks) the matrix stands for; 0 = no stage in progress
+    size_t m = 1;   // points per block (1: the tail of the proof)
+    int folds = 0;  // point folds issued on the side stream in this stage
+    void reset() {
+        pool_free(E[0]);
+        pool_free(E[1]);
+        E[0] = E[1] = nullptr;
+        n = 0;
+        m = 1;
+    }
+    ~MatTail() { reset(); }
+};
+}  // namespace sipp_host
+
 // device-resident A, B of the current round of one prover (or one rank's strided shard of it)
 struct sipp_ctx {
     uint32_t* dA = nullptr;  // n x 16 words, Montgomery
     uint32_t* dB = nullptr;  // n x 32 words
     size_t n = 0, cap = 0;
+    bool stages = false;     // sipp_ctx_set_stages: products / folds may run on pairing-matrix stages
+    bool stale = false;      // a tail stage ran: the points were not folded any more (sipp_ctx_read refuses)
+    sipp_host::MatTail mt;
 };
 
 namespace sipp_host {
@@ -50,7 +74,6 @@ inline bool fq_bytes_canonical(const uint8_t* b, size_t n_fq) {
 }
 // grow-only device memory pool (cudaFree synchronises the device; blocks are recycled, released in sipp_shutdown)
 cudaError_t pool_alloc(void** out, size_t bytes);
-void pool_free(void* p);
 // the line table shared by every Miller launch of the process (grow-only)
 int lines_reserve(size_t bytes);
 uint32_t* lines_buffer();
@@ -80,24 +103,7 @@ struct AbsorbJob {
     }
 };
 
-// Pairing-matrix tail of a single proof (k_mat.cu; SIPP_OPT_MATRIX_TAIL): E[i][j] = e(A_i, B_j) over the points left in a context,
-// then Z_L / Z_R as products of matrix entries and the fold as GT exponentiations of the matrix.  Used by the single-GPU prover and
-// by rank 0's tail of the sharded one.
-struct MatTail {
-    uint32_t* E[2] = {nullptr, nullptr};
-    int cur = 0;
-    size_t n = 0;   // virtual points (blocks) the matrix stands for; 0 = no stage in progress
-    size_t m = 1;   // points per block (1: the tail of the proof)
-    int folds = 0;  // point folds issued on the side stream in this stage
-    void reset() {
-        pool_free(E[0]);
-        pool_free(E[1]);
-        E[0] = E[1] = nullptr;
-        n = 0;
-        m = 1;
-    }
-    ~MatTail() { reset(); }
-};
+// pairing-matrix stages (sipp_b200.cu): used by the single-GPU prover and by rank 0's tail of the sharded one
 size_t mat_stage_first(size_t n);  // blocks of the stage built from the inputs themselves (0: none)
 int mat_diag_product(MatTail& mt, uint8_t* z);
 size_t mat_stage(size_t n);  // number of blocks of the stage that starts with n points left (0: a plain round)

@@ -151,9 +151,8 @@ struct CudaBackend {
     sipp_ctx* ctx = nullptr;
     bool collapsed = false;  // the tail lives on rank 0 alone
     int last_nprod = 0;
-    MatTail mt;              // rank 0 alone (collapsed tail, or a world of one): the last rounds on the pairing matrix (k_mat.cu)
-    bool mat_round = false;  // this round's products came from the matrix
-    uint8_t tail_out[768];
+    uint8_t tail_out[768];   // rank 0 alone (the collapsed tail): products straight from the context (pairing-matrix stages, k_mat.cu)
+    bool tail_round = false;
 };
 bool cb_alone(const CudaBackend* b) { return b->collapsed || g_comm.world == 1; }
 
@@ -163,16 +162,10 @@ int cb_products(void* u, int which) {
     CudaBackend* b = (CudaBackend*)u;
     const int nprod = which == 0 ? 1 : 2;
     b->last_nprod = nprod;
-    if (which == 1 && cb_alone(b)) {
-        if (!b->mt.n) {
-            const size_t nr = mat_stage(b->ctx->n);
-            if (nr) {
-                int rc = mat_build(b->ctx, b->mt, nr);
-                if (rc) return rc;
-            }
-        }
-        b->mat_round = b->mt.n != 0;
-        if (b->mat_round) return mat_products(b->mt, b->tail_out, b->tail_out + 384);
+    b->tail_round = which == 1 && cb_alone(b);
+    if (b->tail_round) {
+        b->ctx->stages = true;
+        return sipp_ctx_cross_products(b->ctx, b->tail_out, b->tail_out + 384);
     }
     const size_t bytes = (size_t)nprod * SIPP_PARTIAL_BYTES;
     const int slot = b->collapsed ? 0 : g_comm.rank;
@@ -184,7 +177,7 @@ int cb_products(void* u, int which) {
 
 int cb_combine(void* u, int nprod, uint8_t* out) {
     CudaBackend* b = (CudaBackend*)u;
-    if (b->mat_round && nprod == 2) {
+    if (b->tail_round && nprod == 2) {
         memcpy(out, b->tail_out, 768);
         return SIPP_OK;
     }
@@ -194,10 +187,7 @@ int cb_combine(void* u, int nprod, uint8_t* out) {
 int cb_broadcast(void*, uint8_t* xs) { return comm_broadcast_xs(xs); }
 
 int cb_fold(void* u, const uint8_t* x, const uint8_t* xinv) {
-    CudaBackend* b = (CudaBackend*)u;
-    if (!b->mat_round) return sipp_ctx_fold(b->ctx, x, xinv);
-    b->mat_round = false;
-    return mat_fold(b->ctx, b->mt, x, xinv);
+    return sipp_ctx_fold(((CudaBackend*)u)->ctx, x, xinv);
 }
 
 // The tail moves to rank 0: every rank holds L = (points left) / world of them (strided: local element l is global l world + rank).

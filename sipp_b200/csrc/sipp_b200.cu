@@ -467,6 +467,7 @@ int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[3
         if (le) return cuda_fail((cudaError_t)le, "k_fold (look-ahead stage)");
         g_stats.launches++;
     }
+    if (mt.m == 1) c->stale = true;  // the tail: the points are not folded any more
     g_stats.fold_points += h;
     c->n = h;
     mt.n /= 2;
@@ -665,19 +666,44 @@ int sipp_ctx_destroy(sipp_ctx* c) {
 
 size_t sipp_ctx_len(const sipp_ctx* c) { return c ? c->n : 0; }
 
+int sipp_ctx_set_stages(sipp_ctx* c, int on) {
+    if (!c) return fail(SIPP_ERR_ARG, "null ctx");
+    if (c->mt.n) return fail(SIPP_ERR_ARG, "a pairing-matrix stage is in progress");
+    c->stages = on != 0;
+    return SIPP_OK;
+}
+
 int sipp_ctx_inner_product(sipp_ctx* c, uint8_t out[384]) {
     if (!c || !out) return fail(SIPP_ERR_ARG, "null argument");
+    if (c->stages && !c->mt.n) {
+        if (const size_t nr0 = mat_stage_first(c->n)) {  // Z and the first rounds from ONE matrix over the inputs
+            int rc = mat_build(c, c->mt, nr0);
+            return rc ? rc : mat_diag_product(c->mt, out);
+        }
+    }
     return ctx_products(c, 0, out, nullptr);
 }
 
 int sipp_ctx_cross_products(sipp_ctx* c, uint8_t zl[384], uint8_t zr[384]) {
     if (!c || !zl || !zr) return fail(SIPP_ERR_ARG, "null argument");
+    if (c->stages) {
+        if (c->n < 2) return fail(SIPP_ERR_ARG, "cross products need n >= 2");
+        if (!c->mt.n) {
+            const size_t nr = mat_stage(c->n);  // a pairing-matrix stage starts here?
+            if (nr) {
+                int rc = mat_build(c, c->mt, nr);
+                if (rc) return rc;
+            }
+        }
+        if (c->mt.n) return mat_products(c->mt, zl, zr);
+    }
     return ctx_products(c, 1, zl, zr);
 }
 
 int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
     if (!c || !x || !x_inv) return fail(SIPP_ERR_ARG, "null argument");
     if (c->n < 2) return fail(SIPP_ERR_ARG, "fold needs n >= 2");
+    if (c->mt.n) return mat_fold(c, c->mt, x, x_inv);  // :60-74 on the matrix of the stage in progress
     size_t h = c->n / 2;
     FoldPlan plan;
     if (fold_plan_build(x, x_inv, &plan)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
@@ -709,6 +735,8 @@ int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
 
 int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
     if (!c) return fail(SIPP_ERR_ARG, "null ctx");
+    if (c->stale) return fail(SIPP_ERR_ARG, "the points of this context were not folded during its pairing-matrix tail (sipp_ctx_set_stages)");
+    if (c->mt.n && c->mt.m > 1) CK(order_after(g_stream, g_fold_stream));  // look-ahead stage: the folds run on the side stream
     size_t n = c->n;
     uint32_t* tmp;
     CK(pool_alloc((void**)&tmp, n * 32 * sizeof(uint32_t)));
@@ -835,25 +863,14 @@ int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
     std::vector<uint8_t> fwd(np * 384);  // proof in push order; reversed at the end (prover_native.rs:78)
     size_t k = 0;
     sipp_transcript& tr = job.tr;
-    MatTail mt;
-    int rc;
-    if (const size_t nr0 = mat_stage_first(n)) {                              // Z and the first rounds from ONE matrix over the inputs
-        rc = mat_build(c, mt, nr0);
-        if (!rc) rc = mat_diag_product(mt, &fwd[384 * k]);                    // let Z = inner_product(A, B);   :29
-    } else {
-        rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                        // let Z = inner_product(A, B);   :29
-    }
+    c->stages = true;  // Z_L, Z_R and the folds may come from pairing-matrix stages (same values; k_mat.cu)
+    int rc = sipp_ctx_inner_product(c, &fwd[384 * k]);                       // let Z = inner_product(A, B);   :29
     k++;
     bool first = true;
     while (rc == SIPP_OK && n > 1) {                                          // :45
         uint8_t* zl = &fwd[384 * k];
         uint8_t* zr = &fwd[384 * (k + 1)];
-        if (!mt.n) {
-            const size_t nr = mat_stage(n);                                   // a pairing-matrix stage starts here?
-            if (nr) rc = mat_build(c, mt, nr);
-            if (rc) break;
-        }
-        rc = mt.n ? mat_products(mt, zl, zr) : sipp_ctx_cross_products(c, zl, zr);  // :46-49
+        rc = sipp_ctx_cross_products(c, zl, zr);                              // :46-49
         if (rc) break;
         if (first) {
             g_stats.transcript_ms += job.join();                              // :36-39 finished? (exposed wait only)
@@ -869,11 +886,7 @@ int prove_core(sipp_ctx* c, AbsorbJob& job, uint8_t* proof) {
         rc = sipp_fr_inverse(x, xinv);                                        // :58
         g_stats.transcript_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         if (rc) break;
-        if (mt.n) {
-            rc = mat_fold(c, mt, x, xinv);                                    // :60-74 on the matrix
-        } else {
-            rc = sipp_ctx_fold(c, x, xinv);                                   // :60-74
-        }
+        rc = sipp_ctx_fold(c, x, xinv);                                       // :60-74
         n = c->n;
     }
     if (rc) return rc;

@@ -247,6 +247,44 @@ def test_round_api_matches_reference_structure(sipp, oracle, golden):
     assert foldedA.hex() == c["foldedA"] and foldedB.hex() == c["foldedB"]
 
 
+def test_round_api_with_stages(sipp, oracle, golden):
+    """the same host loop with sipp_ctx_set_stages on: a host that keeps its own transcript gets the pairing-matrix stages too
+    (first stage from the inputs, look-ahead stages, tail) -- every Z, Z_L, Z_R and challenge as on the point-fold route; the
+    folded points stay readable during look-ahead stages and are refused once the tail has begun"""
+    for n, seed in ((16, None), (128, 1), (1024, 12)):
+        if seed is None:
+            c = [x for x in golden["prove"] if x["name"] == "seed11_n16"][0]
+            A, B, want = H(c["A"]), H(c["B"]), bytes.fromhex(c["proof"])
+        else:
+            A, B = oracle.seeded_inputs(seed, n, threads=4)
+            want = oracle.sipp_prove(A, B, threads=8)
+        ctx = sipp.ProverContext(A, B)
+        ctx.set_stages(True)
+        tr = sipp.Transcript()
+        proof = [ctx.inner_product()]
+        for i in range(n):
+            tr.append_g1(A[64 * i:64 * i + 64]); tr.append_g2(B[128 * i:128 * i + 128])
+        tr.append_fq12(proof[0])
+        m, refused = n, False
+        while m > 1:
+            zl, zr = ctx.cross_products()
+            proof += [zl, zr]
+            tr.append_fq12(zl); tr.append_fq12(zr)
+            x = tr.get_challenge()
+            ctx.fold(x, sipp.fr_inverse(x))
+            m //= 2
+            assert len(ctx) == m
+            try:
+                a, b = ctx.read()
+                assert not refused and len(a) == 64 * m
+            except sipp.SippError:
+                refused = True
+        assert refused                                   # the tail stage ran
+        proof.reverse()
+        assert b"".join(proof) == want, n
+        ctx.close()
+
+
 def test_sipp_native_n64(sipp, oracle):
     """mirror of the reference's own test_sipp_native (verifier_native.rs:96-106) + bit-exactness vs the oracle"""
     A, B = oracle.seeded_inputs(64, 64, threads=4)
