@@ -549,7 +549,9 @@ def main():
         ach = s2["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / (s2["miller_ms"] * 1e-3)
         sat = {"pairs": int(s2["miller_pairs"]), "miller_ms": s2["miller_ms"], "miller_loops_per_s": s2["miller_pairs"] / (s2["miller_ms"] * 1e-3),
                "kernels": "k_lines + k_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": ach / imad_peak,
-               "algorithmic_input_bytes": m * 192, "traffic": NCU_TRAFFIC.get("saturated")}
+               "algorithmic_input_bytes": m * 192,
+               "traffic": {k: v.get("dram_bytes_per_launch") for k, v in ((NCU_TRAFFIC.get("saturated") or {}).get("kernels") or {}).items()} or None,
+               "line_table_bytes": m * 29120}
 
     # ---- the other BASELINE configurations beside the headline (every rank takes part) ----
     large = []
@@ -581,18 +583,34 @@ def main():
         assert b"".join(proof_res) == b"".join(sipp_b200.sipp_prove_native(A, B)), "sharded proof differs from the single-GPU proof"
     value = n * K / t_res
     e2e = n * K / t_e2e
+    # Units of the Miller kernels: Miller loops their launches compute (pairs e(A_i, B_j) evaluated), each counted at the textbook
+    # 9,008 Fq-mul.  The pairing-matrix stages (SIPP_OPT_MATRIX_*) compute MORE loops than the reference's 3n - 2 --
+    # block products of every pair of blocks, so that rounds become matrix folds -- and compute them cheaper (line coefficients of
+    # a B point shared by all its partners, squarings shared by the pairs of a group); both ratios are reported.
+    loops_step = st["miller_pairs"] / K
     mill_ach = st["miller_pairs"] * FQMUL_PER_MILLER * IMAD_PER_FQMUL / max(st["miller_ms"] * 1e-3, 1e-12)
-    roofline = {"bound": "imad", "kernel": "k_lines / k_lines_wide + k_accum / k_accum_eng (line functions of every pair + accumulation "
-                                           "into the Miller product, rank 0's launches of the timed proves)",
+    useful_ach = miller_loops_per_prove(n) * K * FQMUL_PER_MILLER * IMAD_PER_FQMUL / max(st["miller_ms"] * 1e-3, 1e-12)
+    tr_head = (NCU_TRAFFIC.get("headline") or {}).get("kernels", {})
+    dom = tr_head.get("k_accum") or {}
+    roofline = {"bound": "imad", "kernel": "Miller-loop kernels of rank 0 in the timed proves: first stage k_qlines_batch + k_eval_lines_mat + k_accum "
+                                           "(2^17 loops: the 32 x 32 block matrix of the inputs), later stages k_lines_wide + k_accum_eng",
                 "achieved": mill_ach / 1e12,
-                "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak, "traffic": NCU_TRAFFIC.get("headline"),
+                "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": mill_ach / imad_peak,
+                "units": "Miller loops computed by the launches x 9,008 Fq-mul x 264 IMAD (algorithmic count per loop)",
+                "miller_loops_computed_per_step": loops_step, "miller_loops_of_the_reference_per_step": miller_loops_per_prove(n),
+                "frac_reference_loops_only": useful_ach / imad_peak,
+                "traffic": dom.get("largest_launch_dram_bytes"),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the largest k_accum launch (ncu --set full, profiles/ncu_traffic.json): "
+                                "it reads the line table once (29,120 B per loop); algorithmic input is 192 B per pair",
                 "algorithmic_input_bytes_per_pair": 192, "line_table_bytes_per_pair": 29120,
                 "launches": int(st["miller_launches"]), "avg_launch_ms": st["miller_ms"] / max(1, st["miller_launches"]),
                 "peak_source": "measured in this run (sipp_microbench: max of IMAD, 2 x IMAD.WIDE, lo/hi carry chain, all in "
                                "32x32 product halves/s); MEASURED_PEAKS.json has no integer peak",
                 "kernel_time_share": {"miller_ms": st["miller_ms"] / K, "reduce_final_exp_ms": st["reduce_fe_ms"] / K, "fold_ms": st["fold_ms"] / K,
                                       "other_ms": st["other_ms"] / K, "host_transcript_exposed_ms": st["transcript_ms"] / K,
-                                      "step_ms": t_res / K * 1e3},
+                                      "step_ms": t_res / K * 1e3,
+                                      "note": "the first stage's kernels (~20 ms at n = 2^12) and the look-ahead folds run under the host's absorb chain "
+                                              "or on a side stream: the classes overlap and do not add up to the step"},
                 "fold_hbm_gbs": (st["fold_points"] * 576 / max(st["fold_ms"] * 1e-3, 1e-12)) / 1e9,
                 "saturated": sat, "microbench": peaks}
     line = {"metric": "SIPP native prove throughput (pairings aggregated per second)", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -602,6 +620,8 @@ def main():
                                    "NCCL all-gather of the partial products inside the library" % log2(n // world)),
                        "n": n, "seed": 2, "miller_loops_per_step": miller_loops_per_prove(n), "l2": "flushed between steps (256 MB write)",
                        "fe_normalisation": "exact", "fq12_transcript_order": "w-basis", "parity": parity,
+                       "pairing_matrix_stages": {"tail": lib.sipp_get_option(_lib.OPT_MATRIX_TAIL), "block_n": lib.sipp_get_option(_lib.OPT_MATRIX_BLOCK_N),
+                                                 "block_r": lib.sipp_get_option(_lib.OPT_MATRIX_BLOCK_R), "first": lib.sipp_get_option(_lib.OPT_MATRIX_FIRST)},
                        "nccl_version": lib.sipp_comm_nccl_version() if world > 1 else None},
             "prove_s": t_res / K, "miller_loops_per_s_per_gpu": miller_loops_per_prove(n) * K / t_res / world,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / K * 1e3,

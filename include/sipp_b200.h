@@ -266,7 +266,8 @@ int sipp_seeded_inputs(uint64_t seed, size_t n, uint8_t *A, uint8_t *B);
 
 typedef struct {
     uint64_t launches;          /* kernels launched since the last reset */
-    uint64_t miller_pairs;      /* pairs pushed through the Miller-loop kernel */
+    uint64_t miller_pairs;      /* Miller loops the kernels computed: pairs pushed through the line + accumulation kernels (a pairing-matrix
+                                   stage computes more of them than the reference's 3n - 2, see SIPP_OPT_MATRIX_*) */
     uint64_t miller_launches;
     double miller_ms;           /* CUDA-event time of the Miller-loop kernels (SIPP_OPT_PROFILE = 1) */
     double reduce_fe_ms;        /* product reduction + final exponentiation */

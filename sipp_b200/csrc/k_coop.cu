@@ -34,11 +34,11 @@ __device__ __forceinline__ void lines_of_pair(const G1A& p, const G2A& q, uint32
         Fq2 one = fq2_one(), zero = fq2_zero();
         for (int s = 0; s < SIPP_LINES_PER_PAIR; s++) {
             uint32_t* o = out + s * SIPP_LINE_WORDS;
-            store_fq2_words(o, one);
-            store_fq2_words(o + 16, zero);
-            store_fq2_words(o + 32, zero);
-            store_fq2_words(o + 48, zero);
-            store_fq2_words(o + 64, zero);
+            stream_fq2_words(o, one);
+            stream_fq2_words(o + 16, zero);
+            stream_fq2_words(o + 32, zero);
+            stream_fq2_words(o + 48, zero);
+            stream_fq2_words(o + 64, zero);
         }
         return;
     }
@@ -46,11 +46,11 @@ __device__ __forceinline__ void lines_of_pair(const G1A& p, const G2A& q, uint32
         p, q, [](int) {},
         [&](int s, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
             uint32_t* o = out + s * SIPP_LINE_WORDS;
-            store_fq2_words(o, l0);
-            store_fq2_words(o + 16, l1);
-            store_fq2_words(o + 32, fq2_mul_xi(l1));
-            store_fq2_words(o + 48, l3);
-            store_fq2_words(o + 64, fq2_mul_xi(l3));
+            stream_fq2_words(o, l0);
+            stream_fq2_words(o + 16, l1);
+            stream_fq2_words(o + 32, fq2_mul_xi(l1));
+            stream_fq2_words(o + 48, l3);
+            stream_fq2_words(o + 64, fq2_mul_xi(l3));
         });
 }
 #ifndef SIPP_LINES_MINBLOCKS
@@ -118,20 +118,20 @@ __global__ void __launch_bounds__(128) k_eval_lines_batch(const uint32_t* __rest
     // identity test of Q on its first 64 bytes is not enough (x = 0 alone is a valid coordinate): read both halves
     const G2A q = load_g2(B, ib);
     if (affine_is_identity(p) || affine_is_identity(q)) {
-        store_fq2_words(o, fq2_one());
-        store_fq2_words(o + 16, fq2_zero());
-        store_fq2_words(o + 32, fq2_zero());
-        store_fq2_words(o + 48, fq2_zero());
-        store_fq2_words(o + 64, fq2_zero());
+        stream_fq2_words(o, fq2_one());
+        stream_fq2_words(o + 16, fq2_zero());
+        stream_fq2_words(o + 32, fq2_zero());
+        stream_fq2_words(o + 48, fq2_zero());
+        stream_fq2_words(o + 64, fq2_zero());
         return;
     }
     const uint32_t* src = qlines + (ib * SIPP_LINES_PER_PAIR + step) * SIPP_QLINE_WORDS;
     const Fq2 l0 = fq2_scale(load_fq2_words(src), p.y), l1 = fq2_scale(load_fq2_words(src + 16), p.x), l3 = load_fq2_words(src + 32);
-    store_fq2_words(o, l0);
-    store_fq2_words(o + 16, l1);
-    store_fq2_words(o + 32, fq2_mul_xi(l1));
-    store_fq2_words(o + 48, l3);
-    store_fq2_words(o + 64, fq2_mul_xi(l3));
+    stream_fq2_words(o, l0);
+    stream_fq2_words(o + 16, l1);
+    stream_fq2_words(o + 32, fq2_mul_xi(l1));
+    stream_fq2_words(o + 48, l3);
+    stream_fq2_words(o + 64, fq2_mul_xi(l3));
 }
 
 // pairing-matrix stages (k_mat.cu) with many pairs per entry: entry (i, j) of an nr x nr matrix pairs A[i m + t] with B[j m + t],
@@ -149,20 +149,20 @@ __global__ void __launch_bounds__(128) k_eval_lines_mat(const uint32_t* __restri
     uint32_t* o = lines + t * SIPP_LINE_WORDS;
     const G2A q = load_g2(B, ib);
     if (affine_is_identity(p) || affine_is_identity(q)) {
-        store_fq2_words(o, fq2_one());
-        store_fq2_words(o + 16, fq2_zero());
-        store_fq2_words(o + 32, fq2_zero());
-        store_fq2_words(o + 48, fq2_zero());
-        store_fq2_words(o + 64, fq2_zero());
+        stream_fq2_words(o, fq2_one());
+        stream_fq2_words(o + 16, fq2_zero());
+        stream_fq2_words(o + 32, fq2_zero());
+        stream_fq2_words(o + 48, fq2_zero());
+        stream_fq2_words(o + 64, fq2_zero());
         return;
     }
     const uint32_t* src = qlines + (ib * SIPP_LINES_PER_PAIR + step) * SIPP_QLINE_WORDS;
     const Fq2 l0 = fq2_scale(load_fq2_words(src), p.y), l1 = fq2_scale(load_fq2_words(src + 16), p.x), l3 = load_fq2_words(src + 32);
-    store_fq2_words(o, l0);
-    store_fq2_words(o + 16, l1);
-    store_fq2_words(o + 32, fq2_mul_xi(l1));
-    store_fq2_words(o + 48, l3);
-    store_fq2_words(o + 64, fq2_mul_xi(l3));
+    stream_fq2_words(o, l0);
+    stream_fq2_words(o + 16, l1);
+    stream_fq2_words(o + 32, fq2_mul_xi(l1));
+    stream_fq2_words(o + 48, l3);
+    stream_fq2_words(o + 64, fq2_mul_xi(l3));
 }
 
 // ------------------------------------------------------------------------------------------------ A: accumulation

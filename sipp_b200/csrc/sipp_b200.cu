@@ -395,6 +395,7 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
         }
         g_stats.launches += 4;
         g_stats.miller_launches++;
+        g_stats.miller_pairs += pairs;  // Miller loops these launches compute
     }
     // the staging blocks are only reused by later work on the same stream
     pool_free(aexp);
@@ -419,7 +420,6 @@ int mat_diag_product(MatTail& mt, uint8_t* z) {
         if (le) return cuda_fail((cudaError_t)le, "matrix diagonal");
     }
     g_stats.launches += 2;
-    g_stats.miller_pairs += mt.n * mt.m;
     CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, 384, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     memcpy(z, g_scr.h_out, 384);
@@ -436,7 +436,6 @@ int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr) {
         if (le) return cuda_fail((cudaError_t)le, "matrix products");
     }
     g_stats.launches += 2;
-    g_stats.miller_pairs += 2 * h * mt.m;  // the pairs these two products stand for
     CK(cudaMemcpyAsync(g_scr.h_out, g_scr.out, 2 * 384, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     memcpy(zl, g_scr.h_out, 384);
