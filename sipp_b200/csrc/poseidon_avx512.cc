@@ -17,8 +17,8 @@
 //                  the dependent chain of a round is the S-box, one multiply-add and one reduction.
 // Measured on the GPU box's Xeon (3.79 GHz, tools/probe/run_poseidon_lab.sh): 1.506 -> 1.385 (dot order) -> 1.223 (register MDS)
 // -> 1.18 -> 1.153 (reduction on the carry flag) -> 1.116 (192-bit accumulators pinned in registers by asm blocks) -> 1.065 (the
-// scalar 128 -> 64-bit reduction as one 11-instruction asm block: latency 12.2 -> 10.3 cycles) -> 1.027 us per permutation
-// (column-form MDS, port-balanced vector product).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
+// scalar 128 -> 64-bit reduction as one 11-instruction asm block: latency 12.2 -> 10.3 cycles) -> 1.027 (column-form MDS,
+// port-balanced vector product) -> 1.012 us per permutation (a partial round as three hand-allocated asm blocks).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
 // 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
 #include <immintrin.h>
 #include <stdint.h>
@@ -239,6 +239,80 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));              // lanes 4..7 of s1 are don't-care
 }
 
+// ------------------------------------------------------------------------------------------------ partial rounds, hand-allocated
+// One partial round as three asm blocks with every value pinned in a register.  Written with intrinsics the loop body was 285
+// instructions of which ~80 were register moves and spills (GCC ran out of registers around the 192-bit accumulators) at ~3.1
+// instructions per cycle: 92 cycles per round for a 51-cycle dependent chain.  Everything a round reads besides the state sits in
+// one 256-byte record (PoseidonFastTables::pr), addressed off a single pointer.
+//   pr_dot:   acc = sum_i vhat[i] U[i] (two chains) + x_prev kprev + m00 post        (off the chain: U is the state of round r - 1)
+//   pr_sbox:  p7 = u0^7 (three dependent products, 10-instruction reductions), x = p7 + post
+//   pr_finish: u0' = (acc + p7 m00) mod p
+SIPP_AVX512 inline void pr_dot(const PartialRound* p, const uint64_t* ub, uint64_t xp, unsigned long long& lo, unsigned long long& hi, unsigned long long& top) {
+    unsigned long long lo0, hi0, t0, lo1, hi1, t1, pl, ph;
+    asm("mov 0(%[ub]), %%rdx\n\t" "mulx 128(%[p]), %[lo0], %[hi0]\n\t"
+        "mov 8(%[ub]), %%rdx\n\t" "mulx 136(%[p]), %[lo1], %[hi1]\n\t"
+        "xor %k[t0], %k[t0]\n\t" "xor %k[t1], %k[t1]\n\t"
+        "mov 16(%[ub]), %%rdx\n\t" "mulx 144(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo0]\n\t" "adc %[ph], %[hi0]\n\t" "adc $0, %[t0]\n\t"
+        "mov 24(%[ub]), %%rdx\n\t" "mulx 152(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo1]\n\t" "adc %[ph], %[hi1]\n\t" "adc $0, %[t1]\n\t"
+        "mov 32(%[ub]), %%rdx\n\t" "mulx 160(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo0]\n\t" "adc %[ph], %[hi0]\n\t" "adc $0, %[t0]\n\t"
+        "mov 40(%[ub]), %%rdx\n\t" "mulx 168(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo1]\n\t" "adc %[ph], %[hi1]\n\t" "adc $0, %[t1]\n\t"
+        "mov 48(%[ub]), %%rdx\n\t" "mulx 176(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo0]\n\t" "adc %[ph], %[hi0]\n\t" "adc $0, %[t0]\n\t"
+        "mov 56(%[ub]), %%rdx\n\t" "mulx 184(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo1]\n\t" "adc %[ph], %[hi1]\n\t" "adc $0, %[t1]\n\t"
+        "mov 64(%[ub]), %%rdx\n\t" "mulx 192(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo0]\n\t" "adc %[ph], %[hi0]\n\t" "adc $0, %[t0]\n\t"
+        "mov 72(%[ub]), %%rdx\n\t" "mulx 200(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo1]\n\t" "adc %[ph], %[hi1]\n\t" "adc $0, %[t1]\n\t"
+        "mov 80(%[ub]), %%rdx\n\t" "mulx 208(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo0]\n\t" "adc %[ph], %[hi0]\n\t" "adc $0, %[t0]\n\t"
+        "mov %[xp], %%rdx\n\t" "mulx 216(%[p]), %[pl], %[ph]\n\t" "add %[pl], %[lo1]\n\t" "adc %[ph], %[hi1]\n\t" "adc $0, %[t1]\n\t"
+        "add 224(%[p]), %[lo1]\n\t" "adc $0, %[hi1]\n\t" "adc $0, %[t1]\n\t"
+        "add %[lo1], %[lo0]\n\t" "adc %[hi1], %[hi0]\n\t" "adc %[t1], %[t0]"
+        : [lo0] "=&r"(lo0), [hi0] "=&r"(hi0), [t0] "=&r"(t0), [lo1] "=&r"(lo1), [hi1] "=&r"(hi1), [t1] "=&r"(t1), [pl] "=&r"(pl), [ph] "=&r"(ph)
+        : [p] "r"(p), [ub] "r"(ub), [xp] "r"(xp)
+        : "rdx", "cc", "memory");
+    lo = lo0; hi = hi0; top = t0;
+}
+SIPP_AVX512 inline void pr_sbox(const PartialRound* p, uint64_t u, uint64_t& p7, uint64_t& x) {
+    unsigned long long a, b, h, t;
+    const uint64_t eps = EPS;
+    asm("mov %[u], %%rdx\n\t" "mulx %[u], %[a], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[a]\n\t" "jc 11f\n" "10:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]\n\t"
+        "mulx %[a], %[b], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[b]\n\t" "jc 13f\n" "12:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[b]\n\t" "lea (%[b],%[eps]), %[t]\n\t" "cmovc %[t], %[b]\n\t"
+        "mov %[a], %%rdx\n\t" "mulx %[a], %[a], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[a]\n\t" "jc 15f\n" "14:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]\n\t"
+        "mov %[b], %%rdx\n\t" "mulx %[a], %[a], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[a]\n\t" "jc 17f\n" "16:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]\n\t"
+        "mov %[a], %[b]\n\t" "add 232(%[p]), %[b]\n\t" "lea (%[b],%[eps]), %[t]\n\t" "cmovc %[t], %[b]\n\t"
+        ".subsection 1\n"
+        "11:\n\t" "sub %[eps], %[a]\n\t" "jmp 10b\n"
+        "13:\n\t" "sub %[eps], %[b]\n\t" "jmp 12b\n"
+        "15:\n\t" "sub %[eps], %[a]\n\t" "jmp 14b\n"
+        "17:\n\t" "sub %[eps], %[a]\n\t" "jmp 16b\n"
+        ".previous"
+        : [a] "=&r"(a), [b] "=&r"(b), [h] "=&r"(h), [t] "=&r"(t)
+        : [u] "r"(u), [p] "r"(p), [eps] "r"(eps)
+        : "rdx", "cc", "memory");
+    p7 = a; x = b;
+}
+SIPP_AVX512 inline uint64_t pr_finish(unsigned long long lo, unsigned long long hi, unsigned long long top, uint64_t p7, uint64_t m00) {
+    unsigned long long pl, ph;
+    const uint64_t eps = EPS;
+    asm("mov %[p7], %%rdx\n\t" "mulx %[m00], %[pl], %[ph]\n\t" "add %[pl], %[lo]\n\t" "adc %[ph], %[hi]\n\t" "adc $0, %[top]\n\t"
+        "mov %[hi], %[pl]\n\t" "shr $32, %[pl]\n\t" "mov %k[hi], %k[hi]\n\t" "sub %[pl], %[lo]\n\t" "jc 21f\n" "20:\n\t"
+        "mov %[hi], %[pl]\n\t" "shl $32, %[pl]\n\t" "sub %[hi], %[pl]\n\t" "add %[pl], %[lo]\n\t" "lea (%[lo],%[eps]), %[pl]\n\t" "cmovc %[pl], %[lo]\n\t"
+        "shl $32, %[top]\n\t" "sub %[top], %[lo]\n\t" "jc 23f\n" "22:\n\t"
+        ".subsection 1\n"
+        "21:\n\t" "sub %[eps], %[lo]\n\t" "jmp 20b\n"
+        "23:\n\t" "sub %[eps], %[lo]\n\t" "jmp 22b\n"
+        ".previous"
+        : [lo] "+r"(lo), [hi] "+r"(hi), [top] "+r"(top), [pl] "=&r"(pl), [ph] "=&r"(ph)
+        : [p7] "r"(p7), [m00] "r"(m00), [eps] "r"(eps)
+        : "rdx", "cc");
+    return lo;
+}
+
 SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonFastTables& T) {
     s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
     s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
@@ -271,23 +345,25 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
     // round is the S-box plus two multiply-adds.  Two buffers alternate: round r reads U_{r-1}, writes U_{r+1}.
     alignas(64) uint64_t um[2][16];
     memcpy(um[0], ub, sizeof ub);
+    memcpy(um[1], ub, sizeof ub);  // round 0 reads "U_{-1}" = U_0 (its correction term has x_prev = 0)
     __m512i v0 = _mm512_load_si512(ub), v1 = _mm512_load_si512(ub + 8);
     uint64_t x_prev = 0;
+    const uint64_t m00 = T.m00;
+#pragma GCC unroll 2
     for (int r = 0; r < 22; r++) {
-        Acc192 acc = s_dot11_raw(T.vhat[r], um[r == 0 ? 0 : (r + 1) & 1] + 1);
-        acc_mul(acc, x_prev, T.kprev[r]);
-        acc_add(acc, T.mpost[r]);  // + m00 post[r] (constant), off the chain
-        const uint64_t p7 = s_pow7(u0);
-        uint64_t x = s_add(p7, T.post[r]);
-        acc_mul(acc, p7, T.m00);
-        uint64_t d = acc_reduce(acc);
+        const PartialRound* p = &T.pr[r];
+        uint64_t* cur = um[(r + 1) & 1];  // holds U_{r-1}; receives U_{r+1} at the end of the round
+        unsigned long long lo, hi, top;
+        pr_dot(p, cur + 1, x_prev, lo, hi, top);
+        uint64_t p7, x;
+        pr_sbox(p, u0, p7, x);
+        u0 = pr_finish(lo, hi, top, p7, m00);
         __m512i xb = _mm512_set1_epi64((long long)x);
-        v0 = v_add_canon(v0, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r]))));
-        v1 = v_add_canon(v1, v_canon(v_mul(xb, _mm512_load_si512(T.w16[r] + 8))));
-        _mm512_store_si512(um[(r + 1) & 1], v0);
-        _mm512_store_si512(um[(r + 1) & 1] + 8, v1);
+        v0 = v_add_canon(v0, v_canon(v_mul(xb, _mm512_load_si512(p->w16))));
+        v1 = v_add_canon(v1, v_canon(v_mul(xb, _mm512_load_si512(p->w16 + 8))));
+        _mm512_store_si512(cur, v0);
+        _mm512_store_si512(cur + 8, v1);
         x_prev = x;
-        u0 = d;
     }
     _mm512_store_si512(ub, v0);
     _mm512_store_si512(ub + 8, v1);

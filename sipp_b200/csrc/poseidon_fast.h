@@ -4,6 +4,18 @@
 
 namespace sipp {
 
+// everything one sparse partial round reads besides the state, in one record addressed off a single pointer (the asm blocks of
+// poseidon_avx512.cc use these byte offsets: w16 0, vhat 128, kprev 216, mpost 224, post 232)
+struct alignas(64) PartialRound {
+    uint64_t w16[16];    // w16[i] = w_r[i - 1] for i = 1..11, 0 elsewhere
+    uint64_t vhat[11];
+    uint64_t kprev;      // vhat[r] . w[r-1] (0 for r = 0)
+    uint64_t mpost;      // m00 post[r]
+    uint64_t post;
+    uint64_t pad[2];
+};
+static_assert(sizeof(PartialRound) == 256, "PartialRound layout");
+
 // Sparse-form partial rounds (derivation in transcript.cc) plus vector-friendly copies of the round constants.
 struct PoseidonFastTables {
     alignas(64) uint64_t rc_full[8][16];   // round constants of the 4 + 4 full rounds, lanes 12..15 = 0
@@ -17,6 +29,7 @@ struct PoseidonFastTables {
     uint64_t init[11][11];
     uint64_t vhat[22][11];
     uint64_t m00;
+    PartialRound pr[22];
 };
 
 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T);

@@ -209,6 +209,15 @@ struct FastPartialInit {
                 g_tab.mds_col_b[j][r] = (double)MDS_CIRC[(j - 8 - (r & 3) + 24) % 12];
             }
         g_tab.m00 = g_fp.m00;
+        for (int r = 0; r < 22; r++) {
+            sipp::PartialRound& pr = g_tab.pr[r];
+            memset(&pr, 0, sizeof pr);
+            for (int i = 0; i < 16; i++) pr.w16[i] = g_tab.w16[r][i];
+            for (int i = 0; i < 11; i++) pr.vhat[i] = g_tab.vhat[r][i];
+            pr.kprev = g_tab.kprev[r];
+            pr.mpost = g_tab.mpost[r];
+            pr.post = g_tab.post[r];
+        }
         const char* force = getenv("SIPP_POSEIDON");  // "portable" forces the scalar path (tests compare both)
         g_use_avx512 = sipp::poseidon_avx512_supported() && !(force && !strcmp(force, "portable"));
     }
