@@ -645,6 +645,17 @@ def main():
                                           "%.1f s; GPU proof of the same sample is byte-identical" % (sample_n, n, dt),
                                 "all_cores_fast_variant": {"value": sample_n / dt_fast, "cores": os.cpu_count() or 1,
                                                            "note": "product of Miller loops + one final exponentiation, pthreads"}}
+    if world == 1 and not args.quick:
+        # the verifier of the same statement (verifier_native.rs:14-85: transcript replay, folds, GT updates, final pairing) through
+        # the public call with host buffers
+        sipp_b200.sipp_verify_native(A, B, proof_res)
+        tv = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sipp_b200.sipp_verify_native(A, B, proof_res)
+            tv.append(time.perf_counter() - t0)
+        line["verify"] = {"ms": min(tv) * 1e3, "unit": "ms per sipp_verify_native of the timed proof (host buffers, best of 3)",
+                          "pairs_per_s": n / min(tv)}
     if args.quick:
         line["e2e"] = None
         line["config"]["quick"] = "one warm-up step, e2e leg skipped (--quick)"

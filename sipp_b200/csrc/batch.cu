@@ -132,6 +132,19 @@ int batch_sub_count(size_t n, size_t count) {
 // the whole batch on the device; bytesA / bytesB already hold the boundary bytes.  Enqueues everything; the caller synchronises.
 cudaStream_t g_side = nullptr;  // transcript absorb chains of a large batch, next to the first products
 int g_side_dev = -1;
+}  // namespace
+namespace sipp_host {
+// sipp_shutdown / a device switch: the per-device streams of the batched prover
+void batch_release_streams() {
+    if (g_side_dev >= 0 && g_side) cudaStreamDestroy(g_side);
+    g_side = nullptr;
+    g_side_dev = -1;
+    if (g_sub_streams_dev >= 0)
+        for (int k = 0; k < 8; k++) cudaStreamDestroy(g_sub_streams[k]);
+    g_sub_streams_dev = -1;
+}
+}  // namespace sipp_host
+namespace {
 
 int batch_prove_enqueue(BatchBuffers& b, size_t n, size_t count, cudaStream_t s, bool* side_used, int* subs_used);
 int batch_prove_resident(BatchBuffers& b, size_t n, size_t count, cudaStream_t s) {

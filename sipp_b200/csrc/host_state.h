@@ -55,6 +55,7 @@ int cuda_fail(cudaError_t e, const char* what);   // same for a CUDA error, retu
 int ensure_init();
 bool is_pow2(size_t n);
 
+void batch_release_streams();   // batch.cu
 // context with uninitialised device arrays for n points (pool blocks)
 int ctx_alloc(size_t n, sipp_ctx** out);
 // true when all `n_fq` little-endian 32-byte integers are < p (the canonical encoding ark-serialize requires: a proof element with a

@@ -325,6 +325,8 @@ namespace sipp_host {
 //          side stream, off the critical path, and the next stage starts from them.
 // Every Z_L, Z_R is the same field element as on the point-fold route, bit for bit.
 cudaStream_t g_fold_stream = nullptr;
+FoldPlan* g_fold_plan_dev = nullptr;  // device copy of the plan for k_fold_straus (released in sipp_shutdown)
+int g_live_ctx = 0;                   // contexts alive (a device switch is refused while any exists)
 
 size_t mat_stage(size_t n) {
     if (!g_opt_pipeline || !g_opt_fe_engine || n < 2) return 0;
@@ -479,12 +481,14 @@ int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[3
 
 int ctx_alloc(size_t n, sipp_ctx** out) {
     sipp_ctx* c = new sipp_ctx();
+    g_live_ctx++;
     c->n = c->cap = n;
     cudaError_t e = pool_alloc((void**)&c->dA, n * 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = pool_alloc((void**)&c->dB, n * 32 * sizeof(uint32_t));
     if (e != cudaSuccess) {
         pool_free(c->dA);
         delete c;
+        g_live_ctx--;
         return cuda_fail(e, "cudaMalloc(ctx)");
     }
     *out = c;
@@ -506,13 +510,14 @@ int sipp_init(int device) {
     int n = sipp_device_count();
     if (n <= 0) return fail(SIPP_ERR_CUDA, "no CUDA device: libsipp_b200 has no CPU fallback");
     if (device < 0 || device >= n) return fail(SIPP_ERR_ARG, "device index out of range");
-    CK(cudaSetDevice(device));
-    if (g_device != device) {
-        if (g_stream) cudaStreamDestroy(g_stream);
-        g_stream = nullptr;
-        g_scr = Scratch();
-        pool_release_all();
+    if (g_device >= 0 && g_device != device) {
+        // a device switch: everything the library holds belongs to the old device.  Live contexts would dangle (their points are
+        // pool blocks), so the switch is refused while any exists; otherwise the old device is shut down completely.
+        if (g_live_ctx > 0) return fail(SIPP_ERR_ARG, "sipp_init: contexts of the current device are still alive (destroy them before switching devices)");
+        CK(cudaSetDevice(g_device));
+        sipp_shutdown();
     }
+    CK(cudaSetDevice(device));
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -532,6 +537,9 @@ int sipp_shutdown(void) {
     if (g_scr.lines) cudaFree(g_scr.lines);
     g_scr = Scratch();
     pool_release_all();
+    batch_release_streams();
+    if (g_fold_plan_dev) cudaFree(g_fold_plan_dev);
+    g_fold_plan_dev = nullptr;
     if (g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
     if (g_fold_stream) cudaStreamDestroy(g_fold_stream);
@@ -660,6 +668,7 @@ int sipp_ctx_destroy(sipp_ctx* c) {
     pool_free(c->dA);
     pool_free(c->dB);
     delete c;
+    g_live_ctx--;
     return SIPP_OK;
 }
 
@@ -713,12 +722,8 @@ int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
         if (g_opt_fold_straus && h >= 16384) {
             // a launch that fills the GPU: one thread per element, doublings shared by the components (k_fold_straus reads the plan
             // from device memory: the batched prover has one per instance)
-            static FoldPlan* d_plan = nullptr;
-            static int d_plan_dev = -1;
-            if (d_plan_dev != g_device) {
-                CK(cudaMalloc(&d_plan, sizeof(FoldPlan)));
-                d_plan_dev = g_device;
-            }
+            if (!g_fold_plan_dev) CK(cudaMalloc(&g_fold_plan_dev, sizeof(FoldPlan)));
+            FoldPlan* d_plan = g_fold_plan_dev;
             CK(cudaMemcpyAsync(d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice, g_stream));  // pageable source: staged before the call returns
             e = launch_fold_straus(c->dA, c->dB, h, c->n, 1, d_plan, g_stream);
         } else {
