@@ -354,7 +354,7 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
     const size_t n = c->n, m = n / nr, P = nr * nr, pairs = P * m;
     // small launches: the lane engines (latency); large ones (a first stage): line coefficients of every B point once + the
     // throughput accumulation kernel
-    const bool big = pairs > (size_t)g_opt_wide_max;
+    const bool big = m > 1 && pairs > 8192;
     int kpg = 1;
     if (big) {
         const size_t by_block = (m + 19) / 20, by_fill = (pairs + 11839) / 11840;
@@ -386,7 +386,9 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
                 job.a_off[0] = job.b_off[0] = job.a_off[1] = job.b_off[1] = 0;
                 job.m = pairs;
                 le = launch_mat_gather(c->dA, c->dB, nr, m, aexp, bexp, g_stream);
-                if (!le) le = launch_lines_wide(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream);
+                if (!le)
+                    le = pairs <= (size_t)g_opt_wide_max ? launch_lines_wide(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream)
+                                                         : launch_lines(aexp, bexp, job, 1, 0, pairs, g_scr.lines, g_stream);
                 if (!le) le = m == 1 ? launch_accum_eng_each(g_scr.lines, P, mil, g_stream) : launch_accum_eng(g_scr.lines, m, (int)P, 1, g_scr.partials, 0, g_stream);
             }
         }
