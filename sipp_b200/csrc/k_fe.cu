@@ -268,6 +268,61 @@ int launch_gt_fold_eng(const uint32_t* in, const Scalar256& x, const Scalar256& 
     return (int)cudaGetLastError();
 }
 
+// k_gt_fold_rounds: ALL GT updates of one verification at once.  The verifier's challenges depend only on A, B and the proof
+// (verifier_native.rs:33-45), so once the transcript has been replayed every Z_L^x, Z_R^(1/x) of every round is an independent power:
+// final_Z = Z * prod_rounds Z_L^x_k Z_R^(1/x_k)  (:59-61 unrolled).  Block k < rounds: two machines as in k_gt_fold_eng, their product
+// left as a raw partial; block `rounds`: Z itself.  A reduction (k_reduce_fe_eng, product + encode) finishes.
+// elems: (2 rounds + 1) x 96 words boundary format in the verifier's read order  Z, Z_L(1), Z_R(1), Z_L(2), ...;
+// scalars: rounds x 16 words (x_k, then 1/x_k); partials: (rounds + 1) x 96 words.
+__global__ void __launch_bounds__(64) k_gt_fold_rounds(const uint32_t* __restrict__ elems, const uint32_t* __restrict__ scalars, int rounds,
+                                                      uint32_t* __restrict__ partials) {
+    __shared__ __align__(16) uint32_t smem[2 * SIPP_GTF_SLOTS * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x;
+    uint32_t* slots = smem + warp * (SIPP_GTF_SLOTS * 8);
+    for (int j = lane; j < 37; j += 32) f12_fill_global(slots, j);
+    auto load12 = [&](int reg, const uint32_t* src) {
+        if (lane < 6) {
+            const Fq2 g = fq2_decode(src + 16 * ((lane & 1) * 3 + (lane >> 1)));
+            lp_store(slots, f12_reg_base(reg) + 2 * lane, g.c0);
+            lp_store(slots, f12_reg_base(reg) + 2 * lane + 1, g.c1);
+        }
+        __syncwarp();
+    };
+    uint32_t* o = partials + (size_t)k * 96;
+    if (k == rounds) {  // the factor Z
+        if (warp == 0) {
+            load12(0, elems);
+            for (int w = lane; w < 96; w += 32) o[w] = slots[f12_reg_base(0) * 8 + w];
+        }
+        return;
+    }
+    DevMachine12 mc;
+    mc.slots = slots;
+    mc.lane = lane;
+    load12(1, elems + (size_t)(1 + 2 * k + warp) * 96);
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = scalars[(size_t)k * 16 + warp * 8 + i];
+    const bool started = f12_pow_w2(mc, e);
+    if (!started) {
+        if (lane < 12) lp_store(slots, f12_reg_base(0) + lane, lane == 0 ? fq_one() : fq_zero());
+        __syncwarp();
+        F12_OP2(mc, XI6, 0, 0);
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const uint32_t* other = smem + SIPP_GTF_SLOTS * 8 + f12_reg_base(0) * 8;
+    for (int w = lane; w < SIPP_F12_REG_SLOTS * 8; w += 32) slots[f12_reg_base(4) * 8 + w] = other[w];
+    __syncwarp();
+    F12_OP3(mc, MUL12Y, 0, 0, 4);
+    for (int w = lane; w < 96; w += 32) o[w] = slots[f12_reg_base(0) * 8 + w];
+}
+int launch_gt_fold_rounds(const uint32_t* elems, const uint32_t* scalars, int rounds, uint32_t* partials, cudaStream_t s) {
+    k_gt_fold_rounds<<<rounds + 1, 64, 0, s>>>(elems, scalars, rounds, partials);
+    return (int)cudaGetLastError();
+}
+
 int launch_reduce_fe_eng(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s) {
     k_reduce_fe_eng<<<nprod, SIPP_RFE_THREADS, 0, s>>>(partials, count, nprod, out, final_exp, ark_norm);
     return (int)cudaGetLastError();

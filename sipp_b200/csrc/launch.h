@@ -36,6 +36,7 @@ int launch_miller_block(const uint32_t* A, const uint32_t* B, const MillerJob& j
 int launch_reduce_fe(const uint32_t* partials, int count, int nprod, uint32_t* out, int final_exp, int ark_norm, cudaStream_t s);
 int launch_gt_fold(const uint32_t* in, const Scalar256& x, const Scalar256& xinv, uint32_t* out, cudaStream_t s);
 int launch_gt_fold_eng(const uint32_t* in, const Scalar256& x, const Scalar256& xinv, uint32_t* out, cudaStream_t s);
+int launch_gt_fold_rounds(const uint32_t* elems, const uint32_t* scalars, int rounds, uint32_t* partials, cudaStream_t s);
 int launch_fold(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s);
 int launch_fold_wide(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s);
 // on-curve + G2 subgroup check of decoded points: flags |= 2 (off the curve), |= 4 (outside the prime-order subgroup)

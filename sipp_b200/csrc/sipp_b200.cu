@@ -953,22 +953,60 @@ int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t 
     uint8_t Z[384];
     memcpy(Z, proof + 384 * --top, 384);                                      // let original_Z = proof.pop().unwrap();  :31
     sipp_transcript_append_fq12(&tr, Z);                                      // :33
-    while (n > 1) {                                                           // :35
+    // The challenges depend only on A, B and the proof (:33-45): replay the transcript first, then every fold is queued back to
+    // back and every GT update Z_L^x, Z_R^(1/x) (:59-61) is an independent power -- all of them in ONE launch on the side stream.
+    const size_t rounds = log2_exact(n);
+    std::vector<uint8_t> xs(rounds * 64), elems((2 * rounds + 1) * 384);
+    memcpy(elems.data(), Z, 384);
+    for (size_t k = 0; k < rounds && !rc; k++) {                              // :35
         const uint8_t* zl = proof + 384 * --top;                              // :40
         sipp_transcript_append_fq12(&tr, zl);
         const uint8_t* zr = proof + 384 * --top;                              // :42
         sipp_transcript_append_fq12(&tr, zr);
-        uint8_t x[32], xinv[32];
-        sipp_transcript_get_challenge(&tr, x);                                // :45
-        rc = sipp_fr_inverse(x, xinv);                                        // :46
-        if (rc) break;
-        rc = sipp_ctx_fold(c, x, xinv);                                       // :48-57
-        if (rc) break;
-        uint8_t nz[384];
-        rc = sipp_gt_fold(zl, Z, zr, x, xinv, nz);                            // :59-61
-        if (rc) break;
-        memcpy(Z, nz, 384);
-        n = c->n;
+        sipp_transcript_get_challenge(&tr, &xs[64 * k]);                      // :45
+        rc = sipp_fr_inverse(&xs[64 * k], &xs[64 * k + 32]);                  // :46
+        memcpy(&elems[384 * (1 + 2 * k)], zl, 384);
+        memcpy(&elems[384 * (2 + 2 * k)], zr, 384);
+    }
+    uint32_t *d_elems = nullptr, *d_xs = nullptr, *d_parts = nullptr, *d_z = nullptr;
+    const bool gt_batched = !rc && rounds > 0 && g_opt_fe_engine;
+    if (gt_batched) {
+        if (!g_fold_stream) CK(cudaStreamCreateWithFlags(&g_fold_stream, cudaStreamNonBlocking));
+        cudaError_t e = pool_alloc((void**)&d_elems, elems.size());
+        if (e == cudaSuccess) e = pool_alloc((void**)&d_xs, xs.size());
+        if (e == cudaSuccess) e = pool_alloc((void**)&d_parts, (rounds + 1) * 384);
+        if (e == cudaSuccess) e = pool_alloc((void**)&d_z, 384);
+        if (e == cudaSuccess) e = order_after(g_fold_stream, g_stream);      // pool blocks: earlier users ran on the library stream
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_elems, elems.data(), elems.size(), cudaMemcpyHostToDevice, g_fold_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_xs, xs.data(), xs.size(), cudaMemcpyHostToDevice, g_fold_stream);
+        int le = 0;
+        if (e == cudaSuccess) {
+            Span sp(3, g_fold_stream);
+            le = launch_gt_fold_rounds(d_elems, d_xs, (int)rounds, d_parts, g_fold_stream);
+            if (!le) le = launch_reduce_fe_eng(d_parts, (int)rounds + 1, 1, d_z, 2, g_opt_fe_norm, g_fold_stream);
+            g_stats.launches += 2;
+        }
+        if (e == cudaSuccess && !le) e = cudaMemcpyAsync(Z, d_z, 384, cudaMemcpyDeviceToHost, g_fold_stream);  // Z: pageable, synchronised below
+        if (e != cudaSuccess || le) {
+            cudaStreamSynchronize(g_fold_stream);
+            pool_free(d_elems); pool_free(d_xs); pool_free(d_parts); pool_free(d_z);
+            sipp_ctx_destroy(c);
+            return e != cudaSuccess ? cuda_fail(e, "verifier GT updates") : cuda_fail((cudaError_t)le, "k_gt_fold_rounds");
+        }
+    }
+    for (size_t k = 0; k < rounds && !rc; k++) {
+        rc = sipp_ctx_fold(c, &xs[64 * k], &xs[64 * k + 32]);                 // :48-57
+        if (!rc && !gt_batched) {
+            uint8_t nz[384];
+            rc = sipp_gt_fold(&elems[384 * (1 + 2 * k)], Z, &elems[384 * (2 + 2 * k)], &xs[64 * k], &xs[64 * k + 32], nz);  // :59-61
+            if (!rc) memcpy(Z, nz, 384);
+        }
+    }
+    n = c->n;
+    if (gt_batched) {
+        cudaError_t e = cudaStreamSynchronize(g_fold_stream);
+        pool_free(d_elems); pool_free(d_xs); pool_free(d_parts); pool_free(d_z);
+        if (e != cudaSuccess) { sipp_ctx_destroy(c); return cuda_fail(e, "verifier GT updates"); }
     }
     uint8_t fa[64], fb[128], e[384];
     if (!rc) rc = sipp_ctx_read(c, fa, fb);                                   // final_A: A[0], final_B: B[0]   :74-75
