@@ -58,7 +58,7 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
 #define SIPP_OPT_FE_ENGINE 6          /* 1 = final exponentiation on the 32-lane Fq12 machine (k_reduce_fe_eng) [default];
                                          0 = 6-lane cooperative version (k_reduce_fe_coop) */
 #define SIPP_OPT_WIDE_FOLD_MAX 7      /* folds of at most this many elements per group use the point programs on the lane
-                                         engine (k_fold_wide, latency-bound rounds; a batch uses k_fold_wide_batch up to this + 256 elements); 0 = never */
+                                         engine (k_fold_wide, latency-bound rounds; default 256; a batch uses k_fold_wide_batch up to this + 512 elements); 0 = never */
 #define SIPP_OPT_WIDE_ACCUM_MAX 8     /* launches of at most this many pairs accumulate the lines on the 32-lane Fq12 machine
                                          (k_accum_eng) instead of the 6-lane groups of k_accum; 0 = never */
 #define SIPP_OPT_BATCH_KPG_MAX 9      /* batched instances: at most this many pairs of one product share an accumulator group */

@@ -256,7 +256,7 @@ int batch_prove_enqueue(BatchBuffers& b, size_t n, size_t count, cudaStream_t s,
                 // dependent chain is 3x shorter when a warp spans several instances (divergent digit tests)
                 const size_t elems = c * (m / 2);
                 int e = (g_opt_fold_straus && elems >= 16384)          ? launch_fold_straus(v.dA, v.dB, m / 2, n, c, v.plans, sk)
-                        : elems <= (size_t)g_opt_wide_fold_max + 256   ? launch_fold_wide_batch(v.dA, v.dB, m / 2, n, c, v.plans, sk)  // lane engine: <= 2 waves
+                        : elems <= (size_t)g_opt_wide_fold_max + 512   ? launch_fold_wide_batch(v.dA, v.dB, m / 2, n, c, v.plans, sk)  // lane engine: <= 2 waves
                                                                        : launch_fold_batch(v.dA, v.dB, m / 2, n, c, v.plans, sk);      // :60-74
                 if (e) return cuda_fail((cudaError_t)e, "k_fold_batch");
                 g_stats.launches++;

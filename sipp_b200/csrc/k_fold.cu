@@ -6,6 +6,7 @@
 #include "coop.cuh"
 #include "device_common.cuh"
 #include "fold_plan.h"
+#include "fq2h.cuh"
 
 namespace sipp {
 
@@ -52,6 +53,83 @@ __device__ __forceinline__ Jac<Fq> load_jac1(const uint32_t* src) {
     return p;
 }
 
+// Jacobian point over Fq2H (fq2h.cuh): every lane of a pair moves its halves; same 48-word layout as a Jac<Fq2>
+__device__ __forceinline__ void store_jac_h(uint32_t* dst, const Jac<Fq2H>& p) {
+    const int o = h_odd() ? 8 : 0;
+    store_fq_words(dst + o, p.x.v); store_fq_words(dst + 16 + o, p.y.v); store_fq_words(dst + 32 + o, p.z.v);
+}
+__device__ __forceinline__ Jac<Fq2H> load_jac_h(const uint32_t* src) {
+    const int o = h_odd() ? 8 : 0;
+    Jac<Fq2H> p;
+    p.x.v = load_fq_words(src + o); p.y.v = load_fq_words(src + 16 + o); p.z.v = load_fq_words(src + 32 + o);
+    return p;
+}
+__device__ __forceinline__ Affine<Fq2H> split_g2(const G2A& q) { return Affine<Fq2H>{h_split(q.x), h_split(q.y)}; }
+
+// ---- G1 on a PAIR of lanes.  An Fq product cannot be split, but the products of a doubling / mixed addition are not all
+// dependent: both lanes hold the whole point, each computes one of two independent products per level and the results are
+// exchanged with 8 shuffles -- 7 products in 4 levels (doubling), 11 in 6 (mixed addition) instead of 7 / 11 in a row.  The 128
+// doublings of a GLV component were the longest chain of the lane-split fold once G2 ran on lane pairs.
+__device__ __forceinline__ void pair_mul(const Fq& a_even, const Fq& b_even, const Fq& a_odd, const Fq& b_odd, Fq& r_even, Fq& r_odd) {
+    const bool odd = h_odd();
+    const Fq mine = fq_mul_call(h_select(odd, a_odd, a_even), h_select(odd, b_odd, b_even));
+    const Fq other = h_partner(mine);
+    r_even = h_select(odd, other, mine);
+    r_odd = h_select(odd, mine, other);
+}
+__device__ __noinline__ Jac<Fq> jac_dbl_pair(const Jac<Fq>& p) {  // same formulas as jac_dbl (curve.cuh)
+    Fq A, B, C, S, Fv, YZ, M, unused;
+    pair_mul(p.x, p.x, p.y, p.y, A, B);
+    const Fq xb = fq_add(p.x, B);
+    pair_mul(B, B, xb, xb, C, S);
+    const Fq D = fq_dbl(fq_sub(fq_sub(S, A), C));
+    const Fq E = fq_add(fq_dbl(A), A);
+    pair_mul(E, E, p.y, p.z, Fv, YZ);
+    Jac<Fq> r;
+    r.x = fq_sub(Fv, fq_dbl(D));
+    const Fq dx = fq_sub(D, r.x);
+    pair_mul(E, dx, E, dx, M, unused);
+    r.y = fq_sub(M, fq_dbl(fq_dbl(fq_dbl(C))));
+    r.z = fq_dbl(YZ);
+    return r;
+}
+__device__ __noinline__ Jac<Fq> jac_add_affine_pair(const Jac<Fq>& p, const G1A& q) {  // same formulas and cases as jac_add_affine
+    if (affine_is_identity(q)) return p;
+    if (fq_is_zero(p.z)) return Jac<Fq>{q.x, q.y, fq_one()};
+    Fq zz, yz, u2, s2, hh, zh, hhh, v, r2, yh, M, unused;
+    pair_mul(p.z, p.z, q.y, p.z, zz, yz);
+    pair_mul(q.x, zz, yz, zz, u2, s2);
+    const Fq h = fq_sub(u2, p.x), rr = fq_sub(s2, p.y);
+    if (fq_is_zero(h)) {
+        if (fq_is_zero(rr)) return jac_dbl_pair(p);
+        return jac_identity<Fq>();
+    }
+    pair_mul(h, h, p.z, h, hh, zh);
+    pair_mul(hh, h, p.x, hh, hhh, v);
+    pair_mul(rr, rr, p.y, hhh, r2, yh);
+    Jac<Fq> r;
+    r.x = fq_sub(fq_sub(fq_sub(r2, hhh), v), v);
+    const Fq vx = fq_sub(v, r.x);
+    pair_mul(rr, vx, rr, vx, M, unused);
+    r.y = fq_sub(M, yh);
+    r.z = zh;
+    return r;
+}
+__device__ __forceinline__ Jac<Fq> jac_scalar_mul_naf_pair(const G1A& q, const uint32_t* plus, const uint32_t* minus, int bits) {
+    Jac<Fq> acc = jac_identity<Fq>();
+    for (int i = bits - 1; i >= 0; i--) {
+        acc = jac_dbl_pair(acc);
+        const uint32_t m = 1u << (i & 31);
+        const bool dp = (plus[i >> 5] & m) != 0, dm = (minus[i >> 5] & m) != 0;
+        if (dp || dm) {
+            G1A t = q;
+            if (dm) t.y = fq_neg(q.y);
+            acc = jac_add_affine_pair(acc, t);
+        }
+    }
+    return acc;
+}
+
 // [k_j] (+-) endo^j(p2) for this warp's component
 template <class F>
 __device__ __forceinline__ Jac<F> fold_component(const Affine<F>& p2, const FoldComp& c, int j, int bits) {
@@ -68,28 +146,40 @@ __global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_split(uint32_t* __re
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x < g2_blocks) {
-        size_t i = (size_t)blockIdx.x * 32 + lane;
+        // 16 elements per block, every Fq2 on a PAIR of lanes (fq2h.cuh): an Fq2 product is one lazy inner product per lane
+        // instead of three dependent Fq products on one thread -- the 66-doubling chain of a component gets ~1.75x shorter
+        const int el = lane >> 1;
+        size_t i = (size_t)blockIdx.x * 16 + el;
         const bool valid = i < h;
         if (!valid) i = h - 1;
-        Jac<Fq2> acc = fold_component(load_g2(B, i + h), plan.g2[warp], warp, plan.g2_bits);
-        if (warp > 0) store_jac(xch + ((warp - 1) * 32 + lane) * 48, acc);
+        G2A q = endo_apply(load_g2(B, i + h), warp);
+        if (plan.g2[warp].neg) q.y = f_neg(q.y);
+        Jac<Fq2H> acc = jac_scalar_mul_naf(split_g2(q), plan.g2[warp].plus, plan.g2[warp].minus, plan.g2_bits);
+        if (warp > 0) store_jac_h(xch + ((warp - 1) * 16 + el) * 48, acc);
         __syncthreads();
         if (warp == 0) {
 #pragma unroll 1
-            for (int j = 0; j < 3; j++) acc = jac_add(acc, load_jac2(xch + (j * 32 + lane) * 48));
-            G2A r = jac_to_affine(jac_add_affine(acc, load_g2(B, i)));
-            if (valid) store_g2(B, i, r);
+            for (int j = 0; j < 3; j++) acc = jac_add(acc, load_jac_h(xch + (j * 16 + el) * 48));
+            const Affine<Fq2H> r = jac_to_affine(jac_add_affine(acc, split_g2(load_g2(B, i))));
+            if (valid) {
+                const int o = h_odd() ? 8 : 0;
+                store_fq_words(B + 32 * i + o, r.x.v);
+                store_fq_words(B + 32 * i + 16 + o, r.y.v);
+            }
         }
     } else {
-        const int comp = warp & 1, half = warp >> 1;
-        size_t i = (size_t)(blockIdx.x - g2_blocks) * 64 + half * 32 + lane;
+        // 32 elements per block: warps (0, 1) and (2, 3) hold the two GLV components of 16 elements each, every element on a lane pair
+        const int comp = warp & 1, half = warp >> 1, el = lane >> 1;
+        size_t i = (size_t)(blockIdx.x - g2_blocks) * 32 + half * 16 + el;
         const bool valid = i < h;
         if (!valid) i = h - 1;
-        Jac<Fq> acc = fold_component(load_g1(A, i + h), plan.g1[comp], comp, plan.g1_bits);
-        if (comp == 1) store_jac(xch + (half * 32 + lane) * 24, acc);
+        G1A q = endo_apply(load_g1(A, i + h), comp);
+        if (plan.g1[comp].neg) q.y = fq_neg(q.y);
+        Jac<Fq> acc = jac_scalar_mul_naf_pair(q, plan.g1[comp].plus, plan.g1[comp].minus, plan.g1_bits);
+        if (comp == 1 && !h_odd()) store_jac(xch + (half * 16 + el) * 24, acc);
         __syncthreads();
-        if (comp == 0) {
-            acc = jac_add(acc, load_jac1(xch + (half * 32 + lane) * 24));
+        if (comp == 0 && !h_odd()) {
+            acc = jac_add(acc, load_jac1(xch + (half * 16 + el) * 24));
             G1A r = jac_to_affine(jac_add_affine(acc, load_g1(A, i)));
             if (valid) store_g1(A, i, r);
         }
@@ -102,36 +192,46 @@ __global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_split(uint32_t* __re
 // spans several instances and the digit branches diverge -- those rounds hold 31/127 of an instance's fold work.
 __global__ void __launch_bounds__(SIPP_FOLD_THREADS) k_fold_batch(uint32_t* __restrict__ A, uint32_t* __restrict__ B, size_t h, size_t stride, size_t count,
                                                                  const FoldPlan* __restrict__ plans, unsigned g2_blocks) {
-    __shared__ __align__(16) uint32_t xch[3 * 32 * 48];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint32_t xch[3 * 16 * 48];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, el = lane >> 1;
     const size_t total = count * h;
     if (blockIdx.x < g2_blocks) {
-        size_t e = (size_t)blockIdx.x * 32 + lane;
+        // as k_fold_split: 16 elements per block, every Fq2 on a lane pair; pairs of one warp may follow different digit schedules
+        // (different instances) -- the pair shuffles of fq2h.cuh name only their own two lanes
+        size_t e = (size_t)blockIdx.x * 16 + el;
         const bool valid = e < total;
         if (!valid) e = total - 1;
         const size_t inst = e / h, i = inst * stride + e % h;
         const FoldPlan* pl = plans + inst;
-        Jac<Fq2> acc = fold_component(load_g2(B, i + h), pl->g2[warp], warp, pl->g2_bits);
-        if (warp > 0) store_jac(xch + ((warp - 1) * 32 + lane) * 48, acc);
+        G2A q = endo_apply(load_g2(B, i + h), warp);
+        if (pl->g2[warp].neg) q.y = f_neg(q.y);
+        Jac<Fq2H> acc = jac_scalar_mul_naf(split_g2(q), pl->g2[warp].plus, pl->g2[warp].minus, pl->g2_bits);
+        if (warp > 0) store_jac_h(xch + ((warp - 1) * 16 + el) * 48, acc);
         __syncthreads();
         if (warp == 0) {
 #pragma unroll 1
-            for (int j = 0; j < 3; j++) acc = jac_add(acc, load_jac2(xch + (j * 32 + lane) * 48));
-            G2A r = jac_to_affine(jac_add_affine(acc, load_g2(B, i)));
-            if (valid) store_g2(B, i, r);
+            for (int j = 0; j < 3; j++) acc = jac_add(acc, load_jac_h(xch + (j * 16 + el) * 48));
+            const Affine<Fq2H> r = jac_to_affine(jac_add_affine(acc, split_g2(load_g2(B, i))));
+            if (valid) {
+                const int o = h_odd() ? 8 : 0;
+                store_fq_words(B + 32 * i + o, r.x.v);
+                store_fq_words(B + 32 * i + 16 + o, r.y.v);
+            }
         }
     } else {
         const int comp = warp & 1, half = warp >> 1;
-        size_t e = (size_t)(blockIdx.x - g2_blocks) * 64 + half * 32 + lane;
+        size_t e = (size_t)(blockIdx.x - g2_blocks) * 32 + half * 16 + el;
         const bool valid = e < total;
         if (!valid) e = total - 1;
         const size_t inst = e / h, i = inst * stride + e % h;
         const FoldPlan* pl = plans + inst;
-        Jac<Fq> acc = fold_component(load_g1(A, i + h), pl->g1[comp], comp, pl->g1_bits);
-        if (comp == 1) store_jac(xch + (half * 32 + lane) * 24, acc);
+        G1A q = endo_apply(load_g1(A, i + h), comp);
+        if (pl->g1[comp].neg) q.y = fq_neg(q.y);
+        Jac<Fq> acc = jac_scalar_mul_naf_pair(q, pl->g1[comp].plus, pl->g1[comp].minus, pl->g1_bits);
+        if (comp == 1 && !h_odd()) store_jac(xch + (half * 16 + el) * 24, acc);
         __syncthreads();
-        if (comp == 0) {
-            acc = jac_add(acc, load_jac1(xch + (half * 32 + lane) * 24));
+        if (comp == 0 && !h_odd()) {
+            acc = jac_add(acc, load_jac1(xch + (half * 16 + el) * 24));
             G1A r = jac_to_affine(jac_add_affine(acc, load_g1(A, i)));
             if (valid) store_g1(A, i, r);
         }
@@ -230,13 +330,13 @@ int launch_validate_points(const uint32_t* dA, const uint32_t* dB, size_t n, int
 int launch_fold(uint32_t* A, uint32_t* B, size_t h, const FoldPlan& plan, cudaStream_t s) {
     // In-place: an element's partner i + h is only read by the block that owns i, and i < h <= i + h, so no block reads
     // what another block writes.
-    unsigned g2_blocks = (unsigned)((h + 31) / 32), g1_blocks = (unsigned)((h + 63) / 64);
+    unsigned g2_blocks = (unsigned)((h + 15) / 16), g1_blocks = (unsigned)((h + 31) / 32);
     k_fold_split<<<g2_blocks + g1_blocks, SIPP_FOLD_THREADS, 0, s>>>(A, B, h, plan, g2_blocks);
     return (int)cudaGetLastError();
 }
 int launch_fold_batch(uint32_t* A, uint32_t* B, size_t h, size_t stride, size_t count, const FoldPlan* plans, cudaStream_t s) {
     size_t total = count * h;
-    unsigned g2_blocks = (unsigned)((total + 31) / 32), g1_blocks = (unsigned)((total + 63) / 64);
+    unsigned g2_blocks = (unsigned)((total + 15) / 16), g1_blocks = (unsigned)((total + 31) / 32);
     k_fold_batch<<<g2_blocks + g1_blocks, SIPP_FOLD_THREADS, 0, s>>>(A, B, h, stride, count, plans, g2_blocks);
     return (int)cudaGetLastError();
 }

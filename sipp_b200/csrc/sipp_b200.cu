@@ -24,7 +24,7 @@ int g_device = -1;
 cudaStream_t g_stream = nullptr;
 int g_opt_fe_norm = 0, g_opt_fq12_order = 0, g_opt_profile = 0, g_opt_pipeline = 1;
 int g_opt_fe_engine = 1;
-int g_opt_wide_fold_max = 512;
+int g_opt_wide_fold_max = 256;
 int g_opt_wide_accum_max = 1536;
 int g_opt_wide_max = 8192;  // pairs per launch up to which the 16-lanes-per-pair line kernel is used (latency-bound rounds)
 int g_sm_count = 148;

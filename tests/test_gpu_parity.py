@@ -115,7 +115,7 @@ def pipeline(request, sipp):
     sipp.set_option(_lib.OPT_PIPELINE, 1)
     sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
     sipp.set_option(_lib.OPT_FE_ENGINE, 1)
-    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
+    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 256)
     sipp.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1536)
 
 
@@ -204,7 +204,7 @@ def test_fold_round(sipp, oracle, wide_fold):
         ctx.fold(x, xinv)
         assert ctx.read() == (oracle.fold_g1(A, x), oracle.fold_g2(B, xinv))
         ctx.close()
-    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
+    sipp.set_option(_lib.OPT_WIDE_FOLD_MAX, 256)
 
 
 def test_prove_golden(sipp, golden, pipeline):

@@ -30,7 +30,7 @@ for it in range(iters):
         sts = sipp_b200.sipp_verify_native_batch(A, B, n, proofs)
     finally:
         for k, v in ((_lib.OPT_BATCH_KPG_MAX, 32), (_lib.OPT_FOLD_STRAUS, 1), (_lib.OPT_BATCH_QLINES, 1), (_lib.OPT_FE_ENGINE, 1),
-                     (_lib.OPT_WIDE_LINES_MAX, 8192), (_lib.OPT_WIDE_FOLD_MAX, 512)):
+                     (_lib.OPT_WIDE_LINES_MAX, 8192), (_lib.OPT_WIDE_FOLD_MAX, 256)):
             sipp_b200.set_option(k, v)
     assert all(not isinstance(s, Exception) for s in sts), (it, n, count, seed, opts)
     for j in rng.sample(range(count), min(count, 3)):

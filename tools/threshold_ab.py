@@ -17,6 +17,6 @@ for v in (2048, 4096):
 sipp_b200.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1536)
 for v in (1024, 2048):
     sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, v); run("wide_fold_max=%d" % v)
-sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
+sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 256)
 for v in (4096, 16384):
     sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, v); run("wide_lines_max=%d" % v)

@@ -9,7 +9,7 @@ for n in (4096, 128):
     for wide in (0, 8192):
         sipp_b200.set_option(_lib.OPT_WIDE_LINES_MAX, wide)
         sipp_b200.set_option(_lib.OPT_FE_ENGINE, 1 if wide else 0)
-        sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 512 if wide else 0)
+        sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 256 if wide else 0)
         sipp_b200.set_option(_lib.OPT_WIDE_ACCUM_MAX, 1536 if wide else 0)
         for rep in range(3):
             sipp_b200.set_option(_lib.OPT_PROFILE, 1)
@@ -56,4 +56,4 @@ for h in (64, 256, 512, 1024, 2048):
             st = sipp_b200.stats(reset=True)
             ctx.close()
         print("fold h=%5d wide=%d  %.3f ms" % (h, 1 if wide else 0, st["fold_ms"]))
-sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 512)
+sipp_b200.set_option(_lib.OPT_WIDE_FOLD_MAX, 256)
