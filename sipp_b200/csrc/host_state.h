@@ -20,6 +20,7 @@ struct MatTail {
     int cur = 0;
     size_t n = 0;   // virtual points (blocks) the matrix stands for; 0 = no stage in progress
     size_t m = 1;   // points per block (1: the tail of the proof)
+    bool fold_points = false;  // the points are still folded with every challenge (side stream): a later stage is built from them
     int folds = 0;  // point folds issued on the side stream in this stage
     void reset() {
         pool_free(E[0]);
@@ -27,6 +28,7 @@ struct MatTail {
         E[0] = E[1] = nullptr;
         n = 0;
         m = 1;
+        fold_points = false;
     }
     ~MatTail() { reset(); }
 };
@@ -109,6 +111,8 @@ size_t mat_stage_first(size_t n);  // blocks of the stage built from the inputs 
 int mat_diag_product(MatTail& mt, uint8_t* z);
 size_t mat_stage(size_t n);  // number of blocks of the stage that starts with n points left (0: a plain round)
 int mat_build(sipp_ctx* c, MatTail& mt, size_t nr);
+int mat_build_ex(sipp_ctx* c, MatTail& mt, size_t nr, uint32_t* raw_out);
+int mat_adopt(MatTail& mt, const uint32_t* gathered, int ranks, size_t nr);
 int mat_products(MatTail& mt, uint8_t* zl, uint8_t* zr);
 int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[32]);
 

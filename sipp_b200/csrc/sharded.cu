@@ -80,6 +80,7 @@ int nccl_fail(int rc, const char* what) {
 // ------------------------------------------------------------------------------------------------ communicator of this process
 enum { COMM_NONE = 0, COMM_NCCL = 1, COMM_HOST = 2 };
 const size_t SLOT = 2 * SIPP_PARTIAL_BYTES;  // bytes per rank in the gather buffer per round: two partials
+const size_t STAGE_ENTRIES_MAX = 1024;        // entries of a distributed first stage (32 x 32 blocks): each rank ships 384 B per entry
 const size_t COLLAPSE_MAX = 4096;            // the collapse gathers at most this many points (192 B each) through the same buffer
 const size_t XS = 72;                        // x || x^-1 || status word (+ padding)
 
@@ -98,6 +99,7 @@ struct Comm {
 int comm_buffers() {
     g_comm.gather_bytes = (size_t)g_comm.world * SLOT;
     if (g_comm.gather_bytes < COLLAPSE_MAX * 192) g_comm.gather_bytes = COLLAPSE_MAX * 192;
+    if (g_comm.gather_bytes < (size_t)g_comm.world * STAGE_ENTRIES_MAX * SIPP_PARTIAL_BYTES) g_comm.gather_bytes = (size_t)g_comm.world * STAGE_ENTRIES_MAX * SIPP_PARTIAL_BYTES;
     CK(cudaMalloc(&g_comm.d_gather, g_comm.gather_bytes));
     CK(cudaMalloc(&g_comm.d_xs, XS));
     CK(cudaMallocHost(&g_comm.h_stage, g_comm.gather_bytes + XS));
@@ -150,10 +152,26 @@ int comm_broadcast_xs(uint8_t* xs) {
 struct CudaBackend {
     sipp_ctx* ctx = nullptr;
     bool collapsed = false;  // the tail lives on rank 0 alone
+    size_t collapse_at = 0;  // points left (in all) at which the tail moves to rank 0
     int last_nprod = 0;
-    uint8_t tail_out[768];   // rank 0 alone (the collapsed tail): products straight from the context (pairing-matrix stages, k_mat.cu)
+    uint8_t tail_out[768];   // products that rank 0 computes alone: the collapsed tail, and the rounds of a distributed first stage
     bool tail_round = false;
+    int stage_left = 0;      // rounds the distributed first stage still serves (the same on every rank)
 };
+// The FIRST stage over the ranks (sipp_b200.cu mat_stage_first, k_mat.cu): with strided ownership a block of m consecutive global
+// indices holds m / world points of every rank, so each rank computes ITS factor of every block product <A_block_i, B_block_j>
+// (un-exponentiated), the factors are all-gathered (384 B per entry and rank: 3 MB at 32 x 32 blocks on 8 GPUs -- the one real
+// exchange of the protocol) and rank 0 multiplies and exponentiates them.  The first log2(nr) rounds then need no collective but
+// the challenge broadcast: rank 0 folds the matrix, every rank folds its own points.  Blocks: as many as keep a rank under 2^17
+// Miller loops, at most 32, and the stage must end before the tail moves to rank 0.
+size_t cb_first_stage_blocks(size_t local_n, size_t collapse_at) {
+    const size_t world = (size_t)g_comm.world, n = local_n * world;
+    if (world == 1 || !g_opt_matrix_first || !g_opt_pipeline || !g_opt_fe_engine || g_opt_matrix_n < 2) return 0;
+    size_t end_n = collapse_at > 2 * world ? collapse_at : 2 * world;
+    size_t nr = 32;
+    while (nr >= 4 && (local_n * nr > ((size_t)1 << 17) || nr > local_n || n / nr < end_n)) nr >>= 1;
+    return nr >= 4 ? nr : 0;
+}
 bool cb_alone(const CudaBackend* b) { return b->collapsed || g_comm.world == 1; }
 
 size_t cb_local_len(void* u) { return ((CudaBackend*)u)->ctx ? ((CudaBackend*)u)->ctx->n : 0; }
@@ -162,6 +180,28 @@ int cb_products(void* u, int which) {
     CudaBackend* b = (CudaBackend*)u;
     const int nprod = which == 0 ? 1 : 2;
     b->last_nprod = nprod;
+    if (which == 0 && !b->collapsed) {
+        const size_t nr = cb_first_stage_blocks(b->ctx->n, b->collapse_at);
+        if (nr) {
+            // every rank: its factors of the nr^2 block products, straight into its slot of the gather buffer
+            const size_t bytes = nr * nr * SIPP_PARTIAL_BYTES;
+            MatTail none;
+            int rc = mat_build_ex(b->ctx, none, nr, (uint32_t*)(g_comm.d_gather + (size_t)g_comm.rank * bytes));
+            if (!rc) rc = comm_allgather(bytes);
+            if (rc) return rc;
+            int log2nr = 0;
+            while (((size_t)1 << log2nr) < nr) log2nr++;
+            b->stage_left = log2nr;
+            b->tail_round = true;
+            if (g_comm.rank != 0) return SIPP_OK;
+            rc = mat_adopt(b->ctx->mt, (const uint32_t*)g_comm.d_gather, g_comm.world, nr);
+            return rc ? rc : mat_diag_product(b->ctx->mt, b->tail_out);      // Z = prod E[i][i]
+        }
+    }
+    if (which == 1 && b->stage_left > 0 && !b->collapsed) {                  // a round of the distributed stage: rank 0's matrix
+        b->tail_round = true;
+        return g_comm.rank == 0 ? mat_products(b->ctx->mt, b->tail_out, b->tail_out + 384) : SIPP_OK;
+    }
     b->tail_round = which == 1 && cb_alone(b);
     if (b->tail_round) {
         b->ctx->stages = true;
@@ -177,8 +217,8 @@ int cb_products(void* u, int which) {
 
 int cb_combine(void* u, int nprod, uint8_t* out) {
     CudaBackend* b = (CudaBackend*)u;
-    if (b->tail_round && nprod == 2) {
-        memcpy(out, b->tail_out, 768);
+    if (b->tail_round) {
+        memcpy(out, b->tail_out, (size_t)nprod * 384);
         return SIPP_OK;
     }
     return sipp_combine_partials(g_comm.d_gather, b->collapsed ? 1 : g_comm.world, nprod, out, g_stream);
@@ -187,7 +227,9 @@ int cb_combine(void* u, int nprod, uint8_t* out) {
 int cb_broadcast(void*, uint8_t* xs) { return comm_broadcast_xs(xs); }
 
 int cb_fold(void* u, const uint8_t* x, const uint8_t* xinv) {
-    return sipp_ctx_fold(((CudaBackend*)u)->ctx, x, xinv);
+    CudaBackend* b = (CudaBackend*)u;
+    if (b->stage_left > 0) b->stage_left--;
+    return sipp_ctx_fold(b->ctx, x, xinv);  // rank 0 during a stage: the matrix AND (side stream) its points; otherwise the points
 }
 
 // The tail moves to rank 0: every rank holds L = (points left) / world of them (strided: local element l is global l world + rank).
@@ -345,6 +387,7 @@ int prove_sharded(sipp_ctx* c, int create_rc, size_t n, const uint8_t* A_full, c
         // rank 0 runs the look-ahead stages and the pairing-matrix tail (k_mat.cu) alone: collapse where they begin
         size_t at = g_opt_pipeline && g_opt_fe_engine ? (size_t)(g_opt_matrix_block_n > g_opt_matrix_n ? g_opt_matrix_block_n : g_opt_matrix_n) : 0;
         if (at > COLLAPSE_MAX) at = COLLAPSE_MAX;
+        b.collapse_at = at;
         rc = sharded_protocol(&be, n, A_full, B_full, proof, job, at);
     }
     if (b.ctx) {

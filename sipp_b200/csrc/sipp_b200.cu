@@ -350,7 +350,11 @@ size_t mat_stage_first(size_t n) {
     return (nr * n <= ((size_t)1 << 17) && n / nr >= 2) ? nr : 0;
 }
 
-int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
+int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) { return mat_build_ex(c, mt, nr, nullptr); }
+
+// raw_out != NULL (a rank of the sharded prover): only this shard's UN-exponentiated entry products are computed and written there
+// (nr^2 x 96 words, register-shaped) -- they are all-gathered and rank 0 finishes with mat_adopt; `mt` is not touched
+int mat_build_ex(sipp_ctx* c, MatTail& mt, size_t nr, uint32_t* raw_out) {
     const size_t n = c->n, m = n / nr, P = nr * nr, pairs = P * m;
     // small launches: the lane engines (latency); large ones (a first stage): line coefficients of every B point once + the
     // throughput accumulation kernel
@@ -366,12 +370,16 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
     int rc = scratch_reserve(m == 1 ? nr : (blocks * P + 1) / 2);
     if (!rc) rc = lines_reserve(pairs * lines_bytes_per_pair());
     if (rc) return rc;
-    cudaError_t e = pool_alloc((void**)&mt.E[0], P * 384);
-    if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (P / 4) * 384);
+    cudaError_t e = cudaSuccess;
+    if (!raw_out) {
+        e = pool_alloc((void**)&mt.E[0], P * 384);
+        if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (P / 4) * 384);
+    }
     if (e == cudaSuccess && !big) e = pool_alloc((void**)&aexp, pairs * 64);
     if (e == cudaSuccess && !big) e = pool_alloc((void**)&bexp, pairs * 128);
     if (e == cudaSuccess && big) e = pool_alloc((void**)&ql, n * qlines_bytes_per_point());
-    if (e == cudaSuccess && m == 1) e = pool_alloc((void**)&mil, P * 384);
+    if (e == cudaSuccess && m == 1 && !raw_out) e = pool_alloc((void**)&mil, P * 384);
+    if (m == 1 && raw_out) mil = raw_out;
     int le = 0;
     if (e == cudaSuccess) {
         {
@@ -392,7 +400,10 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
                 if (!le) le = m == 1 ? launch_accum_eng_each(g_scr.lines, P, mil, g_stream) : launch_accum_eng(g_scr.lines, m, (int)P, 1, g_scr.partials, 0, g_stream);
             }
         }
-        if (!le) {
+        if (!le && raw_out) {
+            Span sp(1, g_stream);  // product of the entry's partials, no exponentiation
+            if (m > 1) le = launch_reduce_fe_eng(g_scr.partials, (int)blocks, (int)P, raw_out, 0, g_opt_fe_norm, g_stream);
+        } else if (!le) {
             Span sp(1, g_stream);
             le = m == 1 ? launch_mat_fe(mil, P, mt.E[0], g_opt_fe_norm, g_stream)
                         : launch_reduce_fe_eng(g_scr.partials, (int)blocks, (int)P, mt.E[0], 3, g_opt_fe_norm, g_stream);
@@ -404,12 +415,37 @@ int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) {
     // the staging blocks are only reused by later work on the same stream
     pool_free(aexp);
     pool_free(bexp);
-    pool_free(mil);
+    if (mil != raw_out) pool_free(mil);
     pool_free(ql);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pairing matrix)");
     if (le) return cuda_fail((cudaError_t)le, "pairing matrix");
+    if (raw_out) return SIPP_OK;
     mt.n = nr;
     mt.m = m;
+    mt.fold_points = m > 1;
+    mt.cur = 0;
+    mt.folds = 0;
+    return SIPP_OK;
+}
+
+// rank 0 of the sharded prover: the matrix from the gathered entry products of all ranks (layout [rank][nr^2][96 words]): product over
+// the ranks + one final exponentiation per entry.  The points of this rank's shard keep being folded with every challenge.
+int mat_adopt(MatTail& mt, const uint32_t* gathered, int ranks, size_t nr) {
+    const size_t P = nr * nr;
+    int rc = scratch_reserve(nr);
+    if (rc) return rc;
+    cudaError_t e = pool_alloc((void**)&mt.E[0], P * 384);
+    if (e == cudaSuccess) e = pool_alloc((void**)&mt.E[1], (P / 4) * 384);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pairing matrix)");
+    {
+        Span sp(1, g_stream);
+        int le = launch_reduce_fe_eng(gathered, ranks, (int)P, mt.E[0], 3, g_opt_fe_norm, g_stream);
+        if (le) return cuda_fail((cudaError_t)le, "pairing matrix (gathered)");
+    }
+    g_stats.launches++;
+    mt.n = nr;
+    mt.m = 2;  // blocks of several points (spread over the ranks)
+    mt.fold_points = true;
     mt.cur = 0;
     mt.folds = 0;
     return SIPP_OK;
@@ -460,7 +496,7 @@ int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[3
         mt.cur ^= 1;
     }
     const size_t h = c->n / 2;
-    if (mt.m > 1) {
+    if (mt.fold_points) {
         FoldPlan fp;
         if (fold_plan_build(x, xinv, &fp)) return fail(SIPP_ERR_ENCODING, "fold scalar out of range (must be < r)");
         if (!g_fold_stream) CK(cudaStreamCreateWithFlags(&g_fold_stream, cudaStreamNonBlocking));
@@ -470,12 +506,12 @@ int mat_fold(sipp_ctx* c, MatTail& mt, const uint8_t x[32], const uint8_t xinv[3
         if (le) return cuda_fail((cudaError_t)le, "k_fold (look-ahead stage)");
         g_stats.launches++;
     }
-    if (mt.m == 1) c->stale = true;  // the tail: the points are not folded any more
+    if (!mt.fold_points) c->stale = true;  // the tail: the points are not folded any more
     g_stats.fold_points += h;
     c->n = h;
     mt.n /= 2;
     if (mt.n == 1) {  // stage over
-        if (mt.m > 1) CK(order_after(g_stream, g_fold_stream));
+        if (mt.fold_points) CK(order_after(g_stream, g_fold_stream));
         mt.reset();
     }
     return SIPP_OK;
@@ -742,7 +778,7 @@ int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
 int sipp_ctx_read(sipp_ctx* c, uint8_t* A_out, uint8_t* B_out) {
     if (!c) return fail(SIPP_ERR_ARG, "null ctx");
     if (c->stale) return fail(SIPP_ERR_ARG, "the points of this context were not folded during its pairing-matrix tail (sipp_ctx_set_stages)");
-    if (c->mt.n && c->mt.m > 1) CK(order_after(g_stream, g_fold_stream));  // look-ahead stage: the folds run on the side stream
+    if (c->mt.n && c->mt.fold_points) CK(order_after(g_stream, g_fold_stream));  // look-ahead stage: the folds run on the side stream
     size_t n = c->n;
     uint32_t* tmp;
     CK(pool_alloc((void**)&tmp, n * 32 * sizeof(uint32_t)));
