@@ -73,16 +73,16 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          inputs are built); failure = SIPP_ERR_ENCODING.  0 = trusted inputs: the caller guarantees it (the folds
                                          use the GLV / GLS endomorphisms, which act as scalars only on the r-torsion -- results for other points
                                          are unspecified) */
-#define SIPP_OPT_MATRIX_TAIL 14       /* single proof: once at most this many points are left (default 16, 0 = off, a power of two <= 64) the prover
+#define SIPP_OPT_MATRIX_TAIL 14       /* single proof: once at most this many points are left (default 32, 0 = off, a power of two <= 64) the prover
                                          computes E[i][j] = e(A_i, B_j) for all pairs and the remaining rounds fold that MATRIX in GT
                                          (E'[i][j] = E[i][j] E[i+h][j+h] E[i+h][j]^x E[i][j+h]^(1/x), k_mat.cu) instead of the points:
                                          same Z_L, Z_R bit for bit, one short kernel per round.  The context's points are then left
                                          as they were when the tail began (only its length keeps halving) */
 #define SIPP_OPT_MATRIX_BLOCK_N 15    /* look-ahead stages of the same kind BEFORE the tail: when at most this many points are left (default
-                                         256; 0 = off) they are cut into SIPP_OPT_MATRIX_BLOCK_R blocks, E[i][j] = <A_block_i, B_block_j> is
+                                         256; 0 = off) they are cut into n / 16 blocks, at most SIPP_OPT_MATRIX_BLOCK_R, E[i][j] = <A_block_i, B_block_j> is
                                          computed for all block pairs in one launch set, and log2(R) rounds take Z_L, Z_R from that matrix
                                          while the points are folded on a side stream, off the critical path */
-#define SIPP_OPT_MATRIX_FIRST 17      /* 1 [default]: the FIRST stage is built from the inputs themselves (up to 32 blocks, at most 2^17 Miller
+#define SIPP_OPT_MATRIX_FIRST 17      /* 1 [default]: the FIRST stage is built from the inputs themselves (n / 32 blocks, between 8 and 32, at most 2^17 Miller
                                          loops) while the host still hashes A and B: Z is the product of its diagonal and the first
                                          log2(blocks) rounds are one matrix fold each.  0 = the first rounds run on the points */
 #define SIPP_OPT_MATRIX_BLOCK_R 16    /* blocks per look-ahead stage: 4, 8 (default), 16 or 32 (capped so that the stage ends where the tail begins) */

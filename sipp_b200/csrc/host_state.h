@@ -41,6 +41,8 @@ struct sipp_ctx {
     size_t n = 0, cap = 0;
     bool stages = false;     // sipp_ctx_set_stages: products / folds may run on pairing-matrix stages
     bool stale = false;      // a tail stage ran: the points were not folded any more (sipp_ctx_read refuses)
+    bool pending_validation = false;  // the on-curve / subgroup check of these points is still running on the side stream
+    cudaEvent_t validated = nullptr;
     sipp_host::MatTail mt;
 };
 

@@ -32,7 +32,7 @@ int g_opt_fold_straus = 1;     // throughput folds (batched instances, large rou
 int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own streams (0 = choose by batch size)
 int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
-int g_opt_matrix_n = 16;       // pairing-matrix tail (k_mat.cu) once at most this many points are left; 0 = off
+int g_opt_matrix_n = 32;       // pairing matrix of single points (k_mat.cu) once at most this many points are left; 0 = off
 int g_opt_matrix_first = 1;     // the first matrix is built from the inputs, under the host's absorb chain
 int g_opt_matrix_block_n = 256, g_opt_matrix_block_r = 8;  // look-ahead stages: from at most this many points, that many blocks
 int g_opt_validate = 1;        // every prove / verify entry point checks its points: on the curve, B_i in the order-r subgroup
@@ -152,6 +152,7 @@ struct Scratch {
     uint32_t* out = nullptr;       // 4 x 96 words device result
     uint8_t* h_out = nullptr;      // pinned mirror
     int* flag = nullptr;
+    int* vflag = nullptr;          // result of a deferred point validation (sipp_prove_native / sipp_verify_native)
     uint32_t* lines = nullptr;     // split pipeline: [nprod][mc][91][80 words]
     size_t lines_bytes = 0;
 } g_scr;
@@ -161,6 +162,7 @@ int scratch_reserve(size_t blocks) {
         CK(cudaMalloc(&g_scr.out, 4 * 96 * sizeof(uint32_t)));
         CK(cudaMallocHost(&g_scr.h_out, 4 * 384));
         CK(cudaMalloc(&g_scr.flag, sizeof(int)));
+        CK(cudaMalloc(&g_scr.vflag, sizeof(int)));
     }
     if (blocks > g_scr.partial_blocks) {
         if (g_scr.partials) CK(cudaFree(g_scr.partials));
@@ -328,26 +330,31 @@ cudaStream_t g_fold_stream = nullptr;
 FoldPlan* g_fold_plan_dev = nullptr;  // device copy of the plan for k_fold_straus (released in sipp_shutdown)
 int g_live_ctx = 0;                   // contexts alive (a device switch is refused while any exists)
 
+// Stage sizes (measured on B200, tools/tail_ab.py, profiles/r02_v7_stage_ab.txt).  A matrix of single points pays from 32 points
+// down (1,024 Miller loops + final exponentiations in one latency); a look-ahead stage takes n / 16 blocks, at most
+// SIPP_OPT_MATRIX_BLOCK_R (it ends at 16 or 32 points, where the matrix of single points takes over); the first stage takes n / 32 blocks, between 8 and 32, as long as the launch stays under 2^17 loops
+// (more blocks than that and the matrix no longer fits under the absorb chain of a small proof: n = 512 with 32 blocks lost 1 ms).
 size_t mat_stage(size_t n) {
     if (!g_opt_pipeline || !g_opt_fe_engine || n < 2) return 0;
     if (n <= (size_t)g_opt_matrix_n) return n;
     if (g_opt_matrix_n < 2 || n > (size_t)g_opt_matrix_block_n) return 0;
-    size_t nr = n / (size_t)g_opt_matrix_n;  // the stage ends where the tail begins
+    size_t nr = n / 16;
     if (nr > (size_t)g_opt_matrix_block_r) nr = (size_t)g_opt_matrix_block_r;
+    while (nr >= 4 && n / nr < 2) nr >>= 1;
     return nr >= 4 ? nr : 0;
 }
 
 // The FIRST stage of a proof starts from the inputs themselves, before any challenge exists: it runs in the shadow of the host's
 // 8n-permutation absorb chain, gives Z as the product of its diagonal, and the first log2(nr) rounds cost one matrix fold each.
-// As many blocks as keep the launch under 2^17 pairs (the matrix needs n nr Miller loops), at most 32.
 size_t mat_stage_first(size_t n) {
-    if (!g_opt_matrix_first || !g_opt_pipeline || !g_opt_fe_engine || n < 8 || g_opt_matrix_n < 2) return 0;
+    if (!g_opt_matrix_first || !g_opt_pipeline || !g_opt_fe_engine || n < 2 || g_opt_matrix_n < 2) return 0;
     if (n <= (size_t)g_opt_matrix_n) return n;               // the whole proof on the matrix of its inputs
-    size_t nr = n / (size_t)g_opt_matrix_n;                  // ideally the stage ends where the tail begins
+    size_t nr = n / 32;
+    if (nr < 8) nr = 8;
     if (nr > 32) nr = 32;
     while (nr > 1 && nr * n > ((size_t)1 << 17)) nr >>= 1;   // n nr Miller loops
-    if (nr < 4) nr = 4;
-    return (nr * n <= ((size_t)1 << 17) && n / nr >= 2) ? nr : 0;
+    while (nr >= 4 && n / nr < 2) nr >>= 1;
+    return nr >= 4 ? nr : 0;
 }
 
 int mat_build(sipp_ctx* c, MatTail& mt, size_t nr) { return mat_build_ex(c, mt, nr, nullptr); }
@@ -366,7 +373,7 @@ int mat_build_ex(sipp_ctx* c, MatTail& mt, size_t nr, uint32_t* raw_out) {
         if (kpg < 1) kpg = 1;
     }
     const size_t blocks = big ? (size_t)accum_blocks(m, kpg) : (size_t)accum_eng_blocks(m, 1);
-    uint32_t *aexp = nullptr, *bexp = nullptr, *mil = nullptr, *ql = nullptr;
+    uint32_t *aexp = nullptr, *bexp = nullptr, *mil = nullptr, *ql = nullptr, *prod = nullptr;
     int rc = scratch_reserve(m == 1 ? nr : (blocks * P + 1) / 2);
     if (!rc) rc = lines_reserve(pairs * lines_bytes_per_pair());
     if (rc) return rc;
@@ -404,9 +411,18 @@ int mat_build_ex(sipp_ctx* c, MatTail& mt, size_t nr, uint32_t* raw_out) {
             Span sp(1, g_stream);  // product of the entry's partials, no exponentiation
             if (m > 1) le = launch_reduce_fe_eng(g_scr.partials, (int)blocks, (int)P, raw_out, 0, g_opt_fe_norm, g_stream);
         } else if (!le) {
+            // one final exponentiation per entry on k_mat_fe (4 machines per block, 3 blocks per SM: 1,024 entries in 1.1 ms; the
+            // reduction kernel's blocks are register-bound at 2 per SM and took 3.7 ms); entries accumulated by several blocks are
+            // multiplied together first (raw product, in place of the first block's partials)
             Span sp(1, g_stream);
-            le = m == 1 ? launch_mat_fe(mil, P, mt.E[0], g_opt_fe_norm, g_stream)
-                        : launch_reduce_fe_eng(g_scr.partials, (int)blocks, (int)P, mt.E[0], 3, g_opt_fe_norm, g_stream);
+            const uint32_t* src = m == 1 ? mil : g_scr.partials;
+            if (m > 1 && blocks > 1) {
+                if (pool_alloc((void**)&prod, P * 384) != cudaSuccess) le = (int)cudaErrorMemoryAllocation;
+                if (!le) le = launch_reduce_fe_eng(g_scr.partials, (int)blocks, (int)P, prod, 0, g_opt_fe_norm, g_stream);
+                src = prod;
+                g_stats.launches++;
+            }
+            if (!le) le = launch_mat_fe(src, P, mt.E[0], g_opt_fe_norm, g_stream);
         }
         g_stats.launches += 4;
         g_stats.miller_launches++;
@@ -417,6 +433,7 @@ int mat_build_ex(sipp_ctx* c, MatTail& mt, size_t nr, uint32_t* raw_out) {
     pool_free(bexp);
     if (mil != raw_out) pool_free(mil);
     pool_free(ql);
+    pool_free(prod);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pairing matrix)");
     if (le) return cuda_fail((cudaError_t)le, "pairing matrix");
     if (raw_out) return SIPP_OK;
@@ -572,6 +589,7 @@ int sipp_shutdown(void) {
     if (g_scr.out) cudaFree(g_scr.out);
     if (g_scr.h_out) cudaFreeHost(g_scr.h_out);
     if (g_scr.flag) cudaFree(g_scr.flag);
+    if (g_scr.vflag) cudaFree(g_scr.vflag);
     if (g_scr.lines) cudaFree(g_scr.lines);
     g_scr = Scratch();
     pool_release_all();
@@ -650,7 +668,10 @@ int sipp_reset_stats(void) {
 }
 
 // ------------------------------------------------------------------------------------------------ contexts
-int sipp_ctx_create_from_device(const void* dA, const void* dB, size_t n, sipp_ctx** out) {
+// `defer`: the on-curve / subgroup check (1.35 ms of pure latency at any size: one 63-bit scalar multiplication per thread) runs on
+// the side stream next to the prover's first kernels instead of in front of them; the whole-protocol entry points collect its
+// verdict with ctx_finish_validation before they return anything, and the first in-place fold waits for it.
+static int ctx_create_from_device_ex(const void* dA, const void* dB, size_t n, sipp_ctx** out, bool defer) {
     int rc = ensure_init();
     if (rc) return rc;
     if (!dA || !dB || !out || n == 0) return fail(SIPP_ERR_ARG, "sipp_ctx_create: null pointer or n == 0");
@@ -662,15 +683,29 @@ int sipp_ctx_create_from_device(const void* dA, const void* dB, size_t n, sipp_c
     launch_decode((const uint32_t*)dA, c->dA, n * 2, g_stream, true);
     launch_codec_decode((const uint32_t*)dB, c->dB, n * 4, g_scr.flag, g_stream);
     g_stats.launches++;
+    cudaError_t e = cudaSuccess;
     if (g_opt_validate) {
         // what G1Affine::new / G2Affine::new assert in the reference: on the curve, in the prime-order subgroup (the folds use
         // the endomorphisms, which are [lambda] / [6x^2] only there)
-        Span sp(3, g_stream);
-        launch_validate_points(c->dA, c->dB, n, g_scr.flag, g_stream);
+        if (defer) {
+            if (!g_fold_stream) e = cudaStreamCreateWithFlags(&g_fold_stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = order_after(g_fold_stream, g_stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(g_scr.vflag, 0, sizeof(int), g_fold_stream);
+            if (e == cudaSuccess) {
+                Span sp(3, g_fold_stream);
+                launch_validate_points(c->dA, c->dB, n, g_scr.vflag, g_fold_stream);
+            }
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->validated, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(c->validated, g_fold_stream);
+            c->pending_validation = e == cudaSuccess;
+        } else {
+            Span sp(3, g_stream);
+            launch_validate_points(c->dA, c->dB, n, g_scr.flag, g_stream);
+        }
         g_stats.launches++;
     }
     int flag = 0;
-    cudaError_t e = cudaMemcpyAsync(&flag, g_scr.flag, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, g_scr.flag, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
     if (e != cudaSuccess) { sipp_ctx_destroy(c); return cuda_fail(e, "decode"); }
     if (flag) {
@@ -681,8 +716,24 @@ int sipp_ctx_create_from_device(const void* dA, const void* dB, size_t n, sipp_c
     *out = c;
     return SIPP_OK;
 }
+int sipp_ctx_create_from_device(const void* dA, const void* dB, size_t n, sipp_ctx** out) { return ctx_create_from_device_ex(dA, dB, n, out, false); }
 
-int sipp_ctx_create(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out) {
+// the verdict of a deferred validation (SIPP_OK when there was none)
+static int ctx_finish_validation(sipp_ctx* c) {
+    if (!c || !c->pending_validation) return SIPP_OK;
+    c->pending_validation = false;
+    int flag = 0;
+    cudaError_t e = cudaEventSynchronize(c->validated);
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, g_scr.vflag, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaEventDestroy(c->validated);
+    c->validated = nullptr;
+    if (e != cudaSuccess) return cuda_fail(e, "point validation");
+    if (flag) return fail(SIPP_ERR_ENCODING, (flag & 2) ? "input point is not on the curve" : "input G2 point is not in the prime-order subgroup");
+    return SIPP_OK;
+}
+
+static int ctx_create_ex(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out, bool defer);
+static int ctx_create_ex(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out, bool defer) {
     int rc = ensure_init();
     if (rc) return rc;
     if (!A || !B || !out || n == 0) return fail(SIPP_ERR_ARG, "sipp_ctx_create: null pointer or n == 0");
@@ -693,14 +744,21 @@ int sipp_ctx_create(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out
     e = cudaMemcpyAsync(tA, A, n * 64, cudaMemcpyHostToDevice, g_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(tB, B, n * 128, cudaMemcpyHostToDevice, g_stream);
     if (e != cudaSuccess) { pool_free(tA); pool_free(tB); return cuda_fail(e, "H2D"); }
-    rc = sipp_ctx_create_from_device(tA, tB, n, out);  // synchronises the stream: the staging blocks are idle on return
+    rc = ctx_create_from_device_ex(tA, tB, n, out, defer);  // synchronises the stream: the staging blocks are idle on return
     pool_free(tA);
     pool_free(tB);
     return rc;
 }
 
+int sipp_ctx_create(const uint8_t* A, const uint8_t* B, size_t n, sipp_ctx** out) { return ctx_create_ex(A, B, n, out, false); }
+
 int sipp_ctx_destroy(sipp_ctx* c) {
     if (!c) return SIPP_OK;
+    if (c->pending_validation) {  // the side stream still reads the points
+        cudaEventSynchronize(c->validated);
+        cudaEventDestroy(c->validated);
+        c->pending_validation = false;
+    }
     // every entry point that enqueues work on a context synchronises before returning results, and a block handed
     // out again is only touched by later work on the same stream, so recycling without a device sync is safe
     pool_free(c->dA);
@@ -749,6 +807,7 @@ int sipp_ctx_cross_products(sipp_ctx* c, uint8_t zl[384], uint8_t zr[384]) {
 int sipp_ctx_fold(sipp_ctx* c, const uint8_t x[32], const uint8_t x_inv[32]) {
     if (!c || !x || !x_inv) return fail(SIPP_ERR_ARG, "null argument");
     if (c->n < 2) return fail(SIPP_ERR_ARG, "fold needs n >= 2");
+    if (c->pending_validation) CK(cudaStreamWaitEvent(g_stream, c->validated, 0));  // the deferred check reads the points folded here
     if (c->mt.n) return mat_fold(c, c->mt, x, x_inv);  // :60-74 on the matrix of the stage in progress
     size_t h = c->n / 2;
     FoldPlan plan;
@@ -958,11 +1017,12 @@ int sipp_prove_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t b
     AbsorbJob job;
     job.start(A, B, a_len);
     sipp_ctx* c;
-    rc = sipp_ctx_create(A, B, a_len, &c);
+    rc = ctx_create_ex(A, B, a_len, &c, true);  // the point validation runs beside the first kernels; its verdict is collected below
     if (rc) return rc;
     rc = prove_core(c, job, proof);
+    const int vrc = ctx_finish_validation(c);
     sipp_ctx_destroy(c);
-    return rc;
+    return vrc ? vrc : rc;
 }
 
 int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t b_len, const uint8_t* proof, size_t proof_len, uint8_t* final_A,

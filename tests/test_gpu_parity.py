@@ -330,7 +330,7 @@ def test_matrix_tail_thresholds(sipp, oracle):
                     got = b"".join(sipp.sipp_prove_native(A[:64 * m], B[:128 * m]))
                     assert got == (want if m == 64 else oracle.sipp_prove(A[:64 * m], B[:128 * m], threads=4)), (first, thr, m)
         sipp.set_option(_lib.OPT_MATRIX_FIRST, 1)
-        sipp.set_option(_lib.OPT_MATRIX_TAIL, 16)
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 32)
         # stages with the 16-lane line engine switched off (found by tools/fuzz_single.py: the matrix build must not take its
         # throughput path for single-point blocks)
         sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 0)
@@ -345,7 +345,7 @@ def test_matrix_tail_thresholds(sipp, oracle):
     finally:
         sipp.set_option(_lib.OPT_FE_NORMALISATION, 0)
         sipp.set_option(_lib.OPT_WIDE_LINES_MAX, 8192)
-        sipp.set_option(_lib.OPT_MATRIX_TAIL, 16)
+        sipp.set_option(_lib.OPT_MATRIX_TAIL, 32)
         sipp.set_option(_lib.OPT_MATRIX_BLOCK_N, 256)
         sipp.set_option(_lib.OPT_MATRIX_BLOCK_R, 8)
         sipp.set_option(_lib.OPT_MATRIX_FIRST, 1)

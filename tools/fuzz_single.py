@@ -10,7 +10,7 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 t0 = time.time()
 defaults = ((_lib.OPT_PIPELINE, 1), (_lib.OPT_FE_ENGINE, 1), (_lib.OPT_WIDE_LINES_MAX, 8192), (_lib.OPT_WIDE_FOLD_MAX, 256), (_lib.OPT_WIDE_ACCUM_MAX, 1536),
-            (_lib.OPT_MATRIX_TAIL, 16), (_lib.OPT_MATRIX_BLOCK_N, 256), (_lib.OPT_MATRIX_BLOCK_R, 8), (_lib.OPT_MATRIX_FIRST, 1))
+            (_lib.OPT_MATRIX_TAIL, 32), (_lib.OPT_MATRIX_BLOCK_N, 256), (_lib.OPT_MATRIX_BLOCK_R, 8), (_lib.OPT_MATRIX_FIRST, 1))
 for it in range(iters):
     n = 1 << rng.randrange(0, 10 if it % 8 == 0 else 7)
     seed = rng.randrange(1, 1 << 40)
