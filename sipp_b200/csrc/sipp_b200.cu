@@ -1041,7 +1041,7 @@ int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t 
     AbsorbJob job;
     job.start(A, B, n);
     sipp_ctx* c;
-    rc = sipp_ctx_create(A, B, n, &c);
+    rc = ctx_create_ex(A, B, n, &c, true);  // point validation beside the transcript replay; verdict collected before the result
     if (rc) return rc;
     g_stats.transcript_ms += job.join();
     sipp_transcript& tr = job.tr;
@@ -1107,7 +1107,9 @@ int sipp_verify_native(const uint8_t* A, size_t a_len, const uint8_t* B, size_t 
     uint8_t fa[64], fb[128], e[384];
     if (!rc) rc = sipp_ctx_read(c, fa, fb);                                   // final_A: A[0], final_B: B[0]   :74-75
     if (!rc) rc = sipp_ctx_inner_product(c, e);                               // pairing(final_A, final_B)      :80
+    const int vrc = ctx_finish_validation(c);                                 // G1Affine::new / G2Affine::new of the inputs
     sipp_ctx_destroy(c);
+    if (vrc) return vrc;
     if (rc) return rc;
     if (final_A) memcpy(final_A, fa, 64);
     if (final_B) memcpy(final_B, fb, 128);
