@@ -1,9 +1,9 @@
-// k_mat.cu -- the pairing-matrix tail of a single proof.
+// k_mat.cu -- pairing-matrix stages of a single proof (host side: sipp_b200.cu mat_*; stage kinds and sizes: DESIGN.md section 4).
 //
-// The last rounds of /root/reference/src/prover_native.rs:45-75 are a strictly serial chain of tiny launches: fold the points
+// The rounds of /root/reference/src/prover_native.rs:45-75 are a strictly serial chain of small launches: fold the points
 // (:60-69), run the Miller loops of Z_L, Z_R (:48-49), exponentiate, hash, next challenge -- 2.7 ms per round on a GPU that is
-// almost empty.  Once only n <= 32 points are left the chain is cut by bilinearity: with E[i][j] = e(A_i, B_j) for ALL n^2
-// pairs (one launch set, the GPU has room),
+// almost empty.  The chain is cut by bilinearity: with E[i][j] = e(A_i, B_j) for ALL pairs of the n points left -- or, with blocks
+// of m points as "virtual points", E[i][j] = prod_t e(A[i m + t], B[j m + t]) -- computed in one launch set (the GPU has room),
 //     Z_L = prod_{i<h} E[i+h][i],   Z_R = prod_{i<h} E[i][i+h]                                            (h = n / 2)
 // and the fold A'_i = A_i + x A_{i+h}, B'_j = B_j + x^-1 B_{j+h} carries over to the matrix,
 //     E'[i][j] = e(A'_i, B'_j) = E[i][j] * E[i+h][j+h] * E[i+h][j]^x * E[i][j+h]^(x^-1),
