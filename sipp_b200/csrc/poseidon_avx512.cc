@@ -18,7 +18,8 @@
 // Measured on the GPU box's Xeon (3.79 GHz, tools/probe/run_poseidon_lab.sh): 1.506 -> 1.385 (dot order) -> 1.223 (register MDS)
 // -> 1.18 -> 1.153 (reduction on the carry flag) -> 1.116 (192-bit accumulators pinned in registers by asm blocks) -> 1.065 (the
 // scalar 128 -> 64-bit reduction as one 11-instruction asm block: latency 12.2 -> 10.3 cycles) -> 1.027 (column-form MDS,
-// port-balanced vector product) -> 1.012 us per permutation (a partial round as three hand-allocated asm blocks).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
+// port-balanced vector product) -> 1.012 (a partial round as three hand-allocated asm blocks) -> 1.004 us per permutation (the
+// two carries of the MDS recombination decided in parallel).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
 // 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
 #include <immintrin.h>
 #include <stdint.h>
@@ -224,14 +225,15 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     }
     const __m512i eps = lo32;
     auto combine = [&](__m512i alo, __m512i ahi) SIPP_AVX512 {  // < 2^43 each; value = alo + 2^32 ahi
+        // the carry of alo + (ahi << 32) and the carry of adding (ahi >> 32) (2^32 - 1) are decided in parallel (they exclude each
+        // other: a wrapped low word is < 2^43), each worth one + EPS
         __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
-        __mmask8 c = _mm512_cmplt_epu64_mask(lo, alo);
         __m512i hi = _mm512_srli_epi64(ahi, 32);
-        hi = _mm512_mask_add_epi64(hi, c, hi, _mm512_set1_epi64(1));
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);  // hi * (2^32 - 1), hi < 2^12
+        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);  // hi * (2^32 - 1), hi < 2^11
         __m512i r = _mm512_add_epi64(lo, m);
+        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
         __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        return _mm512_mask_add_epi64(r, c2, r, eps);
+        return _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
     };
     s0 = combine(_mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(al[0], al[1]), _mm512_add_pd(al[2], al[3]))),
                  _mm512_cvtpd_epu64(_mm512_add_pd(_mm512_add_pd(ah[0], ah[1]), _mm512_add_pd(ah[2], ah[3]))));
