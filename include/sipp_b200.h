@@ -300,6 +300,11 @@ int sipp_test_transcript_round_device(uint64_t *states, const uint8_t *fq12s, in
 /* host copy of the binary Fr inversion used by the device transcript (glv_core.h): 0 ok, -1 x >= r, -2 x == 0; no GPU needed */
 int sipp_test_fr_inverse_binary(const uint8_t x[32], uint8_t out[32]);
 int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);
+/* host Poseidon self-checks (no GPU): a chain of `count` permutations by the AVX-512 and the portable code side by side, index of the
+ * first mismatch or -1; the scalar helpers of the AVX-512 file on crafted operands (which = 0: (in[0] + 2^64 in[1]) mod p; 1: the closing
+ * multiply-add of a partial round, in = lo, hi, top, p7, m00; 2: out[0] = in[0]^7, out[1] = in[0]^7 + in[1]); -1 without AVX-512 */
+long sipp_test_poseidon_chain(uint64_t seed, long count);
+int sipp_test_poseidon_scalar(int which, const uint64_t *in, uint64_t *out);
 /* the derived tables of the host Poseidon (sipp::PoseidonFastTables, poseidon_fast.h), for tools/probe/poseidon_lab.cc */
 const void *sipp_test_poseidon_tables(void);
 

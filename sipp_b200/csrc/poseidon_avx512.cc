@@ -380,6 +380,20 @@ SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTable
     memcpy(s, buf, 96);
 }
 
+// test hooks for the scalar helpers (their cold fix-up paths -- a borrow of probability 2^-32 -- are not reachable by random
+// permutations; tests/test_host_cpu.py feeds them crafted operands)
+SIPP_AVX512 uint64_t poseidon_test_red128(uint64_t lo, uint64_t hi) { return s_red128(lo, hi); }
+SIPP_AVX512 uint64_t poseidon_test_finish(uint64_t lo, uint64_t hi, uint64_t top, uint64_t p7, uint64_t m00) { return pr_finish(lo, hi, top, p7, m00); }
+SIPP_AVX512 uint64_t poseidon_test_sbox(uint64_t u, uint64_t post, uint64_t* x_out) {
+    PartialRound pr;
+    memset(&pr, 0, sizeof pr);
+    pr.post = post;
+    uint64_t p7, x;
+    pr_sbox(&pr, u, p7, x);
+    *x_out = x;
+    return p7;
+}
+
 bool poseidon_avx512_supported() {
     return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vl") &&
            __builtin_cpu_supports("bmi2");
@@ -389,6 +403,9 @@ bool poseidon_avx512_supported() {
 #else
 namespace sipp {
 void poseidon_permute_avx512(uint64_t*, const PoseidonFastTables&) {}
+uint64_t poseidon_test_red128(uint64_t, uint64_t) { return 0; }
+uint64_t poseidon_test_finish(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
+uint64_t poseidon_test_sbox(uint64_t, uint64_t, uint64_t*) { return 0; }
 bool poseidon_avx512_supported() { return false; }
 }  // namespace sipp
 #endif

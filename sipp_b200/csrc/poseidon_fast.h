@@ -34,5 +34,9 @@ struct PoseidonFastTables {
 
 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T);
 bool poseidon_avx512_supported();
+// test hooks (poseidon_avx512.cc)
+uint64_t poseidon_test_red128(uint64_t lo, uint64_t hi);
+uint64_t poseidon_test_finish(uint64_t lo, uint64_t hi, uint64_t top, uint64_t p7, uint64_t m00);
+uint64_t poseidon_test_sbox(uint64_t u, uint64_t post, uint64_t* x_out);
 
 }  // namespace sipp

@@ -281,7 +281,33 @@ void sipp_poseidon_permute(uint64_t s[12]) {
     else sipp_poseidon_permute_portable(s);
 }
 int sipp_poseidon_backend(void) { return g_use_avx512 ? 1 : 0; }
-const void* sipp_test_poseidon_tables(void) { return &g_tab; }  // benchmark hook: tools/probe/poseidon_lab.cc times the layers
+const void* sipp_test_poseidon_tables(void) { return &g_tab; }
+// a chain of `count` permutations run by the AVX-512 and the portable code side by side; returns the index of the first
+// permutation whose outputs differ, -1 if none (or if the CPU has no AVX-512).  The rare carry paths of the vector code need
+// ~10^5 permutations to show up, which is too slow through ctypes one call at a time.
+long sipp_test_poseidon_chain(uint64_t seed, long count) {
+    if (!g_use_avx512) return -1;
+    uint64_t a[12], b[12];
+    uint64_t z = seed;
+    for (int i = 0; i < 12; i++) { z = z * 6364136223846793005ull + 1442695040888963407ull; a[i] = b[i] = z; }
+    for (long k = 0; k < count; k++) {
+        sipp::poseidon_permute_avx512(a, g_tab);
+        sipp_poseidon_permute_portable(b);
+        for (int i = 0; i < 12; i++)
+            if (a[i] != b[i]) return k;
+        if ((k & 1023) == 1023) { a[k % 12] = b[k % 12] = ~a[(k + 5) % 12]; }  // also non-canonical lanes now and then
+    }
+    return -1;
+}
+// scalar helpers of the AVX-512 file with crafted operands: which = 0 (lo + 2^64 hi) mod p; 1 the closing multiply-add + reduction of a
+// partial round ((lo + 2^64 hi + 2^128 top) + p7 m00) mod p; 2 u^7 (out[0]) and u^7 + post (out[1])
+int sipp_test_poseidon_scalar(int which, const uint64_t* in, uint64_t* out) {
+    if (!sipp::poseidon_avx512_supported()) return -1;
+    if (which == 0) out[0] = sipp::poseidon_test_red128(in[0], in[1]);
+    else if (which == 1) out[0] = sipp::poseidon_test_finish(in[0], in[1], in[2], in[3], in[4]);
+    else out[0] = sipp::poseidon_test_sbox(in[0], in[1], &out[1]);
+    return 0;
+}  // benchmark hook: tools/probe/poseidon_lab.cc times the layers
 
 void sipp_transcript_new(sipp_transcript* t) { memset(t, 0, sizeof *t); }
 

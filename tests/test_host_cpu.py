@@ -172,6 +172,46 @@ def test_poseidon_avx512_matches_portable():
         st = list(a)
 
 
+def test_poseidon_avx512_rare_paths():
+    """the carry paths of the vector code show up once in ~10^5 permutations, the borrow fix-ups of the scalar asm blocks once in
+    2^32 calls: a 400,000-permutation chain against the portable code inside the library, and crafted operands for the blocks"""
+    import random
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    lib.sipp_test_poseidon_chain.argtypes = [ctypes.c_uint64, ctypes.c_long]
+    lib.sipp_test_poseidon_chain.restype = ctypes.c_long
+    lib.sipp_test_poseidon_scalar.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    if lib.sipp_poseidon_backend() != 1:
+        pytest.skip("no AVX-512 on this CPU")
+    assert lib.sipp_test_poseidon_chain(12345, 400000) == -1
+    PG, M = 2**64 - 2**32 + 1, 2**64 - 1
+    rng = random.Random(5)
+
+    def call(which, *ins):
+        a = (ctypes.c_uint64 * 5)(*(list(ins) + [0] * (5 - len(ins))))
+        o = (ctypes.c_uint64 * 2)()
+        assert lib.sipp_test_poseidon_scalar(which, a, o) == 0
+        return o[0], o[1]
+
+    edge = [0, 1, 2**32 - 1, 2**32, 2**63, PG - 1, PG, M, M - 2**32, 0xFFFFFFFF00000000, 0x00000000FFFFFFFF]
+    pairs = [(lo, hi) for lo in edge for hi in edge] + [(rng.randrange(2**64), rng.randrange(2**64)) for _ in range(2000)]
+    pairs += [(rng.randrange(2**20), (0xFFFFFFFF << 32) | rng.randrange(2**32)) for _ in range(200)]      # lo < hi >> 32: the borrow fix-up
+    for lo, hi in pairs:
+        assert call(0, lo, hi)[0] % PG == ((hi << 64) + lo) % PG, (hex(lo), hex(hi))
+    for _ in range(3000):
+        lo, hi, top = rng.choice(edge + [rng.randrange(2**64)]), rng.choice(edge + [rng.randrange(2**64)]), rng.randrange(14)
+        if rng.random() < 0.2:
+            lo, hi = rng.randrange(2**16), 0                                                                # small sum, large top: the second fix-up
+        p7, m00 = rng.choice(edge + [rng.randrange(2**64)]), rng.randrange(PG)
+        if ((hi << 64) + lo + p7 * m00) >> 128:
+            continue                                                                                          # the caller's sum stays below 2^128 + top
+        assert call(1, lo, hi, top, p7, m00)[0] % PG == ((top << 128) + (hi << 64) + lo + p7 * m00) % PG
+    for u in edge + [rng.randrange(2**64) for _ in range(2000)]:
+        post = rng.choice([0, 1, PG - 1, rng.randrange(PG)])
+        p7, x = call(2, u, post)
+        assert p7 % PG == pow(u, 7, PG) and x % PG == (pow(u, 7, PG) + post) % PG, hex(u)
+
+
 def test_statement_public_input_vector(golden):
     """SIPPStatement <-> the u32 vector of statements.rs:133-170 (what the untouched plonky2 circuit consumes): layout, the
     MyFq12 coefficient order (against the independent pure-Python model) and the round trip"""
