@@ -321,6 +321,197 @@ SIPP_AVX512 inline void v_full_round(__m512i& s0, __m512i& s1, const uint64_t* r
     v_mds(s0, s1, T);
 }
 
+
+// ------------------------------------------------------------------------------------------------ IFMA path
+// Partial rounds with every rank-1 update unrolled algebraically (tables: poseidon_fast.h, PoseidonIfmaTables).  The scalar ports
+// run nothing but the dependent chain -- S-box, one multiply-add by m00, a 5-instruction reduction -- plus, off the chain, one
+// row close per round (recombine the three accumulator lanes of C-row j + 1, add its newest term, reduce); every other product of
+// the 22 rounds (330 for the initial matrix, 450 for the x_k terms) is a vpmadd52 lane on the vector ports, seven instructions per
+// eight 64 x 64-bit products, with ONE reduction per row at the very end instead of one per product.
+#define SIPP_IFMA __attribute__((target("avx512f,avx512dq,avx512vl,avx512ifma,bmi2,adx")))
+struct IfmaBlock { __m512i a0, a1, a2; };
+// acc += x * c over eight lanes: x = xl + 2^52 xh, c = cl + 2^52 ch (vpmadd52 reads the low 52 bits of its operands)
+SIPP_IFMA inline void ifma_unit(IfmaBlock& A, __m512i xb, __m512i xh, const uint64_t* c) {
+    const __m512i cl = _mm512_load_si512(c), ch = _mm512_load_si512(c + 8);
+    A.a0 = _mm512_madd52lo_epu64(A.a0, xb, cl);
+    A.a1 = _mm512_madd52hi_epu64(A.a1, xb, cl);
+    A.a2 = _mm512_madd52hi_epu64(A.a2, xb, ch);
+    A.a1 = _mm512_madd52lo_epu64(A.a1, xb, ch);
+    A.a2 = _mm512_madd52hi_epu64(A.a2, xh, cl);
+    A.a1 = _mm512_madd52lo_epu64(A.a1, xh, cl);
+    A.a2 = _mm512_madd52lo_epu64(A.a2, xh, ch);
+}
+SIPP_IFMA inline void ifma_store(uint64_t* sc, const IfmaBlock& A) {
+    _mm512_store_si512(sc, A.a0);
+    _mm512_store_si512(sc + 8, A.a1);
+    _mm512_store_si512(sc + 16, A.a2);
+}
+// (a0 + 2^52 a1 - 2^8 a2 + c x) mod p: one lane of an accumulator block (2^104 = -2^8; the row constant carries a + p, so the
+// subtraction cannot borrow) plus the newest term of the row
+SIPP_IFMA inline uint64_t row_close(uint64_t a0, uint64_t a1, uint64_t a2, uint64_t c, uint64_t x) {
+    unsigned long long t, pl, ph, top;
+    const uint64_t eps = EPS;
+    asm("mov %[a1], %[t]\n\t" "shl $52, %[t]\n\t" "shr $12, %[a1]\n\t" "add %[t], %[a0]\n\t" "adc $0, %[a1]\n\t"
+        "shl $8, %[a2]\n\t" "sub %[a2], %[a0]\n\t" "sbb $0, %[a1]\n\t"
+        "xor %k[top], %k[top]\n\t"
+        "mulx %[c], %[pl], %[ph]\n\t" "add %[pl], %[a0]\n\t" "adc %[ph], %[a1]\n\t" "adc $0, %[top]\n\t"
+        "mov %[a1], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[a1], %k[a1]\n\t" "sub %[t], %[a0]\n\t" "jc 31f\n" "30:\n\t"
+        "mov %[a1], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[a1], %[t]\n\t" "add %[t], %[a0]\n\t" "lea (%[a0],%[eps]), %[t]\n\t" "cmovc %[t], %[a0]\n\t"
+        "shl $32, %[top]\n\t" "sub %[top], %[a0]\n\t" "jc 33f\n" "32:\n\t"
+        ".subsection 1\n"
+        "31:\n\t" "sub %[eps], %[a0]\n\t" "jmp 30b\n"
+        "33:\n\t" "sub %[eps], %[a0]\n\t" "jmp 32b\n"
+        ".previous"
+        : [a0] "+r"(a0), [a1] "+r"(a1), [a2] "+r"(a2), [t] "=&r"(t), [pl] "=&r"(pl), [ph] "=&r"(ph), [top] "=&r"(top)
+        : [c] "rm"(c), "d"(x), [eps] "r"(eps)
+        : "cc");
+    return a0;
+}
+// u^7, three dependent products (the S-box block of pr_sbox without the constant)
+SIPP_IFMA inline uint64_t sbox7(uint64_t u) {
+    unsigned long long a, b, h, t;
+    const uint64_t eps = EPS;
+    asm("mov %[u], %%rdx\n\t" "mulx %[u], %[a], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[a]\n\t" "jc 41f\n" "40:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]\n\t"
+        "mulx %[a], %[b], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[b]\n\t" "jc 43f\n" "42:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[b]\n\t" "lea (%[b],%[eps]), %[t]\n\t" "cmovc %[t], %[b]\n\t"
+        "mov %[a], %%rdx\n\t" "mulx %[a], %[a], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[a]\n\t" "jc 45f\n" "44:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]\n\t"
+        "mov %[b], %%rdx\n\t" "mulx %[a], %[a], %[h]\n\t"
+        "mov %[h], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[h], %k[h]\n\t" "sub %[t], %[a]\n\t" "jc 47f\n" "46:\n\t"
+        "mov %[h], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[h], %[t]\n\t" "add %[t], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]\n\t"
+        ".subsection 1\n"
+        "41:\n\t" "sub %[eps], %[a]\n\t" "jmp 40b\n"
+        "43:\n\t" "sub %[eps], %[b]\n\t" "jmp 42b\n"
+        "45:\n\t" "sub %[eps], %[a]\n\t" "jmp 44b\n"
+        "47:\n\t" "sub %[eps], %[a]\n\t" "jmp 46b\n"
+        ".previous"
+        : [a] "=&r"(a), [b] "=&r"(b), [h] "=&r"(h), [t] "=&r"(t)
+        : [u] "r"(u), [eps] "r"(eps)
+        : "rdx", "cc");
+    return a;
+}
+// (e + z7) mod 2^64-representative: one wrap correction
+SIPP_IFMA inline uint64_t chain_close(uint64_t e, uint64_t z7) {
+    unsigned long long t;
+    const uint64_t eps = EPS;
+    asm("add %[z7], %[e]\n\t" "lea (%[e],%[eps]), %[t]\n\t" "cmovc %[t], %[e]" : [e] "+r"(e), [t] "=&r"(t) : [z7] "r"(z7), [eps] "r"(eps) : "cc");
+    return e;
+}
+// all eight lanes of a block closed at once: (a0 + 2^52 a1 - 2^8 a2) mod p
+SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
+    const __m512i one = _mm512_set1_epi64(1);
+    __m512i t = _mm512_slli_epi64(A.a1, 52);
+    __m512i lo = _mm512_add_epi64(A.a0, t);
+    __mmask8 c = _mm512_cmplt_epu64_mask(lo, t);
+    __m512i hi = _mm512_srli_epi64(A.a1, 12);
+    hi = _mm512_mask_add_epi64(hi, c, hi, one);
+    __m512i s = _mm512_slli_epi64(A.a2, 8);
+    __mmask8 b = _mm512_cmplt_epu64_mask(lo, s);
+    lo = _mm512_sub_epi64(lo, s);
+    hi = _mm512_mask_sub_epi64(hi, b, hi, one);
+    return v_reduce(lo, hi);
+}
+
+}  // namespace
+
+SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T, const PoseidonIfmaTables& I) {
+    alignas(64) uint64_t buf[16];
+    memcpy(buf, s, 96);
+    buf[12] = buf[13] = buf[14] = buf[15] = 0;
+    __m512i s0 = _mm512_load_si512(buf), s1 = _mm512_load_si512(buf + 8);
+    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[k], T);
+
+    s0 = v_add_canon(s0, _mm512_load_si512(T.first));
+    s1 = v_add_canon(s1, _mm512_load_si512(T.first + 8));
+    alignas(64) uint64_t y[16], yh[16];
+    _mm512_store_si512(y, s0);
+    _mm512_store_si512(y + 8, s1);
+    _mm512_store_si512(yh, _mm512_srli_epi64(s0, 52));
+    _mm512_store_si512(yh + 8, _mm512_srli_epi64(s1, 52));
+    IfmaBlock A[4];
+#pragma GCC unroll 4
+    for (int b = 0; b < 4; b++) {
+        A[b].a0 = _mm512_load_si512(I.acc_init[b][0]);
+        A[b].a1 = _mm512_load_si512(I.acc_init[b][1]);
+        A[b].a2 = _mm512_setzero_si512();
+    }
+    // the y part of a row block: 11 units; block 0 now, the others spread over the rounds that precede their first use
+    auto init_unit = [&](int i, int b) SIPP_IFMA { ifma_unit(A[b], _mm512_set1_epi64((long long)y[1 + i]), _mm512_set1_epi64((long long)yh[1 + i]), I.init_c[i][b][0]); };
+#pragma GCC unroll 11
+    for (int i = 0; i < 11; i++) init_unit(i, 0);
+    uint64_t u0 = y[0];
+    uint64_t e;
+    {
+        Acc192 a = s_dot11_raw(I.row0, y + 1);
+        acc_add(a, I.k0);
+        e = acc_reduce(a);
+    }
+    uint64_t p7_prev = 0;
+    auto lane_of = [](const IfmaBlock& B, int lane, uint64_t& a0, uint64_t& a1, uint64_t& a2) SIPP_IFMA {
+        alignas(64) uint64_t t[24];
+        ifma_store(t, B);
+        a0 = t[lane]; a1 = t[8 + lane]; a2 = t[16 + lane];
+    };
+#pragma GCC unroll 22
+    for (int j = 0; j < 22; j++) {
+        const uint64_t p7 = sbox7(u0);
+        u0 = chain_close(e, p7);  // z_{j+1}
+        if (j >= 1) {  // the vector terms of x_{j-1}: behind the chain of this round in program order, so the chain is served first
+            const int k = j - 1;
+            const __m512i xb = _mm512_set1_epi64((long long)p7_prev), xh = _mm512_set1_epi64((long long)(p7_prev >> 52));
+            if (k <= 6) ifma_unit(A[0], xb, xh, I.upd_c[k][0][0]);
+            if (k <= 14) ifma_unit(A[1], xb, xh, I.upd_c[k][1][0]);
+            ifma_unit(A[2], xb, xh, I.upd_c[k][2][0]);
+            ifma_unit(A[3], xb, xh, I.upd_c[k][3][0]);
+        }
+        {
+            const int blk = j <= 5 ? 1 : (j >= 7 && j <= 12) ? 2 : (j >= 13 && j <= 18) ? 3 : 0;
+            const int base = j <= 5 ? 0 : j <= 12 ? 7 : 13;
+            if (blk) {
+                const int i0 = 2 * (j - base);
+                init_unit(i0, blk);
+                if (i0 + 1 < 11) init_unit(i0 + 1, blk);
+            }
+        }
+        if (j + 1 <= 21) {  // close C-row j + 1: vector terms k <= j - 1, newest term x_j
+            const int row = j + 1, b = row <= 8 ? 0 : row <= 16 ? 1 : row <= 20 ? 2 : 3;
+            const int lane = row <= 8 ? row - 1 : row <= 16 ? row - 9 : row <= 20 ? row - 13 : 0;
+            uint64_t a0, a1, a2;
+            lane_of(A[b], lane, a0, a1, a2);
+            e = row_close(a0, a1, a2, I.cdiag[row], p7);
+        }
+        p7_prev = p7;
+    }
+    {
+        const __m512i xb = _mm512_set1_epi64((long long)p7_prev), xh = _mm512_set1_epi64((long long)(p7_prev >> 52));
+        ifma_unit(A[2], xb, xh, I.upd_c[21][2][0]);
+        ifma_unit(A[3], xb, xh, I.upd_c[21][3][0]);
+    }
+    s0 = _mm512_mask_set1_epi64(v_close(A[3]), 1, (long long)s_mul(u0, I.lam22));
+    s1 = v_close(A[2]);
+    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[4 + k], T);
+    s0 = v_canon(s0);
+    s1 = v_canon(s1);
+    _mm512_store_si512(buf, s0);
+    _mm512_store_si512(buf + 8, s1);
+    memcpy(s, buf, 96);
+}
+bool poseidon_ifma_supported() { return poseidon_avx512_supported() && __builtin_cpu_supports("avx512ifma"); }
+SIPP_IFMA void poseidon_test_ifma_close(const uint64_t in[5], uint64_t out[2]) {
+    out[0] = row_close(in[0], in[1], in[2], in[3], in[4]);
+    IfmaBlock B;
+    B.a0 = _mm512_set1_epi64((long long)in[0]);
+    B.a1 = _mm512_set1_epi64((long long)in[1]);
+    B.a2 = _mm512_set1_epi64((long long)in[2]);
+    alignas(64) uint64_t t[8];
+    _mm512_store_si512(t, v_close(B));
+    out[1] = t[3];
+}
+namespace {
 }  // namespace
 
 SIPP_AVX512 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T) {
@@ -403,6 +594,9 @@ bool poseidon_avx512_supported() {
 #else
 namespace sipp {
 void poseidon_permute_avx512(uint64_t*, const PoseidonFastTables&) {}
+void poseidon_permute_ifma(uint64_t*, const PoseidonFastTables&, const PoseidonIfmaTables&) {}
+bool poseidon_ifma_supported() { return false; }
+void poseidon_test_ifma_close(const uint64_t*, uint64_t*) {}
 uint64_t poseidon_test_red128(uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_finish(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_sbox(uint64_t, uint64_t, uint64_t*) { return 0; }

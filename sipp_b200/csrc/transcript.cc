@@ -185,10 +185,74 @@ void init_fast_partial() {
     }
 }
 sipp::PoseidonFastTables g_tab;
+sipp::PoseidonIfmaTables g_ifma;
 bool g_use_avx512 = false;
+bool g_use_ifma = false;
+
+uint64_t gl_dot11(const uint64_t* a, const uint64_t* b) {
+    uint64_t acc = 0;
+    for (int i = 0; i < 11; i++) acc = gl_add(acc, gl_mul(a[i], b[i]));
+    return gl_canon(acc);
+}
+// tables of the algebraically unrolled partial rounds (layout and derivation: poseidon_fast.h)
+void init_ifma_tables() {
+    memset(&g_ifma, 0, sizeof g_ifma);
+    // lane -> row: C-row j as j (0..21), U-row i as 32 + i
+    auto row_of = [](int b, int l) { return b == 0 ? 1 + l : b == 1 ? 9 + l : b == 2 ? (l < 4 ? 32 + 7 + l : 13 + l) : (l == 0 ? 21 : 32 + l - 1); };
+    // the chain runs on z_j = u0_j / lam_j with lam_0 = 1, lam_{j+1} = m00 lam_j^7: then z_{j+1} = z_j^7 + R_j / lam_{j+1}, the product by
+    // m00 has left the dependent chain; the S-box outputs the vector side sees are z_k^7 = p7_k / lam_k^7
+    uint64_t lam[23], lam7[22], lam_inv[23];
+    lam[0] = 1;
+    for (int j = 0; j < 22; j++) {
+        lam7[j] = gl_canon(gl_pow7(lam[j]));
+        lam[j + 1] = gl_canon(gl_mul(g_fp.m00, lam7[j]));
+    }
+    for (int j = 0; j < 23; j++) lam_inv[j] = gl_inv(lam[j]);
+    auto row_scale = [&](int row) -> uint64_t { return row < 32 ? lam_inv[row + 1] : 1; };
+    auto raw_y = [&](int row, int i) -> uint64_t {  // coefficient of y[1 + i]
+        if (row >= 32) return g_fp.init[row - 32][i];
+        uint64_t acc = 0;
+        for (int m = 0; m < 11; m++) acc = gl_add(acc, gl_mul(g_fp.vhat[row][m], g_fp.init[m][i]));
+        return gl_canon(acc);
+    };
+    auto raw_x = [&](int row, int k) -> uint64_t {  // coefficient of x_k = p7_k + post_k (every k < row for a C-row)
+        if (row >= 32) return g_fp.w[k][row - 32];
+        return k < row ? gl_dot11(g_fp.vhat[row], g_fp.w[k]) : 0;
+    };
+    auto coef_y = [&](int row, int i) -> uint64_t { return gl_canon(gl_mul(raw_y(row, i), row_scale(row))); };
+    auto coef_x = [&](int row, int k) -> uint64_t { return gl_canon(gl_mul(gl_mul(raw_x(row, k), lam7[k]), row_scale(row))); };
+    auto konst = [&](int row) -> uint64_t {  // the post part of every term
+        uint64_t acc = row < 32 ? gl_mul(g_fp.m00, g_fp.post[row]) : 0;
+        for (int k = 0; k < 22; k++) acc = gl_add(acc, gl_mul(raw_x(row, k), g_fp.post[k]));
+        return gl_canon(gl_mul(acc, row_scale(row)));
+    };
+    const uint64_t M52 = (1ull << 52) - 1;
+    for (int b = 0; b < 4; b++)
+        for (int l = 0; l < 8; l++) {
+            const int row = row_of(b, l);
+            const uint64_t K = konst(row);
+            g_ifma.acc_init[b][0][l] = (K & M52) + (GL_P & M52);
+            g_ifma.acc_init[b][1][l] = (K >> 52) + (GL_P >> 52);
+            for (int i = 0; i < 11; i++) {
+                const uint64_t c = coef_y(row, i);
+                g_ifma.init_c[i][b][0][l] = c;
+                g_ifma.init_c[i][b][1][l] = c >> 52;
+            }
+            for (int k = 0; k < 22; k++) {
+                const uint64_t c = (row < 32 && k > row - 2) ? 0 : coef_x(row, k);  // the newest term of a C-row is a scalar multiply-add
+                g_ifma.upd_c[k][b][0][l] = c;
+                g_ifma.upd_c[k][b][1][l] = c >> 52;
+            }
+        }
+    for (int i = 0; i < 11; i++) g_ifma.row0[i] = coef_y(0, i);
+    g_ifma.k0 = konst(0);
+    for (int j = 1; j < 22; j++) g_ifma.cdiag[j] = coef_x(j, j - 1);
+    g_ifma.lam22 = lam[22];
+}
 struct FastPartialInit {
     FastPartialInit() {
         init_fast_partial();
+        init_ifma_tables();
         memset(&g_tab, 0, sizeof g_tab);
         for (int k = 0; k < 8; k++)
             for (int i = 0; i < 12; i++) g_tab.rc_full[k][i] = SIPP_POSEIDON_RC[12 * (k < 4 ? k : 22 + k) + i];
@@ -220,6 +284,7 @@ struct FastPartialInit {
         }
         const char* force = getenv("SIPP_POSEIDON");  // "portable" forces the scalar path (tests compare both)
         g_use_avx512 = sipp::poseidon_avx512_supported() && !(force && !strcmp(force, "portable"));
+        g_use_ifma = g_use_avx512 && sipp::poseidon_ifma_supported() && !(force && !strcmp(force, "avx512"));  // "avx512": the path without IFMA
     }
 } g_fp_init;
 
@@ -277,35 +342,44 @@ void sipp_poseidon_permute_portable(uint64_t s[12]) {
 }
 
 void sipp_poseidon_permute(uint64_t s[12]) {
-    if (g_use_avx512) sipp::poseidon_permute_avx512(s, g_tab);
+    if (g_use_ifma) sipp::poseidon_permute_ifma(s, g_tab, g_ifma);
+    else if (g_use_avx512) sipp::poseidon_permute_avx512(s, g_tab);
     else sipp_poseidon_permute_portable(s);
 }
-int sipp_poseidon_backend(void) { return g_use_avx512 ? 1 : 0; }
+int sipp_poseidon_backend(void) { return g_use_ifma ? 2 : g_use_avx512 ? 1 : 0; }
+const void* sipp_test_poseidon_ifma_tables(void) { return &g_ifma; }
 const void* sipp_test_poseidon_tables(void) { return &g_tab; }
 // a chain of `count` permutations run by the AVX-512 and the portable code side by side; returns the index of the first
 // permutation whose outputs differ, -1 if none (or if the CPU has no AVX-512).  The rare carry paths of the vector code need
 // ~10^5 permutations to show up, which is too slow through ctypes one call at a time.
 long sipp_test_poseidon_chain(uint64_t seed, long count) {
-    if (!g_use_avx512) return -1;
-    uint64_t a[12], b[12];
+    if (!sipp::poseidon_avx512_supported()) return -1;
+    const bool ifma = sipp::poseidon_ifma_supported();  // every path this CPU can run, whichever one is selected
+    uint64_t a[12], b[12], c[12];
     uint64_t z = seed;
-    for (int i = 0; i < 12; i++) { z = z * 6364136223846793005ull + 1442695040888963407ull; a[i] = b[i] = z; }
+    for (int i = 0; i < 12; i++) { z = z * 6364136223846793005ull + 1442695040888963407ull; a[i] = b[i] = c[i] = z; }
     for (long k = 0; k < count; k++) {
         sipp::poseidon_permute_avx512(a, g_tab);
+        if (ifma) sipp::poseidon_permute_ifma(c, g_tab, g_ifma);
         sipp_poseidon_permute_portable(b);
         for (int i = 0; i < 12; i++)
-            if (a[i] != b[i]) return k;
-        if ((k & 1023) == 1023) { a[k % 12] = b[k % 12] = ~a[(k + 5) % 12]; }  // also non-canonical lanes now and then
+            if (a[i] != b[i] || (ifma && c[i] != b[i])) return k;
+        if ((k & 1023) == 1023) { a[k % 12] = b[k % 12] = c[k % 12] = ~a[(k + 5) % 12]; }  // also non-canonical lanes now and then
     }
     return -1;
 }
 // scalar helpers of the AVX-512 file with crafted operands: which = 0 (lo + 2^64 hi) mod p; 1 the closing multiply-add + reduction of a
-// partial round ((lo + 2^64 hi + 2^128 top) + p7 m00) mod p; 2 u^7 (out[0]) and u^7 + post (out[1])
+// partial round ((lo + 2^64 hi + 2^128 top) + p7 m00) mod p; 2 u^7 (out[0]) and u^7 + post (out[1]); 3 (IFMA path) the closing of an
+// accumulator lane, in = a0, a1, a2, c, x: out[0] = scalar, out[1] = vector form of (a0 + 2^52 a1 - 2^8 a2 [+ c x]) mod p
 int sipp_test_poseidon_scalar(int which, const uint64_t* in, uint64_t* out) {
     if (!sipp::poseidon_avx512_supported()) return -1;
     if (which == 0) out[0] = sipp::poseidon_test_red128(in[0], in[1]);
     else if (which == 1) out[0] = sipp::poseidon_test_finish(in[0], in[1], in[2], in[3], in[4]);
-    else out[0] = sipp::poseidon_test_sbox(in[0], in[1], &out[1]);
+    else if (which == 2) out[0] = sipp::poseidon_test_sbox(in[0], in[1], &out[1]);
+    else {
+        if (!sipp::poseidon_ifma_supported()) return -1;
+        sipp::poseidon_test_ifma_close(in, out);
+    }
     return 0;
 }  // benchmark hook: tools/probe/poseidon_lab.cc times the layers
 

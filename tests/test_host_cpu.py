@@ -181,9 +181,9 @@ def test_poseidon_avx512_rare_paths():
     lib.sipp_test_poseidon_chain.argtypes = [ctypes.c_uint64, ctypes.c_long]
     lib.sipp_test_poseidon_chain.restype = ctypes.c_long
     lib.sipp_test_poseidon_scalar.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
-    if lib.sipp_poseidon_backend() != 1:
+    if lib.sipp_poseidon_backend() < 1:
         pytest.skip("no AVX-512 on this CPU")
-    assert lib.sipp_test_poseidon_chain(12345, 400000) == -1
+    assert lib.sipp_test_poseidon_chain(12345, 400000) == -1        # AVX-512, IFMA (when the CPU has it) and portable side by side
     PG, M = 2**64 - 2**32 + 1, 2**64 - 1
     rng = random.Random(5)
 
@@ -210,6 +210,25 @@ def test_poseidon_avx512_rare_paths():
         post = rng.choice([0, 1, PG - 1, rng.randrange(PG)])
         p7, x = call(2, u, post)
         assert p7 % PG == pow(u, 7, PG) and x % PG == (pow(u, 7, PG) + post) % PG, hex(u)
+    if lib.sipp_poseidon_backend() == 2:
+        # closing of an IFMA accumulator lane: a0 < 2^59 and a1 < 2^59 (sums of 52-bit halves, a1 >= 4095 from the + p in the row
+        # constant), a2 < 2^32; the borrow of the - 2^8 a2 step (low word of a0 + 2^52 a1 below 2^8 a2) is a 2^-25 event in real data
+        for it in range(4000):
+            a1 = 4095 + rng.randrange(2**58)
+            a2 = rng.randrange(2**32)
+            a0 = rng.randrange(2**58)
+            if it % 4 == 0:                                            # low 64 bits of a0 + 2^52 a1 tiny: force the borrow
+                a1 = (a1 >> 12) << 12
+                a0 = rng.randrange(1 + min(2**20, (a2 << 8)))
+            if it % 4 == 1:                                            # a0 + (a1 << 52) carries out of the low word
+                a1 |= 0xFFF
+                a0 = 2**52 + rng.randrange(2**58)
+            c, x = rng.choice(edge + [rng.randrange(PG)]), rng.choice(edge + [rng.randrange(2**64)])
+            base = a0 + (a1 << 52) - (a2 << 8)
+            assert base >= 0
+            sc, ve = call(3, a0, a1, a2, c, x)
+            assert sc % PG == (base + c * x) % PG, (hex(a0), hex(a1), hex(a2), hex(c), hex(x))
+            assert ve % PG == base % PG, (hex(a0), hex(a1), hex(a2))
 
 
 def test_statement_public_input_vector(golden):

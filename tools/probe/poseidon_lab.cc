@@ -26,6 +26,7 @@ static double now() { return std::chrono::duration<double>(std::chrono::steady_c
 #include POS_IMPL
 using namespace sipp;
 extern "C" const void* sipp_test_poseidon_tables(void);
+extern "C" const void* sipp_test_poseidon_ifma_tables(void);
 #define T256 __attribute__((target("avx512f,avx512dq,avx512vl,bmi2,adx")))
 T256 static inline __m256i w_reduce(__m256i lo, __m256i hi) {
     const __m256i eps = _mm256_set1_epi64x((long long)EPS);
@@ -151,6 +152,18 @@ T512 int main() {
             if (dt < best) best = dt;
         }
         printf("backend %d\n", sipp_poseidon_backend());
+#ifndef LAB_NO_IFMA
+        if (poseidon_ifma_supported()) {
+            double b2 = 1e9;
+            for (int rep = 0; rep < 5; rep++) {
+                double t0 = now();
+                for (int i = 0; i < P; i++) poseidon_permute_ifma(s, *(const PoseidonFastTables*)sipp_test_poseidon_tables(), *(const PoseidonIfmaTables*)sipp_test_poseidon_ifma_tables());
+                double dt = now() - t0;
+                if (dt < b2) b2 = dt;
+            }
+            report("Poseidon permutation (IFMA partial rounds), chained", b2, P);
+        }
+#endif
         report("Poseidon permutation (this variant), chained", best, P);
         { uint64_t a[12], b[12]; for (int i = 0; i < 12; i++) a[i] = b[i] = 0x123456789abcdefull * (i + 3); poseidon_permute_avx512(a, *(const PoseidonFastTables*)sipp_test_poseidon_tables()); sipp_poseidon_permute_portable(b); printf("bit-exact vs portable: %s\n", memcmp(a, b, 96) == 0 ? "yes" : "NO"); }
         best = 1e9;
