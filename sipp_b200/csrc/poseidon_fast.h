@@ -50,6 +50,9 @@ struct alignas(64) PoseidonIfmaTables {
     uint64_t k0;                   // its constant, m00 post_0
     uint64_t cdiag[22];            // cdiag[j]: coefficient of x_{j-1} in C-row j, j = 1..21
     uint64_t lam22;                // u0_22 = lam22 z_22
+    alignas(64) uint64_t mds_icol_a[12][8];  // PoseidonFastTables::mds_col_a / _b as integers (the MDS layer on vpmadd52luq)
+    alignas(64) uint64_t mds_icol_b[12][8];
+    alignas(64) uint64_t mds_icol_p[12][8];  // rows 8..11 for a (low half, high half) pair broadcast: lane l holds the entry of row 8 + l / 2
 };
 
 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T);

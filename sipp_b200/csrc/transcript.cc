@@ -272,6 +272,12 @@ struct FastPartialInit {
                 g_tab.mds_col_a[j][r] = (double)(MDS_CIRC[(j - r + 12) % 12] + ((j == 0 && r == 0) ? 8 : 0));
                 g_tab.mds_col_b[j][r] = (double)MDS_CIRC[(j - 8 - (r & 3) + 24) % 12];
             }
+        for (int j = 0; j < 12; j++)
+            for (int r = 0; r < 8; r++) {
+                g_ifma.mds_icol_a[j][r] = (uint64_t)g_tab.mds_col_a[j][r];
+                g_ifma.mds_icol_b[j][r] = (uint64_t)g_tab.mds_col_b[j][r];
+                g_ifma.mds_icol_p[j][r] = MDS_CIRC[(j - 8 - (r >> 1) + 24) % 12];
+            }
         g_tab.m00 = g_fp.m00;
         for (int r = 0; r < 22; r++) {
             sipp::PartialRound& pr = g_tab.pr[r];

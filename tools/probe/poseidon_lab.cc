@@ -50,6 +50,25 @@ T256 static inline __m256i w_mul(__m256i x, __m256i y) {
     return w_reduce(lo, hi);
 }
 
+#if !defined(LAB_NO_IFMA) && !defined(LAB_NO_IFMA_LAYERS)
+template <class Rep> SIPP_IFMA static void lab_ifma_layers(__m512i& s0, const PoseidonFastTables& T, const PoseidonIfmaTables& I, int R, Rep report) {
+    uint64_t t[4] = {9, 10, 11, 12};
+    double t0 = now();
+    for (int i = 0; i < R; i++) s0 = v_pow7_fast(s0);
+    report("IFMA path: one zmm x^7 (fast product), chained", now() - t0, R);
+    t0 = now();
+    for (int i = 0; i < R; i++) s0 = v_mul_fast(s0, s0);
+    report("IFMA path: fast zmm modmul, chained", now() - t0, R);
+    t0 = now();
+    for (int i = 0; i < R; i++) full_round_mixed(s0, t, T.rc_full[i & 7], I);
+    report("IFMA path: mixed full round, chained", now() - t0, R);
+    __m512i s1 = s0;
+    t0 = now();
+    for (int i = 0; i < R; i++) v_mds_ifma(s0, s1, I);
+    report("IFMA path: MDS layer (2 zmm, vpmadd52), chained", now() - t0, R);
+    printf("  [%llu]\n", (unsigned long long)t[0]);
+}
+#endif
 T512 int main() {
     const int N = 20000000;
     // core clock: dependent 64-bit adds retire one per cycle
@@ -128,6 +147,12 @@ T512 int main() {
         t0 = now();
         for (int i = 0; i < R; i++) v_full_round(s0, s1, T.rc_full[i & 7], T);
         report("full round, chained", now() - t0, R);
+#if !defined(LAB_NO_IFMA) && !defined(LAB_NO_IFMA_LAYERS)
+        if (poseidon_ifma_supported()) {
+            const PoseidonIfmaTables& I = *(const PoseidonIfmaTables*)sipp_test_poseidon_ifma_tables();
+            lab_ifma_layers(s0, T, I, R, report);
+        }
+#endif
         uint64_t u = 12345;
         t0 = now();
         for (int i = 0; i < R; i++) u = s_pow7(u);

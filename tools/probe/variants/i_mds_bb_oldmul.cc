@@ -1,3 +1,5 @@
+#define LAB_MDS_BB 1
+#define LAB_OLD_MODMUL 1
 // poseidon_avx512.cc -- AVX-512 implementation of the plonky2 Poseidon permutation over Goldilocks (width 12).
 //
 // The Fiat-Shamir transcript of the SIPP native protocol (/root/reference/src/transcript_native.rs:25-30) is a strictly
@@ -142,11 +144,6 @@ SIPP_AVX512 inline uint64_t acc_reduce(const Acc192& s) {
     return d;
 }
 
-// The MDS layers below store the state halves and read every one back as a broadcast LOAD (load ports).  Left alone, GCC forwards
-// the stored vectors through registers instead -- vextracti64x2 / valignq / vpbroadcastq chains, all on port 5, ~40 shuffles per
-// layer; this barrier makes the round trip through memory real.
-#define SIPP_THROUGH_MEMORY(ptr) asm volatile("" : "+r"(ptr) : : "memory")
-
 // ------------------------------------------------------------------------------------------------ vector helpers
 SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
     const __m512i eps = _mm512_set1_epi64((long long)EPS);
@@ -216,14 +213,11 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
     _mm512_store_pd(H, _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)));
     _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
-    const double *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
     __m512d al[4], ah[4], ab[4];
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
-        const __m512d bl = _mm512_set1_pd(Lm[j]), bh = _mm512_set1_pd(Hm[j]);
-        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&Hm[j]));
+        const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
+        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
         const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
         if (j < 4) {
             al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
@@ -433,15 +427,12 @@ SIPP_IFMA inline void v_mds_ifma(__m512i& s0, __m512i& s1, const PoseidonIfmaTab
     _mm512_store_si512(L + 8, _mm512_and_si512(s1, lo32));
     _mm512_store_si512(H, _mm512_srli_epi64(s0, 32));
     _mm512_store_si512(H + 8, _mm512_srli_epi64(s1, 32));
-    const uint64_t *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
     __m512i al[4], ah[4], ab[4];
     const __m512i zero = _mm512_setzero_si512();
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
-        const __m512i bl = _mm512_set1_epi64((long long)Lm[j]), bh = _mm512_set1_epi64((long long)Hm[j]);
-        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)Hm[j]);
+        const __m512i bl = _mm512_set1_epi64((long long)L[j]), bh = _mm512_set1_epi64((long long)H[j]);
+        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)H[j]);
         const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cb = _mm512_load_si512(I.mds_icol_b[j]);
         al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
         ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
@@ -526,15 +517,12 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
     }
     _mm512_store_si512(L, _mm512_and_si512(s0, lo32));
     _mm512_store_si512(H, _mm512_srli_epi64(s0, 32));
-    const uint64_t *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
     __m512i al[4], ah[4], ab[4];
     const __m512i zero = _mm512_setzero_si512();
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
-        const __m512i bl = _mm512_set1_epi64((long long)Lm[j]), bh = _mm512_set1_epi64((long long)Hm[j]);
-        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)Hm[j]);
+        const __m512i bl = _mm512_set1_epi64((long long)L[j]), bh = _mm512_set1_epi64((long long)H[j]);
+        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)H[j]);
         const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cb = _mm512_load_si512(I.mds_icol_b[j]);
         al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
         ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
@@ -573,13 +561,11 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         _mm512_store_si512(pr, _mm512_unpacklo_epi64(L, H));      // pairs of lanes 0, 2, 4, 6
         _mm512_store_si512(pr + 8, _mm512_unpackhi_epi64(L, H));  // pairs of lanes 1, 3, 5, 7
     }
-    const uint64_t* prm = pr;
-    SIPP_THROUGH_MEMORY(prm);
     __m512i al[4], ah[4], ab[4];
     const __m512i zero = _mm512_setzero_si512();
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
-        const uint64_t* q = prm + (j < 8 ? ((j & 1) ? 7 + j : j) : 2 * j);
+        const uint64_t* q = pr + (j < 8 ? ((j & 1) ? 7 + j : j) : 2 * j);
         const __m512i bl = _mm512_set1_epi64((long long)q[0]), bh = _mm512_set1_epi64((long long)q[1]);
         // (the pairs of the scalar lanes are written by two 8-byte stores: a 16-byte load across them would not be forwarded)
         const __m512i bb = j < 8 ? _mm512_broadcast_i64x2(_mm_load_si128((const __m128i*)q)) : _mm512_mask_blend_epi64(0xAA, bl, bh);

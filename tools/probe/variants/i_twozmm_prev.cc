@@ -1,3 +1,4 @@
+#define LAB_NO_IFMA_LAYERS 1
 // poseidon_avx512.cc -- AVX-512 implementation of the plonky2 Poseidon permutation over Goldilocks (width 12).
 //
 // The Fiat-Shamir transcript of the SIPP native protocol (/root/reference/src/transcript_native.rs:25-30) is a strictly
@@ -142,11 +143,6 @@ SIPP_AVX512 inline uint64_t acc_reduce(const Acc192& s) {
     return d;
 }
 
-// The MDS layers below store the state halves and read every one back as a broadcast LOAD (load ports).  Left alone, GCC forwards
-// the stored vectors through registers instead -- vextracti64x2 / valignq / vpbroadcastq chains, all on port 5, ~40 shuffles per
-// layer; this barrier makes the round trip through memory real.
-#define SIPP_THROUGH_MEMORY(ptr) asm volatile("" : "+r"(ptr) : : "memory")
-
 // ------------------------------------------------------------------------------------------------ vector helpers
 SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
     const __m512i eps = _mm512_set1_epi64((long long)EPS);
@@ -216,14 +212,11 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
     _mm512_store_pd(H, _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)));
     _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
-    const double *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
     __m512d al[4], ah[4], ab[4];
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
-        const __m512d bl = _mm512_set1_pd(Lm[j]), bh = _mm512_set1_pd(Hm[j]);
-        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&Hm[j]));
+        const __m512d bl = _mm512_set1_pd(L[j]), bh = _mm512_set1_pd(H[j]);
+        const __m512d bb = _mm512_mask_broadcastsd_pd(bl, 0xF0, _mm_load_sd(&H[j]));
         const __m512d ca = _mm512_load_pd(T.mds_col_a[j]), cb = _mm512_load_pd(T.mds_col_b[j]);
         if (j < 4) {
             al[j] = _mm512_mul_pd(bl, ca); ah[j] = _mm512_mul_pd(bh, ca); ab[j] = _mm512_mul_pd(bb, cb);
@@ -375,98 +368,6 @@ SIPP_IFMA inline uint64_t row_close(uint64_t a0, uint64_t a1, uint64_t a2, uint6
         : "cc");
     return a0;
 }
-// (e + z7) mod 2^64-representative: one wrap correction
-SIPP_IFMA inline uint64_t chain_close(uint64_t e, uint64_t z7) {
-    unsigned long long t;
-    const uint64_t eps = EPS;
-    asm("add %[z7], %[e]\n\t" "lea (%[e],%[eps]), %[t]\n\t" "cmovc %[t], %[e]" : [e] "+r"(e), [t] "=&r"(t) : [z7] "r"(z7), [eps] "r"(eps) : "cc");
-    return e;
-}
-// Latency-optimised vector product for the path below, where ONE vector (lanes 0..7) is left on the vector ports and its x^7 chain
-// is the critical path of a full round: the partial products are summed as a shallow tree (three 32-bit middle terms, no carry
-// between them) and hl (2^32 - 1) is a shift and a subtraction instead of a multiply -- 28 instead of 35 cycles, four more micro-ops.
-SIPP_IFMA inline __m512i v_reduce_fast(__m512i lo, __m512i hi) {
-    const __m512i eps = _mm512_set1_epi64((long long)EPS);
-    __m512i hh = _mm512_srli_epi64(hi, 32);
-    __m512i t = _mm512_sub_epi64(lo, hh);
-    __mmask8 b = _mm512_cmplt_epu64_mask(lo, hh);
-    t = _mm512_mask_sub_epi64(t, b, t, eps);
-    __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), _mm512_and_si512(hi, eps));
-    __m512i r = _mm512_add_epi64(t, m);
-    __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
-    return _mm512_mask_add_epi64(r, c, r, eps);
-}
-SIPP_IFMA inline __m512i v_mul_fast(__m512i x, __m512i y) {
-    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    __m512i xh = v_hi(x), yh = v_hi(y);
-    __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
-    __m512i mid = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(ll, 32), _mm512_and_si512(lh, lo32)), _mm512_and_si512(hl, lo32));
-    __m512i hs = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(lh, 32), _mm512_srli_epi64(hl, 32)), hh);
-    return v_reduce_fast(v_join(ll, mid), _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32)));
-}
-SIPP_IFMA inline __m512i v_sqr_fast(__m512i x) {
-    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    __m512i xh = v_hi(x);
-    __m512i ll = _mm512_mul_epu32(x, x), lh = _mm512_mul_epu32(x, xh), hh = _mm512_mul_epu32(xh, xh);
-    __m512i lhl = _mm512_and_si512(lh, lo32), lhh = _mm512_srli_epi64(lh, 32);
-    __m512i mid = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(ll, 32), lhl), lhl);
-    __m512i hs = _mm512_add_epi64(_mm512_add_epi64(lhh, lhh), hh);
-    return v_reduce_fast(v_join(ll, mid), _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32)));
-}
-SIPP_IFMA inline __m512i v_pow7_fast(__m512i x) {
-    __m512i x2 = v_sqr_fast(x), x4 = v_sqr_fast(x2), x3 = v_mul_fast(x2, x);
-    return v_mul_fast(x3, x4);
-}
-// a + c, one wrap correction (c canonical, or a + c < 2^65 - 2^32)
-SIPP_IFMA inline uint64_t s_add1(uint64_t a, uint64_t c) {
-    unsigned long long t;
-    const uint64_t eps = EPS;
-    asm("add %[c], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]" : [a] "+r"(a), [t] "=&r"(t) : [c] "rm"(c), [eps] "r"(eps) : "cc");
-    return a;
-}
-// the MDS layer of v_mds on the integer multiplier: the 32-bit halves times the small circulant entries are exact in the low 52 bits
-// of a vpmadd52luq, so the two int <-> double conversions and the FP add tree of the FMA form go away
-SIPP_IFMA inline void v_mds_ifma(__m512i& s0, __m512i& s1, const PoseidonIfmaTables& I) {
-    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    alignas(64) uint64_t L[16], H[16];
-    _mm512_store_si512(L, _mm512_and_si512(s0, lo32));
-    _mm512_store_si512(L + 8, _mm512_and_si512(s1, lo32));
-    _mm512_store_si512(H, _mm512_srli_epi64(s0, 32));
-    _mm512_store_si512(H + 8, _mm512_srli_epi64(s1, 32));
-    const uint64_t *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
-    __m512i al[4], ah[4], ab[4];
-    const __m512i zero = _mm512_setzero_si512();
-#pragma GCC unroll 12
-    for (int j = 0; j < 12; j++) {
-        const __m512i bl = _mm512_set1_epi64((long long)Lm[j]), bh = _mm512_set1_epi64((long long)Hm[j]);
-        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)Hm[j]);
-        const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cb = _mm512_load_si512(I.mds_icol_b[j]);
-        al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
-        ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cb);
-    }
-    const __m512i eps = lo32;
-    auto combine = [&](__m512i alo, __m512i ahi) SIPP_IFMA {
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
-        __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        return _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
-    };
-    s0 = combine(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
-                 _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
-    const __m512i bi = _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3]));
-    s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));
-}
-SIPP_IFMA inline void v_full_round_ifma(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonIfmaTables& I) {
-    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
-    s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
-    v_mds_ifma(s0, s1, I);
-}
 // u^7, three dependent products (the S-box block of pr_sbox without the constant)
 SIPP_IFMA inline uint64_t sbox7(uint64_t u) {
     unsigned long long a, b, h, t;
@@ -494,118 +395,13 @@ SIPP_IFMA inline uint64_t sbox7(uint64_t u) {
         : "rdx", "cc");
     return a;
 }
-// (alo + 2^32 ahi) mod p for the two sums (< 2^43) of an MDS row
-SIPP_IFMA inline uint64_t s_mds_close(uint64_t alo, uint64_t ahi) {
+// (e + z7) mod 2^64-representative: one wrap correction
+SIPP_IFMA inline uint64_t chain_close(uint64_t e, uint64_t z7) {
     unsigned long long t;
     const uint64_t eps = EPS;
-    asm("mov %[ahi], %[t]\n\t" "shl $32, %[t]\n\t" "shr $32, %[ahi]\n\t" "add %[t], %[alo]\n\t" "adc $0, %[ahi]\n\t"
-        "mov %[ahi], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[ahi], %[t]\n\t" "add %[t], %[alo]\n\t" "lea (%[alo],%[eps]), %[t]\n\t" "cmovc %[t], %[alo]"
-        : [alo] "+r"(alo), [ahi] "+r"(ahi), [t] "=&r"(t)
-        : [eps] "r"(eps)
-        : "cc");
-    return alo;
+    asm("add %[z7], %[e]\n\t" "lea (%[e],%[eps]), %[t]\n\t" "cmovc %[t], %[e]" : [e] "+r"(e), [t] "=&r"(t) : [z7] "r"(z7), [eps] "r"(eps) : "cc");
+    return e;
 }
-// A full round with lanes 0..7 in one vector and lanes 8..11 on the scalar ports.  Two zmm x^7 share the two 512-bit ports and the
-// second is half empty (134 cycles for the S-box layer against 115 for one vector alone); the four scalar x^7 (33 cycles each,
-// independent) run in the shadow of the vector chain, which comes first in program order so that it is served first.  The
-// scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store.
-SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc16, const PoseidonIfmaTables& I) {
-    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-#ifdef LAB_OLD_MODMUL
-    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
-#else
-    s0 = v_pow7_fast(v_add_canon(s0, _mm512_load_si512(rc16)));
-#endif
-#ifdef LAB_MDS_BB
-    alignas(64) uint64_t L[16], H[16];
-#pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) {
-        const uint64_t q = sbox7(s_add1(t[i], rc16[8 + i]));
-        L[8 + i] = (uint32_t)q;
-        H[8 + i] = q >> 32;
-    }
-    _mm512_store_si512(L, _mm512_and_si512(s0, lo32));
-    _mm512_store_si512(H, _mm512_srli_epi64(s0, 32));
-    const uint64_t *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
-    __m512i al[4], ah[4], ab[4];
-    const __m512i zero = _mm512_setzero_si512();
-#pragma GCC unroll 12
-    for (int j = 0; j < 12; j++) {
-        const __m512i bl = _mm512_set1_epi64((long long)Lm[j]), bh = _mm512_set1_epi64((long long)Hm[j]);
-        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)Hm[j]);
-        const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cb = _mm512_load_si512(I.mds_icol_b[j]);
-        al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
-        ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cb);
-    }
-    const __m512i eps = lo32;
-    auto combine = [&](__m512i alo, __m512i ahi) SIPP_IFMA {
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
-        __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        return _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
-    };
-    s0 = combine(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
-                 _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
-    const __m512i bi = _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3]));
-    alignas(64) uint64_t o[8];
-    _mm512_store_si512(o, combine(bi, _mm512_alignr_epi64(bi, bi, 4)));
-    t[0] = o[0]; t[1] = o[1]; t[2] = o[2]; t[3] = o[3];
-}
-#else
-    // MDS layer.  The 32-bit halves of every lane are stored as (low, high) pairs: a 64-bit broadcast of either feeds rows 0..7,
-    // ONE 128-bit broadcast of the pair feeds rows 8..11 (lane 2i: low sums of row 8 + i, lane 2i + 1: high sums) -- no merge of
-    // two broadcasts on the vector ports; rows 8..11 are recombined on the scalar ports, where their lanes live.
-    alignas(64) uint64_t pr[24];
-#pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) {
-        const uint64_t q = sbox7(s_add1(t[i], rc16[8 + i]));
-        pr[16 + 2 * i] = (uint32_t)q;
-        pr[17 + 2 * i] = q >> 32;
-    }
-    {
-        const __m512i L = _mm512_and_si512(s0, lo32), H = _mm512_srli_epi64(s0, 32);
-        _mm512_store_si512(pr, _mm512_unpacklo_epi64(L, H));      // pairs of lanes 0, 2, 4, 6
-        _mm512_store_si512(pr + 8, _mm512_unpackhi_epi64(L, H));  // pairs of lanes 1, 3, 5, 7
-    }
-    const uint64_t* prm = pr;
-    SIPP_THROUGH_MEMORY(prm);
-    __m512i al[4], ah[4], ab[4];
-    const __m512i zero = _mm512_setzero_si512();
-#pragma GCC unroll 12
-    for (int j = 0; j < 12; j++) {
-        const uint64_t* q = prm + (j < 8 ? ((j & 1) ? 7 + j : j) : 2 * j);
-        const __m512i bl = _mm512_set1_epi64((long long)q[0]), bh = _mm512_set1_epi64((long long)q[1]);
-        // (the pairs of the scalar lanes are written by two 8-byte stores: a 16-byte load across them would not be forwarded)
-        const __m512i bb = j < 8 ? _mm512_broadcast_i64x2(_mm_load_si128((const __m128i*)q)) : _mm512_mask_blend_epi64(0xAA, bl, bh);
-        const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cp = _mm512_load_si512(I.mds_icol_p[j]);
-        al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
-        ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cp);
-    }
-    {
-        const __m512i eps = lo32;
-        const __m512i alo = _mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3]));
-        const __m512i ahi = _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3]));
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
-        __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        s0 = _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
-    }
-    alignas(64) uint64_t o[8];
-    _mm512_store_si512(o, _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3])));
-#pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) t[i] = s_mds_close(o[2 * i], o[2 * i + 1]);
-}
-#endif
 // all eight lanes of a block closed at once: (a0 + 2^52 a1 - 2^8 a2) mod p
 SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
     const __m512i one = _mm512_set1_epi64(1);
@@ -624,19 +420,19 @@ SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
 }  // namespace
 
 SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T, const PoseidonIfmaTables& I) {
-    __m512i s0 = _mm512_loadu_si512(s);
-    uint64_t t[4] = {s[8], s[9], s[10], s[11]};
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[k], I);
+    alignas(64) uint64_t buf[16];
+    memcpy(buf, s, 96);
+    buf[12] = buf[13] = buf[14] = buf[15] = 0;
+    __m512i s0 = _mm512_load_si512(buf), s1 = _mm512_load_si512(buf + 8);
+    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[k], T);
 
     s0 = v_add_canon(s0, _mm512_load_si512(T.first));
+    s1 = v_add_canon(s1, _mm512_load_si512(T.first + 8));
     alignas(64) uint64_t y[16], yh[16];
     _mm512_store_si512(y, s0);
+    _mm512_store_si512(y + 8, s1);
     _mm512_store_si512(yh, _mm512_srli_epi64(s0, 52));
-#pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) {
-        y[8 + i] = s_add1(t[i], T.first[8 + i]);
-        yh[8 + i] = y[8 + i] >> 52;
-    }
+    _mm512_store_si512(yh + 8, _mm512_srli_epi64(s1, 52));
     IfmaBlock A[4];
 #pragma GCC unroll 4
     for (int b = 0; b < 4; b++) {
@@ -697,14 +493,13 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
         ifma_unit(A[3], xb, xh, I.upd_c[21][3][0]);
     }
     s0 = _mm512_mask_set1_epi64(v_close(A[3]), 1, (long long)s_mul(u0, I.lam22));
-    {
-        alignas(64) uint64_t o[8];
-        _mm512_store_si512(o, v_close(A[2]));
-        t[0] = o[0]; t[1] = o[1]; t[2] = o[2]; t[3] = o[3];
-    }
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[4 + k], I);
-    _mm512_storeu_si512(s, v_canon(s0));
-    for (int i = 0; i < 4; i++) s[8 + i] = t[i] - (t[i] >= GL_P ? GL_P : 0);
+    s1 = v_close(A[2]);
+    for (int k = 0; k < 4; k++) v_full_round(s0, s1, T.rc_full[4 + k], T);
+    s0 = v_canon(s0);
+    s1 = v_canon(s1);
+    _mm512_store_si512(buf, s0);
+    _mm512_store_si512(buf + 8, s1);
+    memcpy(s, buf, 96);
 }
 bool poseidon_ifma_supported() { return poseidon_avx512_supported() && __builtin_cpu_supports("avx512ifma"); }
 SIPP_IFMA void poseidon_test_ifma_close(const uint64_t in[5], uint64_t out[2]) {
