@@ -82,9 +82,10 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          256; 0 = off) they are cut into n / 16 blocks, at most SIPP_OPT_MATRIX_BLOCK_R, E[i][j] = <A_block_i, B_block_j> is
                                          computed for all block pairs in one launch set, and log2(R) rounds take Z_L, Z_R from that matrix
                                          while the points are folded on a side stream, off the critical path */
-#define SIPP_OPT_MATRIX_FIRST 17      /* 1 [default]: the FIRST stage is built from the inputs themselves (n / 32 blocks, between 8 and 32, at most 2^17 Miller
-                                         loops) while the host still hashes A and B: Z is the product of its diagonal and the first
-                                         log2(blocks) rounds are one matrix fold each.  0 = the first rounds run on the points */
+#define SIPP_OPT_MATRIX_FIRST 17      /* 1 [default]: the FIRST stage is built from the inputs themselves (n / 32 blocks, between 8 and 32, inside a budget
+                                         of 16 n (n <= 2^11) or 32 n Miller loops, at most 2^18) while the host still hashes A and B: Z is the
+                                         product of its diagonal and the first log2(blocks) rounds are one matrix fold each.  10..24 = the
+                                         budget is 2^value loops whatever n.  0 = the first rounds run on the points */
 #define SIPP_OPT_MATRIX_BLOCK_R 16    /* blocks per look-ahead stage: 4, 8 (default), 16 or 32 (capped so that the stage ends where the tail begins) */
 int sipp_set_option(int option, int value);
 int sipp_get_option(int option);

@@ -145,7 +145,8 @@ SIPP_AVX512 inline uint64_t acc_reduce(const Acc192& s) {
 // The MDS layers below store the state halves and read every one back as a broadcast LOAD (load ports).  Left alone, GCC forwards
 // the stored vectors through registers instead -- vextracti64x2 / valignq / vpbroadcastq chains, all on port 5, ~40 shuffles per
 // layer; this barrier makes the round trip through memory real.
-#define SIPP_THROUGH_MEMORY(ptr) asm volatile("" : "+r"(ptr) : : "memory")
+// (the operand names the one array: a "memory" clobber would also spill and reload every accumulator that lives in an array)
+#define SIPP_THROUGH_MEMORY(arr) asm volatile("" : "+m"(arr))
 
 // ------------------------------------------------------------------------------------------------ vector helpers
 SIPP_AVX512 inline __m512i v_reduce(__m512i lo, __m512i hi) {
@@ -216,9 +217,9 @@ SIPP_AVX512 inline void v_mds(__m512i& s0, __m512i& s1, const PoseidonFastTables
     _mm512_store_pd(L + 8, _mm512_cvtepu64_pd(_mm512_and_si512(s1, lo32)));
     _mm512_store_pd(H, _mm512_cvtepu64_pd(_mm512_srli_epi64(s0, 32)));
     _mm512_store_pd(H + 8, _mm512_cvtepu64_pd(_mm512_srli_epi64(s1, 32)));
+    SIPP_THROUGH_MEMORY(L);
+    SIPP_THROUGH_MEMORY(H);
     const double *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
     __m512d al[4], ah[4], ab[4];
 #pragma GCC unroll 12
     for (int j = 0; j < 12; j++) {
@@ -357,20 +358,19 @@ SIPP_IFMA inline void ifma_store(uint64_t* sc, const IfmaBlock& A) {
 // (a0 + 2^52 a1 - 2^8 a2 + c x) mod p: one lane of an accumulator block (2^104 = -2^8; the row constant carries a + p, so the
 // subtraction cannot borrow) plus the newest term of the row
 SIPP_IFMA inline uint64_t row_close(uint64_t a0, uint64_t a1, uint64_t a2, uint64_t c, uint64_t x) {
-    unsigned long long t, pl, ph, top;
+    unsigned long long t, pl, ph;  // (a2 doubles as the third limb once it has been subtracted: the block is short of registers around it)
     const uint64_t eps = EPS;
     asm("mov %[a1], %[t]\n\t" "shl $52, %[t]\n\t" "shr $12, %[a1]\n\t" "add %[t], %[a0]\n\t" "adc $0, %[a1]\n\t"
         "shl $8, %[a2]\n\t" "sub %[a2], %[a0]\n\t" "sbb $0, %[a1]\n\t"
-        "xor %k[top], %k[top]\n\t"
-        "mulx %[c], %[pl], %[ph]\n\t" "add %[pl], %[a0]\n\t" "adc %[ph], %[a1]\n\t" "adc $0, %[top]\n\t"
+        "mulx %[c], %[pl], %[ph]\n\t" "xor %k[a2], %k[a2]\n\t" "add %[pl], %[a0]\n\t" "adc %[ph], %[a1]\n\t" "adc $0, %[a2]\n\t"
         "mov %[a1], %[t]\n\t" "shr $32, %[t]\n\t" "mov %k[a1], %k[a1]\n\t" "sub %[t], %[a0]\n\t" "jc 31f\n" "30:\n\t"
         "mov %[a1], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[a1], %[t]\n\t" "add %[t], %[a0]\n\t" "lea (%[a0],%[eps]), %[t]\n\t" "cmovc %[t], %[a0]\n\t"
-        "shl $32, %[top]\n\t" "sub %[top], %[a0]\n\t" "jc 33f\n" "32:\n\t"
+        "shl $32, %[a2]\n\t" "sub %[a2], %[a0]\n\t" "jc 33f\n" "32:\n\t"
         ".subsection 1\n"
         "31:\n\t" "sub %[eps], %[a0]\n\t" "jmp 30b\n"
         "33:\n\t" "sub %[eps], %[a0]\n\t" "jmp 32b\n"
         ".previous"
-        : [a0] "+r"(a0), [a1] "+r"(a1), [a2] "+r"(a2), [t] "=&r"(t), [pl] "=&r"(pl), [ph] "=&r"(ph), [top] "=&r"(top)
+        : [a0] "+r"(a0), [a1] "+r"(a1), [a2] "+r"(a2), [t] "=&r"(t), [pl] "=&r"(pl), [ph] "=&r"(ph)
         : [c] "rm"(c), "d"(x), [eps] "r"(eps)
         : "cc");
     return a0;
@@ -424,49 +424,6 @@ SIPP_IFMA inline uint64_t s_add1(uint64_t a, uint64_t c) {
     asm("add %[c], %[a]\n\t" "lea (%[a],%[eps]), %[t]\n\t" "cmovc %[t], %[a]" : [a] "+r"(a), [t] "=&r"(t) : [c] "rm"(c), [eps] "r"(eps) : "cc");
     return a;
 }
-// the MDS layer of v_mds on the integer multiplier: the 32-bit halves times the small circulant entries are exact in the low 52 bits
-// of a vpmadd52luq, so the two int <-> double conversions and the FP add tree of the FMA form go away
-SIPP_IFMA inline void v_mds_ifma(__m512i& s0, __m512i& s1, const PoseidonIfmaTables& I) {
-    const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    alignas(64) uint64_t L[16], H[16];
-    _mm512_store_si512(L, _mm512_and_si512(s0, lo32));
-    _mm512_store_si512(L + 8, _mm512_and_si512(s1, lo32));
-    _mm512_store_si512(H, _mm512_srli_epi64(s0, 32));
-    _mm512_store_si512(H + 8, _mm512_srli_epi64(s1, 32));
-    const uint64_t *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
-    __m512i al[4], ah[4], ab[4];
-    const __m512i zero = _mm512_setzero_si512();
-#pragma GCC unroll 12
-    for (int j = 0; j < 12; j++) {
-        const __m512i bl = _mm512_set1_epi64((long long)Lm[j]), bh = _mm512_set1_epi64((long long)Hm[j]);
-        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)Hm[j]);
-        const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cb = _mm512_load_si512(I.mds_icol_b[j]);
-        al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
-        ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cb);
-    }
-    const __m512i eps = lo32;
-    auto combine = [&](__m512i alo, __m512i ahi) SIPP_IFMA {
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
-        __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        return _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
-    };
-    s0 = combine(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
-                 _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
-    const __m512i bi = _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3]));
-    s1 = combine(bi, _mm512_alignr_epi64(bi, bi, 4));
-}
-SIPP_IFMA inline void v_full_round_ifma(__m512i& s0, __m512i& s1, const uint64_t* rc16, const PoseidonIfmaTables& I) {
-    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
-    s1 = v_pow7(v_add_canon(s1, _mm512_load_si512(rc16 + 8)));
-    v_mds_ifma(s0, s1, I);
-}
 // u^7, three dependent products (the S-box block of pr_sbox without the constant)
 SIPP_IFMA inline uint64_t sbox7(uint64_t u) {
     unsigned long long a, b, h, t;
@@ -511,53 +468,7 @@ SIPP_IFMA inline uint64_t s_mds_close(uint64_t alo, uint64_t ahi) {
 // scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store.
 SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc16, const PoseidonIfmaTables& I) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-#ifdef LAB_OLD_MODMUL
-    s0 = v_pow7(v_add_canon(s0, _mm512_load_si512(rc16)));
-#else
     s0 = v_pow7_fast(v_add_canon(s0, _mm512_load_si512(rc16)));
-#endif
-#ifdef LAB_MDS_BB
-    alignas(64) uint64_t L[16], H[16];
-#pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) {
-        const uint64_t q = sbox7(s_add1(t[i], rc16[8 + i]));
-        L[8 + i] = (uint32_t)q;
-        H[8 + i] = q >> 32;
-    }
-    _mm512_store_si512(L, _mm512_and_si512(s0, lo32));
-    _mm512_store_si512(H, _mm512_srli_epi64(s0, 32));
-    const uint64_t *Lm = L, *Hm = H;
-    SIPP_THROUGH_MEMORY(Lm);
-    SIPP_THROUGH_MEMORY(Hm);
-    __m512i al[4], ah[4], ab[4];
-    const __m512i zero = _mm512_setzero_si512();
-#pragma GCC unroll 12
-    for (int j = 0; j < 12; j++) {
-        const __m512i bl = _mm512_set1_epi64((long long)Lm[j]), bh = _mm512_set1_epi64((long long)Hm[j]);
-        const __m512i bb = _mm512_mask_set1_epi64(bl, 0xF0, (long long)Hm[j]);
-        const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cb = _mm512_load_si512(I.mds_icol_b[j]);
-        al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
-        ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cb);
-    }
-    const __m512i eps = lo32;
-    auto combine = [&](__m512i alo, __m512i ahi) SIPP_IFMA {
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
-        __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        return _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
-    };
-    s0 = combine(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
-                 _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
-    const __m512i bi = _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3]));
-    alignas(64) uint64_t o[8];
-    _mm512_store_si512(o, combine(bi, _mm512_alignr_epi64(bi, bi, 4)));
-    t[0] = o[0]; t[1] = o[1]; t[2] = o[2]; t[3] = o[3];
-}
-#else
     // MDS layer.  The 32-bit halves of every lane are stored as (low, high) pairs: a 64-bit broadcast of either feeds rows 0..7,
     // ONE 128-bit broadcast of the pair feeds rows 8..11 (lane 2i: low sums of row 8 + i, lane 2i + 1: high sums) -- no merge of
     // two broadcasts on the vector ports; rows 8..11 are recombined on the scalar ports, where their lanes live.
@@ -573,8 +484,8 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         _mm512_store_si512(pr, _mm512_unpacklo_epi64(L, H));      // pairs of lanes 0, 2, 4, 6
         _mm512_store_si512(pr + 8, _mm512_unpackhi_epi64(L, H));  // pairs of lanes 1, 3, 5, 7
     }
+    SIPP_THROUGH_MEMORY(pr);
     const uint64_t* prm = pr;
-    SIPP_THROUGH_MEMORY(prm);
     __m512i al[4], ah[4], ab[4];
     const __m512i zero = _mm512_setzero_si512();
 #pragma GCC unroll 12
@@ -602,10 +513,11 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
     }
     alignas(64) uint64_t o[8];
     _mm512_store_si512(o, _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3])));
+    SIPP_THROUGH_MEMORY(o);
+    const uint64_t* om = o;
 #pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) t[i] = s_mds_close(o[2 * i], o[2 * i + 1]);
+    for (int i = 0; i < 4; i++) t[i] = s_mds_close(om[2 * i], om[2 * i + 1]);
 }
-#endif
 // all eight lanes of a block closed at once: (a0 + 2^52 a1 - 2^8 a2) mod p
 SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
     const __m512i one = _mm512_set1_epi64(1);
@@ -629,83 +541,88 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
     for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[k], I);
 
     s0 = v_add_canon(s0, _mm512_load_si512(T.first));
-    alignas(64) uint64_t y[16], yh[16];
+    alignas(64) uint64_t y[32];  // y[0..11], y[16 + i] = y[i] >> 52
     _mm512_store_si512(y, s0);
-    _mm512_store_si512(yh, _mm512_srli_epi64(s0, 52));
+    _mm512_store_si512(y + 16, _mm512_srli_epi64(s0, 52));
 #pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
         y[8 + i] = s_add1(t[i], T.first[8 + i]);
-        yh[8 + i] = y[8 + i] >> 52;
+        y[24 + i] = y[8 + i] >> 52;
     }
-    IfmaBlock A[4];
+    // four named blocks selected by switch statements, never through a pointer or an array index: anything else keeps the twelve
+    // accumulators in memory (a load and a store around every vpmadd52)
+    IfmaBlock A0, A1, A2, A3;
+#define BLK_DO(b, stmt) switch (b) { case 0: { IfmaBlock& B = A0; stmt; } break; case 1: { IfmaBlock& B = A1; stmt; } break; \
+                                     case 2: { IfmaBlock& B = A2; stmt; } break; default: { IfmaBlock& B = A3; stmt; } break; }
 #pragma GCC unroll 4
-    for (int b = 0; b < 4; b++) {
-        A[b].a0 = _mm512_load_si512(I.acc_init[b][0]);
-        A[b].a1 = _mm512_load_si512(I.acc_init[b][1]);
-        A[b].a2 = _mm512_setzero_si512();
-    }
+    for (int b = 0; b < 4; b++)
+        BLK_DO(b, (B.a0 = _mm512_load_si512(I.acc_init[b][0]), B.a1 = _mm512_load_si512(I.acc_init[b][1]), B.a2 = _mm512_setzero_si512()))
     // the y part of a row block: 11 units; block 0 now, the others spread over the rounds that precede their first use
-    auto init_unit = [&](int i, int b) SIPP_IFMA { ifma_unit(A[b], _mm512_set1_epi64((long long)y[1 + i]), _mm512_set1_epi64((long long)yh[1 + i]), I.init_c[i][b][0]); };
+    SIPP_THROUGH_MEMORY(y);
+    const uint64_t *ym = y, *ys = y;  // ys: the scalar readers (C-row 0) -- a pointer of their own, or GCC loads every y once into a
+    asm("" : "+r"(ys));                // general register and broadcasts from there (port 5)
+#define init_unit(i, b) BLK_DO(b, ifma_unit(B, _mm512_set1_epi64((long long)ym[1 + (i)]), _mm512_set1_epi64((long long)ym[17 + (i)]), I.init_c[i][b][0]))
 #pragma GCC unroll 11
-    for (int i = 0; i < 11; i++) init_unit(i, 0);
-    uint64_t u0 = y[0];
+    for (int i = 0; i < 11; i++) init_unit(i, 0)
+    uint64_t u0 = ys[0];
     uint64_t e;
     {
-        Acc192 a = s_dot11_raw(I.row0, y + 1);
+        Acc192 a = s_dot11_raw(I.row0, ys + 1);
         acc_add(a, I.k0);
         e = acc_reduce(a);
     }
-    uint64_t p7_prev = 0;
-    auto lane_of = [](const IfmaBlock& B, int lane, uint64_t& a0, uint64_t& a1, uint64_t& a2) SIPP_IFMA {
-        alignas(64) uint64_t t[24];
-        ifma_store(t, B);
-        a0 = t[lane]; a1 = t[8 + lane]; a2 = t[16 + lane];
-    };
+    __m512i xb = _mm512_setzero_si512(), xh = xb;  // broadcasts of the previous round's S-box output
+    alignas(64) uint64_t lanes[24];
 #pragma GCC unroll 22
     for (int j = 0; j < 22; j++) {
         const uint64_t p7 = sbox7(u0);
         u0 = chain_close(e, p7);  // z_{j+1}
         if (j >= 1) {  // the vector terms of x_{j-1}: behind the chain of this round in program order, so the chain is served first
             const int k = j - 1;
-            const __m512i xb = _mm512_set1_epi64((long long)p7_prev), xh = _mm512_set1_epi64((long long)(p7_prev >> 52));
-            if (k <= 6) ifma_unit(A[0], xb, xh, I.upd_c[k][0][0]);
-            if (k <= 14) ifma_unit(A[1], xb, xh, I.upd_c[k][1][0]);
-            ifma_unit(A[2], xb, xh, I.upd_c[k][2][0]);
-            ifma_unit(A[3], xb, xh, I.upd_c[k][3][0]);
+            if (k <= 6) ifma_unit(A0, xb, xh, I.upd_c[k][0][0]);
+            if (k <= 14) ifma_unit(A1, xb, xh, I.upd_c[k][1][0]);
+            ifma_unit(A2, xb, xh, I.upd_c[k][2][0]);
+            ifma_unit(A3, xb, xh, I.upd_c[k][3][0]);
         }
         {
             const int blk = j <= 5 ? 1 : (j >= 7 && j <= 12) ? 2 : (j >= 13 && j <= 18) ? 3 : 0;
             const int base = j <= 5 ? 0 : j <= 12 ? 7 : 13;
             if (blk) {
                 const int i0 = 2 * (j - base);
-                init_unit(i0, blk);
-                if (i0 + 1 < 11) init_unit(i0 + 1, blk);
+                init_unit(i0, blk)
+                if (i0 + 1 < 11) init_unit(i0 + 1, blk)
             }
         }
         if (j + 1 <= 21) {  // close C-row j + 1: vector terms k <= j - 1, newest term x_j
             const int row = j + 1, b = row <= 8 ? 0 : row <= 16 ? 1 : row <= 20 ? 2 : 3;
             const int lane = row <= 8 ? row - 1 : row <= 16 ? row - 9 : row <= 20 ? row - 13 : 0;
             uint64_t a0, a1, a2;
-            lane_of(A[b], lane, a0, a1, a2);
+            BLK_DO(b, ifma_store(lanes, B))
+            // (no barrier here: GCC turns this store + three loads into lane extracts, measured 9 ns per permutation faster)
+            a0 = lanes[lane]; a1 = lanes[8 + lane]; a2 = lanes[16 + lane];
             e = row_close(a0, a1, a2, I.cdiag[row], p7);
         }
-        p7_prev = p7;
+        xb = _mm512_set1_epi64((long long)p7);
+        xh = _mm512_srli_epi64(xb, 52);
     }
     {
-        const __m512i xb = _mm512_set1_epi64((long long)p7_prev), xh = _mm512_set1_epi64((long long)(p7_prev >> 52));
-        ifma_unit(A[2], xb, xh, I.upd_c[21][2][0]);
-        ifma_unit(A[3], xb, xh, I.upd_c[21][3][0]);
+        ifma_unit(A2, xb, xh, I.upd_c[21][2][0]);
+        ifma_unit(A3, xb, xh, I.upd_c[21][3][0]);
     }
-    s0 = _mm512_mask_set1_epi64(v_close(A[3]), 1, (long long)s_mul(u0, I.lam22));
+    s0 = _mm512_mask_set1_epi64(v_close(A3), 1, (long long)s_mul(u0, I.lam22));
     {
         alignas(64) uint64_t o[8];
-        _mm512_store_si512(o, v_close(A[2]));
-        t[0] = o[0]; t[1] = o[1]; t[2] = o[2]; t[3] = o[3];
+        _mm512_store_si512(o, v_close(A2));
+        SIPP_THROUGH_MEMORY(o);
+        const uint64_t* om = o;
+        t[0] = om[0]; t[1] = om[1]; t[2] = om[2]; t[3] = om[3];
     }
     for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[4 + k], I);
     _mm512_storeu_si512(s, v_canon(s0));
     for (int i = 0; i < 4; i++) s[8 + i] = t[i] - (t[i] >= GL_P ? GL_P : 0);
 }
+#undef BLK_DO
+#undef init_unit
 bool poseidon_ifma_supported() { return poseidon_avx512_supported() && __builtin_cpu_supports("avx512ifma"); }
 SIPP_IFMA void poseidon_test_ifma_close(const uint64_t in[5], uint64_t out[2]) {
     out[0] = row_close(in[0], in[1], in[2], in[3], in[4]);

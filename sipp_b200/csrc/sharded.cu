@@ -162,14 +162,14 @@ struct CudaBackend {
 // indices holds m / world points of every rank, so each rank computes ITS factor of every block product <A_block_i, B_block_j>
 // (un-exponentiated), the factors are all-gathered (384 B per entry and rank: 3 MB at 32 x 32 blocks on 8 GPUs -- the one real
 // exchange of the protocol) and rank 0 multiplies and exponentiates them.  The first log2(nr) rounds then need no collective but
-// the challenge broadcast: rank 0 folds the matrix, every rank folds its own points.  Blocks: as many as keep a rank under 2^17
-// Miller loops, at most 32, and the stage must end before the tail moves to rank 0.
+// the challenge broadcast: rank 0 folds the matrix, every rank folds its own points.  Blocks: as many as keep a rank inside the
+// Miller-loop budget of mat_first_budget, at most 32, and the stage must end before the tail moves to rank 0.
 size_t cb_first_stage_blocks(size_t local_n, size_t collapse_at) {
     const size_t world = (size_t)g_comm.world, n = local_n * world;
     if (world == 1 || !g_opt_matrix_first || !g_opt_pipeline || !g_opt_fe_engine || g_opt_matrix_n < 2) return 0;
     size_t end_n = collapse_at > 2 * world ? collapse_at : 2 * world;
     size_t nr = 32;
-    while (nr >= 4 && (local_n * nr > ((size_t)1 << 17) || nr > local_n || n / nr < end_n)) nr >>= 1;
+    while (nr >= 4 && (local_n * nr > mat_first_budget(n) || nr > local_n || n / nr < end_n)) nr >>= 1;
     return nr >= 4 ? nr : 0;
 }
 bool cb_alone(const CudaBackend* b) { return b->collapsed || g_comm.world == 1; }

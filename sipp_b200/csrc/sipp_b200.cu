@@ -33,7 +33,7 @@ int g_opt_batch_streams = 0;   // batched instances: sub-batches on their own st
 int g_opt_batch_qlines = 1;    // batched instances: Q-only line coefficients computed once for Z and the first Z_L / Z_R
 int g_opt_batch_kpg_max = 32;  // batched instances: pairs of one product that share an accumulator group, at most
 int g_opt_matrix_n = 32;       // pairing matrix of single points (k_mat.cu) once at most this many points are left; 0 = off
-int g_opt_matrix_first = 1;     // the first matrix is built from the inputs, under the host's absorb chain
+int g_opt_matrix_first = 1;     // the first matrix is built from the inputs, under the host's absorb chain; 10..24: log2 of its Miller-loop budget
 int g_opt_matrix_block_n = 256, g_opt_matrix_block_r = 8;  // look-ahead stages: from at most this many points, that many blocks
 int g_opt_validate = 1;        // every prove / verify entry point checks its points: on the curve, B_i in the order-r subgroup
 
@@ -346,13 +346,22 @@ size_t mat_stage(size_t n) {
 
 // The FIRST stage of a proof starts from the inputs themselves, before any challenge exists: it runs in the shadow of the host's
 // 8n-permutation absorb chain, gives Z as the product of its diagonal, and the first log2(nr) rounds cost one matrix fold each.
+// Miller loops the first stage may spend.  It has to finish inside the host's absorb of the same inputs: 8 n permutations of 0.67 us
+// against ~6 M loops/s plus ~2.5 ms of fixed work (validation, line coefficients, final exponentiations), i.e. about 32 n - 15,000
+// loops.  Measured on the box (tools/first_ab.py, profiles/r02_v8_first_stage_ab.txt): 16 n is best up to n = 2^11, 32 n from 2^12
+// (slightly over, but it saves a round); the absolute cap bounds the line table (29 KB per loop).
+size_t mat_first_budget(size_t n) {
+    if (g_opt_matrix_first >= 10) return (size_t)1 << g_opt_matrix_first;
+    const size_t by_n = n <= 2048 ? 16 * n : 32 * n, cap = (size_t)1 << SIPP_FIRST_STAGE_LOG2_LOOPS;
+    return by_n < cap ? by_n : cap;
+}
 size_t mat_stage_first(size_t n) {
     if (!g_opt_matrix_first || !g_opt_pipeline || !g_opt_fe_engine || n < 2 || g_opt_matrix_n < 2) return 0;
     if (n <= (size_t)g_opt_matrix_n) return n;               // the whole proof on the matrix of its inputs
     size_t nr = n / 32;
     if (nr < 8) nr = 8;
     if (nr > 32) nr = 32;
-    while (nr > 1 && nr * n > ((size_t)1 << 17)) nr >>= 1;   // n nr Miller loops
+    while (nr > 1 && nr * n > mat_first_budget(n)) nr >>= 1;  // n nr Miller loops
     while (nr >= 4 && n / nr < 2) nr >>= 1;
     return nr >= 4 ? nr : 0;
 }
@@ -623,7 +632,7 @@ int sipp_set_option(int option, int value) {
             if (value < 0 || value > 64 || (value & (value - 1))) return fail(SIPP_ERR_ARG, "SIPP_OPT_MATRIX_TAIL: 0 or a power of two <= 64");
             g_opt_matrix_n = value;
             return SIPP_OK;
-        case SIPP_OPT_MATRIX_FIRST: g_opt_matrix_first = value ? 1 : 0; return SIPP_OK;
+        case SIPP_OPT_MATRIX_FIRST: g_opt_matrix_first = (value >= 10 && value <= 24) ? value : (value ? 1 : 0); return SIPP_OK;
         case SIPP_OPT_MATRIX_BLOCK_N: g_opt_matrix_block_n = value < 0 ? 0 : (value > 4096 ? 4096 : value); return SIPP_OK;
         case SIPP_OPT_MATRIX_BLOCK_R:
             if (value < 4 || value > 32 || (value & (value - 1))) return fail(SIPP_ERR_ARG, "SIPP_OPT_MATRIX_BLOCK_R: 4, 8, 16 or 32");

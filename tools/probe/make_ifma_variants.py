@@ -27,7 +27,4 @@ noclose = src.replace(close_line, "")
 write("i_novec.cc", novec)
 write("i_noclose.cc", noclose)
 write("i_neither.cc", cut(noclose, upd_start, upd_end))
-write("i_mds_bb.cc", "#define LAB_MDS_BB 1\n" + src)            # rows 8..11 of the MDS layer from a merged (low | high) broadcast, closed on the vector ports
-write("i_oldmul.cc", "#define LAB_OLD_MODMUL 1\n" + src)       # the 25-micro-op vector product on the one-vector chain
-write("i_mds_bb_oldmul.cc", "#define LAB_MDS_BB 1\n#define LAB_OLD_MODMUL 1\n" + src)
 print("variants:", sorted(os.listdir(out)))

@@ -5,6 +5,7 @@
 #include <immintrin.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <x86intrin.h>
 
@@ -62,10 +63,6 @@ template <class Rep> SIPP_IFMA static void lab_ifma_layers(__m512i& s0, const Po
     t0 = now();
     for (int i = 0; i < R; i++) full_round_mixed(s0, t, T.rc_full[i & 7], I);
     report("IFMA path: mixed full round, chained", now() - t0, R);
-    __m512i s1 = s0;
-    t0 = now();
-    for (int i = 0; i < R; i++) v_mds_ifma(s0, s1, I);
-    report("IFMA path: MDS layer (2 zmm, vpmadd52), chained", now() - t0, R);
     printf("  [%llu]\n", (unsigned long long)t[0]);
 }
 #endif
@@ -83,8 +80,9 @@ T512 int main() {
         ghz = 8.0 * N / dt / 1e9;
         printf("core clock estimate: %.2f GHz (dependent add chain)  [%llu]\n", ghz, (unsigned long long)a);
     }
+    const bool quick = getenv("LAB_QUICK") != nullptr;  // only the whole permutations
     auto report = [&](const char* name, double dt, double ops) { printf("%-46s %7.2f ns = %6.1f cycles\n", name, dt / ops * 1e9, dt / ops * 1e9 * ghz); };
-    {   // scalar modular product: latency
+    if (!quick) {   // scalar modular product: latency
         uint64_t x = 0x123456789abcdef1ull, y = 0xfedcba9876543211ull;
         double t0 = now();
         for (int i = 0; i < N; i++) x = s_mul(x, y);
@@ -96,7 +94,7 @@ T512 int main() {
         report("scalar modmul, 8 independent chains (per op)", now() - t0, N / 8 * 8);
         printf("  [%llu %llu]\n", (unsigned long long)x, (unsigned long long)a[3]);
     }
-    {   // vector modular product
+    if (!quick) {   // vector modular product
         __m512i x = _mm512_set1_epi64(0x123456789abcdef1ll), y = _mm512_set1_epi64(0x7edcba9876543211ll);
         double t0 = now();
         for (int i = 0; i < N / 4; i++) x = v_mul(x, y);
@@ -118,7 +116,7 @@ T512 int main() {
         _mm256_store_si256((__m256i*)out2, _mm256_add_epi64(_mm256_add_epi64(e, f), _mm256_add_epi64(_mm256_add_epi64(g, h), _mm256_add_epi64(e2, f2))));
         printf("  [%llu %llu %llu]\n", (unsigned long long)out[0], (unsigned long long)out2[1], (unsigned long long)_mm256_extract_epi64(p, 0));
     }
-    {   // mixed: one zmm chain + 4 scalar chains side by side (do the scalar ports run under the 512-bit work?)
+    if (!quick) {   // mixed: one zmm chain + 4 scalar chains side by side (do the scalar ports run under the 512-bit work?)
         __m512i x = _mm512_set1_epi64(0x123456789abcdef1ll), y = _mm512_set1_epi64(0x7edcba9876543211ll);
         uint64_t a[4] = {1, 2, 3, 4}, ys = 0xfedcba9876543211ull;
         double t0 = now();
@@ -131,7 +129,7 @@ T512 int main() {
         _mm512_store_si512(out, x);
         printf("  [%llu %llu]\n", (unsigned long long)out[0], (unsigned long long)a[2]);
     }
-    {   // the layers of a full round, each as a dependent chain over (s0, s1)
+    if (!quick) {   // the layers of a full round, each as a dependent chain over (s0, s1)
         const PoseidonFastTables& T = *(const PoseidonFastTables*)sipp_test_poseidon_tables();
         __m512i s0 = _mm512_set_epi64(8, 7, 6, 5, 4, 3, 2, 1), s1 = _mm512_set_epi64(0, 0, 0, 0, 12, 11, 10, 9);
         const int R = 2000000;
