@@ -52,7 +52,9 @@ struct alignas(64) PoseidonIfmaTables {
     uint64_t lam22;                // u0_22 = lam22 z_22
     alignas(64) uint64_t mds_icol_a[12][8];  // PoseidonFastTables::mds_col_a / _b as integers (the MDS layer on vpmadd52luq)
     alignas(64) uint64_t mds_icol_b[12][8];
-    alignas(64) uint64_t mds_icol_p[12][8];  // rows 8..11 for a (low half, high half) pair broadcast: lane l holds the entry of row 8 + l / 2
+    alignas(64) uint64_t mds_icol_p[12][8];
+    alignas(64) uint64_t rc_next[8][2][8];   // [k][low | high 32-bit half][lane 0..7]: the constants the NEXT layer adds to lanes 0..7, folded into the MDS
+                                              // accumulators of full round k (k = 3: `first`; k = 7: nothing follows)  // rows 8..11 for a (low half, high half) pair broadcast: lane l holds the entry of row 8 + l / 2
 };
 
 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T);

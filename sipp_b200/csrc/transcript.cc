@@ -230,7 +230,8 @@ void init_ifma_tables() {
     for (int b = 0; b < 4; b++)
         for (int l = 0; l < 8; l++) {
             const int row = row_of(b, l);
-            const uint64_t K = konst(row);
+            // U-rows 0..6 become lanes 1..7 of the state the second half of the full rounds starts from: their round constant rides along
+            const uint64_t K = row >= 32 && row - 32 < 7 ? gl_canon(gl_add(konst(row), SIPP_POSEIDON_RC[12 * 26 + 1 + (row - 32)])) : konst(row);
             g_ifma.acc_init[b][0][l] = (K & M52) + (GL_P & M52);
             g_ifma.acc_init[b][1][l] = (K >> 52) + (GL_P >> 52);
             for (int i = 0; i < 11; i++) {
@@ -248,6 +249,12 @@ void init_ifma_tables() {
     g_ifma.k0 = konst(0);
     for (int j = 1; j < 22; j++) g_ifma.cdiag[j] = coef_x(j, j - 1);
     g_ifma.lam22 = lam[22];
+    for (int k = 0; k < 8; k++)
+        for (int l = 0; l < 8; l++) {
+            const uint64_t c = k == 7 ? 0 : k == 3 ? g_fp.first[l] : SIPP_POSEIDON_RC[12 * (k < 3 ? k + 1 : 22 + k + 1) + l];
+            g_ifma.rc_next[k][0][l] = c & 0xFFFFFFFFull;
+            g_ifma.rc_next[k][1][l] = c >> 32;
+        }
 }
 struct FastPartialInit {
     FastPartialInit() {

@@ -579,22 +579,6 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
     for (int j = 0; j < 22; j++) {
         const uint64_t p7 = sbox7(u0);
         u0 = chain_close(e, p7);  // z_{j+1}
-        if (j >= 1) {  // the vector terms of x_{j-1}: behind the chain of this round in program order, so the chain is served first
-            const int k = j - 1;
-            if (k <= 6) ifma_unit(A0, xb, xh, I.upd_c[k][0][0]);
-            if (k <= 14) ifma_unit(A1, xb, xh, I.upd_c[k][1][0]);
-            ifma_unit(A2, xb, xh, I.upd_c[k][2][0]);
-            ifma_unit(A3, xb, xh, I.upd_c[k][3][0]);
-        }
-        {
-            const int blk = j <= 5 ? 1 : (j >= 7 && j <= 12) ? 2 : (j >= 13 && j <= 18) ? 3 : 0;
-            const int base = j <= 5 ? 0 : j <= 12 ? 7 : 13;
-            if (blk) {
-                const int i0 = 2 * (j - base);
-                init_unit(i0, blk)
-                if (i0 + 1 < 11) init_unit(i0 + 1, blk)
-            }
-        }
         if (j + 1 <= 21) {  // close C-row j + 1: vector terms k <= j - 1, newest term x_j
             const int row = j + 1, b = row <= 8 ? 0 : row <= 16 ? 1 : row <= 20 ? 2 : 3;
             const int lane = row <= 8 ? row - 1 : row <= 16 ? row - 9 : row <= 20 ? row - 13 : 0;
@@ -602,7 +586,6 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
             BLK_DO(b, ifma_store(lanes, B))
             // (no barrier here: GCC turns this store + three loads into lane extracts, measured 9 ns per permutation faster)
             a0 = lanes[lane]; a1 = lanes[8 + lane]; a2 = lanes[16 + lane];
-            e = row_close(a0, a1, a2, I.cdiag[row], p7);
         }
         xb = _mm512_set1_epi64((long long)p7);
         xh = _mm512_srli_epi64(xb, 52);

@@ -602,7 +602,6 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
             BLK_DO(b, ifma_store(lanes, B))
             // (no barrier here: GCC turns this store + three loads into lane extracts, measured 9 ns per permutation faster)
             a0 = lanes[lane]; a1 = lanes[8 + lane]; a2 = lanes[16 + lane];
-            e = row_close(a0, a1, a2, I.cdiag[row], p7);
         }
         xb = _mm512_set1_epi64((long long)p7);
         xh = _mm512_srli_epi64(xb, 52);
