@@ -65,6 +65,7 @@ bool poseidon_avx512_supported();
 uint64_t poseidon_test_red128(uint64_t lo, uint64_t hi);
 uint64_t poseidon_test_finish(uint64_t lo, uint64_t hi, uint64_t top, uint64_t p7, uint64_t m00);
 uint64_t poseidon_test_sbox(uint64_t u, uint64_t post, uint64_t* x_out);
+uint64_t poseidon_test_vmul_fast(uint64_t x, uint64_t y, int square);  // one lane of the IFMA path's vector product / square
 void poseidon_test_ifma_close(const uint64_t in[5], uint64_t out[2]);  // out[0] = row_close(in...), out[1] = v_close lane of (in[0..2])
 
 }  // namespace sipp

@@ -383,15 +383,20 @@ long sipp_test_poseidon_chain(uint64_t seed, long count) {
 }
 // scalar helpers of the AVX-512 file with crafted operands: which = 0 (lo + 2^64 hi) mod p; 1 the closing multiply-add + reduction of a
 // partial round ((lo + 2^64 hi + 2^128 top) + p7 m00) mod p; 2 u^7 (out[0]) and u^7 + post (out[1]); 3 (IFMA path) the closing of an
-// accumulator lane, in = a0, a1, a2, c, x: out[0] = scalar, out[1] = vector form of (a0 + 2^52 a1 - 2^8 a2 [+ c x]) mod p
+// accumulator lane, in = a0, a1, a2, c, x: out[0] = scalar, out[1] = vector form of (a0 + 2^52 a1 - 2^8 a2 [+ c x]) mod p; 4 (IFMA path) the
+// vector product of the full rounds: out[0] = in[0] in[1], out[1] = in[0]^2
 int sipp_test_poseidon_scalar(int which, const uint64_t* in, uint64_t* out) {
     if (!sipp::poseidon_avx512_supported()) return -1;
     if (which == 0) out[0] = sipp::poseidon_test_red128(in[0], in[1]);
     else if (which == 1) out[0] = sipp::poseidon_test_finish(in[0], in[1], in[2], in[3], in[4]);
     else if (which == 2) out[0] = sipp::poseidon_test_sbox(in[0], in[1], &out[1]);
-    else {
+    else if (which == 3) {
         if (!sipp::poseidon_ifma_supported()) return -1;
         sipp::poseidon_test_ifma_close(in, out);
+    } else {
+        if (!sipp::poseidon_ifma_supported()) return -1;
+        out[0] = sipp::poseidon_test_vmul_fast(in[0], in[1], 0);
+        out[1] = sipp::poseidon_test_vmul_fast(in[0], in[0], 1);
     }
     return 0;
 }  // benchmark hook: tools/probe/poseidon_lab.cc times the layers

@@ -229,6 +229,20 @@ def test_poseidon_avx512_rare_paths():
             sc, ve = call(3, a0, a1, a2, c, x)
             assert sc % PG == (base + c * x) % PG, (hex(a0), hex(a1), hex(a2), hex(c), hex(x))
             assert ve % PG == base % PG, (hex(a0), hex(a1), hex(a2))
+        # the vector product of the full rounds; its borrow fix-up (low word of the 128-bit product below the top 32 bits) is a cold call
+        ops = [(x, y) for x in edge for y in edge] + [(rng.randrange(2**64), rng.randrange(2**64)) for _ in range(3000)]
+        ops += [(2**63, 2**33), (2**32, 2**64 - 2**32), (2**48 + 3, 2**48 * 65535), (PG - 1, PG - 1), (M, M)]
+        for k in range(33, 64):                                       # x y = 2^(64 + k) (1 + small): low word tiny, top half large
+            ops += [(2**k, 2**64 - 2**(64 - k + 32) * rng.randrange(1, 2**(k - 33) + 1)) for _ in range(20)]
+        borrows = 0
+        for x, y in ops:
+            y %= 2**64
+            prod = x * y
+            borrows += (prod & M) < (prod >> 96)
+            m_, s_ = call(4, x, y)
+            assert m_ % PG == prod % PG, (hex(x), hex(y))
+            assert s_ % PG == x * x % PG, hex(x)
+        assert borrows > 50                                           # the crafted operands do reach the fix-up
 
 
 def test_statement_public_input_vector(golden):

@@ -1,4 +1,3 @@
-#define LAB_NO_IFMA_LAYERS 1
 // poseidon_avx512.cc -- AVX-512 implementation of the plonky2 Poseidon permutation over Goldilocks (width 12).
 //
 // The Fiat-Shamir transcript of the SIPP native protocol (/root/reference/src/transcript_native.rs:25-30) is a strictly
@@ -467,9 +466,11 @@ SIPP_IFMA inline uint64_t s_mds_close(uint64_t alo, uint64_t ahi) {
 // second is half empty (134 cycles for the S-box layer against 115 for one vector alone); the four scalar x^7 (33 cycles each,
 // independent) run in the shadow of the vector chain, which comes first in program order so that it is served first.  The
 // scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store.
-SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc16, const PoseidonIfmaTables& I) {
+// Lanes 0..7 arrive with their round constant already added (the previous MDS layer starts its sums from the halves of the NEXT
+// constants, rc_next: an addition less on the vector chain); the scalar lanes add theirs here, off the chain.
+SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc16, const uint64_t* rc_next, const PoseidonIfmaTables& I) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
-    s0 = v_pow7_fast(v_add_canon(s0, _mm512_load_si512(rc16)));
+    s0 = v_pow7_fast(s0);
     // MDS layer.  The 32-bit halves of every lane are stored as (low, high) pairs: a 64-bit broadcast of either feeds rows 0..7,
     // ONE 128-bit broadcast of the pair feeds rows 8..11 (lane 2i: low sums of row 8 + i, lane 2i + 1: high sums) -- no merge of
     // two broadcasts on the vector ports; rows 8..11 are recombined on the scalar ports, where their lanes live.
@@ -496,8 +497,8 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         // (the pairs of the scalar lanes are written by two 8-byte stores: a 16-byte load across them would not be forwarded)
         const __m512i bb = j < 8 ? _mm512_broadcast_i64x2(_mm_load_si128((const __m128i*)q)) : _mm512_mask_blend_epi64(0xAA, bl, bh);
         const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cp = _mm512_load_si512(I.mds_icol_p[j]);
-        al[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : al[j & 3], bl, ca);
-        ah[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ah[j & 3], bh, ca);
+        al[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next) : j < 4 ? zero : al[j & 3], bl, ca);
+        ah[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next + 8) : j < 4 ? zero : ah[j & 3], bh, ca);
         ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cp);
     }
     {
@@ -539,10 +540,10 @@ SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
 SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T, const PoseidonIfmaTables& I) {
     __m512i s0 = _mm512_loadu_si512(s);
     uint64_t t[4] = {s[8], s[9], s[10], s[11]};
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[k], I);
+    s0 = v_add_canon(s0, _mm512_load_si512(T.rc_full[0]));
+    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[k], I.rc_next[k][0], I);
 
-    s0 = v_add_canon(s0, _mm512_load_si512(T.first));
-    alignas(64) uint64_t y[32];  // y[0..11], y[16 + i] = y[i] >> 52
+    alignas(64) uint64_t y[32];  // (lanes 0..7 already carry `first`)  // y[0..11], y[16 + i] = y[i] >> 52
     _mm512_store_si512(y, s0);
     _mm512_store_si512(y + 16, _mm512_srli_epi64(s0, 52));
 #pragma GCC unroll 4
@@ -610,7 +611,7 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
         ifma_unit(A2, xb, xh, I.upd_c[21][2][0]);
         ifma_unit(A3, xb, xh, I.upd_c[21][3][0]);
     }
-    s0 = _mm512_mask_set1_epi64(v_close(A3), 1, (long long)s_mul(u0, I.lam22));
+    s0 = _mm512_mask_set1_epi64(v_close(A3), 1, (long long)s_add1(s_mul(u0, I.lam22), T.rc_full[4][0]));  // (lanes 1..7: the constant is in the rows)
     {
         alignas(64) uint64_t o[8];
         _mm512_store_si512(o, v_close(A2));
@@ -618,7 +619,7 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
         const uint64_t* om = o;
         t[0] = om[0]; t[1] = om[1]; t[2] = om[2]; t[3] = om[3];
     }
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[4 + k], I);
+    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[4 + k], I.rc_next[4 + k][0], I);
     _mm512_storeu_si512(s, v_canon(s0));
     for (int i = 0; i < 4; i++) s[8 + i] = t[i] - (t[i] >= GL_P ? GL_P : 0);
 }
