@@ -390,6 +390,9 @@ SIPP_IFMA inline uint64_t chain_close(uint64_t e, uint64_t z7) {
 SIPP_IFMA __attribute__((noinline, cold)) __m512i v_borrow_fix(__m512i t, __mmask8 b) {
     return _mm512_mask_sub_epi64(t, b, t, _mm512_set1_epi64((long long)EPS));
 }
+SIPP_IFMA __attribute__((noinline, cold)) __m512i v_carry_fix(__m512i r, __mmask8 c) {
+    return _mm512_mask_add_epi64(r, c, r, _mm512_set1_epi64((long long)EPS));
+}
 SIPP_IFMA inline __m512i v_reduce_fast(__m512i lo, __m512i hi) {
     const __m512i eps = _mm512_set1_epi64((long long)EPS);
     __m512i hh = _mm512_srli_epi64(hi, 32);
@@ -510,13 +513,14 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         const __m512i eps = lo32;
         const __m512i alo = _mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3]));
         const __m512i ahi = _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3]));
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
+        // alo + 2^32 ahi = (alo + (ahi >> 32) (2^32 - 1)) + ((ahi mod 2^32) << 32): the first bracket is below 2^45, so the sum wraps only
+        // when the low word of ahi is within 2^13 of 2^32 -- 2^-19 per lane: a cold branch, no compare on the chain
         __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        s0 = _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
+        __m512i small = _mm512_add_epi64(alo, _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi));
+        __m512i r = _mm512_add_epi64(_mm512_slli_epi64(ahi, 32), small);
+        __mmask8 c = _mm512_cmplt_epu64_mask(r, small);
+        if (__builtin_expect(c != 0, 0)) r = v_carry_fix(r, c);
+        s0 = r;
     }
     alignas(64) uint64_t o[8];
     _mm512_store_si512(o, _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3])));

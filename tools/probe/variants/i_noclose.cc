@@ -385,16 +385,29 @@ SIPP_IFMA inline uint64_t chain_close(uint64_t e, uint64_t z7) {
 // Latency-optimised vector product for the path below, where ONE vector (lanes 0..7) is left on the vector ports and its x^7 chain
 // is the critical path of a full round: the partial products are summed as a shallow tree (three 32-bit middle terms, no carry
 // between them) and hl (2^32 - 1) is a shift and a subtraction instead of a multiply -- 28 instead of 35 cycles, four more micro-ops.
-SIPP_IFMA inline __m512i v_reduce_fast(__m512i lo, __m512i hi) {
-    const __m512i eps = _mm512_set1_epi64((long long)EPS);
-    __m512i hh = _mm512_srli_epi64(hi, 32);
-    __m512i t = _mm512_sub_epi64(lo, hh);
-    __mmask8 b = _mm512_cmplt_epu64_mask(lo, hh);
-    t = _mm512_mask_sub_epi64(t, b, t, eps);
-    __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), _mm512_and_si512(hi, eps));
-    __m512i r = _mm512_add_epi64(t, m);
-    __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
-    return _mm512_mask_add_epi64(r, c, r, eps);
+SIPP_IFMA __attribute__((noinline, cold)) __m512i v_carry_fix(__m512i r, __mmask8 c) {
+    return _mm512_mask_add_epi64(r, c, r, _mm512_set1_epi64((long long)EPS));
+}
+// Reduction of a 128-bit product given as (ll: low 32 bits valid, mid: bits 32.. of the low word plus its carry, hs: high word
+// without that carry) with NO compare on the dependent chain.  With hi = hs + (mid >> 32) = 2^32 hh + hl:
+//     x y = lo_lo + 2^32 lo_hi + 2^64 hi  =  (lo_lo - hl - hh) + 2^32 (lo_hi + hl)              (2^64 = 2^32 - 1, 2^96 = -1)
+// and with S = lo_hi + hl = 2^32 s_c + S_lo (s_c = 0, 1):   = 2^32 S_lo + [lo_lo - hl - hh + s_c (2^32 - 1)].
+// The bracket lies in (-2^33, 2^33), so the wrapping 64-bit sum is the exact value unless S_lo is 0, 1 or 2^32 - 1 (2^-30 per
+// lane): those lanes send the whole vector through the generic reduction, behind a branch that is never taken in practice.
+SIPP_IFMA __attribute__((noinline, cold)) __m512i v_reduce_exact(__m512i ll, __m512i mid, __m512i hi) {
+    return v_reduce(v_join(ll, mid), hi);
+}
+SIPP_IFMA inline __m512i v_reduce_chainless(__m512i ll, __m512i mid, __m512i hs) {
+    const __m512i lo32 = _mm512_set1_epi64((long long)EPS), hi32 = _mm512_set1_epi64((long long)0xFFFFFFFF00000000ull);
+    const __m512i hi = _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32));
+    const __m512i hl = _mm512_and_si512(hi, lo32), hh = _mm512_srli_epi64(hi, 32);
+    const __m512i S = _mm512_add_epi64(_mm512_and_si512(mid, lo32), hl);
+    const __m512i d = _mm512_sub_epi64(_mm512_and_si512(ll, lo32), _mm512_add_epi64(hl, hh));
+    const __m512i sce = _mm512_sub_epi64(_mm512_and_si512(S, hi32), _mm512_srli_epi64(S, 32));  // s_c (2^32 - 1)
+    const __m512i r = _mm512_add_epi64(_mm512_add_epi64(_mm512_slli_epi64(S, 32), d), sce);
+    const __mmask8 rare = _mm512_cmplt_epu64_mask(_mm512_and_si512(_mm512_add_epi64(S, _mm512_set1_epi64(1)), lo32), _mm512_set1_epi64(3));
+    if (__builtin_expect(rare != 0, 0)) return v_reduce_exact(ll, mid, hi);
+    return r;
 }
 SIPP_IFMA inline __m512i v_mul_fast(__m512i x, __m512i y) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
@@ -402,7 +415,7 @@ SIPP_IFMA inline __m512i v_mul_fast(__m512i x, __m512i y) {
     __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
     __m512i mid = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(ll, 32), _mm512_and_si512(lh, lo32)), _mm512_and_si512(hl, lo32));
     __m512i hs = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(lh, 32), _mm512_srli_epi64(hl, 32)), hh);
-    return v_reduce_fast(v_join(ll, mid), _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32)));
+    return v_reduce_chainless(ll, mid, hs);
 }
 SIPP_IFMA inline __m512i v_sqr_fast(__m512i x) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
@@ -411,7 +424,7 @@ SIPP_IFMA inline __m512i v_sqr_fast(__m512i x) {
     __m512i lhl = _mm512_and_si512(lh, lo32), lhh = _mm512_srli_epi64(lh, 32);
     __m512i mid = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(ll, 32), lhl), lhl);
     __m512i hs = _mm512_add_epi64(_mm512_add_epi64(lhh, lhh), hh);
-    return v_reduce_fast(v_join(ll, mid), _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32)));
+    return v_reduce_chainless(ll, mid, hs);
 }
 SIPP_IFMA inline __m512i v_pow7_fast(__m512i x) {
     __m512i x2 = v_sqr_fast(x), x4 = v_sqr_fast(x2), x3 = v_mul_fast(x2, x);
@@ -505,13 +518,14 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         const __m512i eps = lo32;
         const __m512i alo = _mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3]));
         const __m512i ahi = _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3]));
-        __m512i lo = _mm512_add_epi64(alo, _mm512_slli_epi64(ahi, 32));
+        // alo + 2^32 ahi = (alo + (ahi >> 32) (2^32 - 1)) + ((ahi mod 2^32) << 32): the first bracket is below 2^45, so the sum wraps only
+        // when the low word of ahi is within 2^13 of 2^32 -- 2^-19 per lane: a cold branch, no compare on the chain
         __m512i hi = _mm512_srli_epi64(ahi, 32);
-        __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi);
-        __m512i r = _mm512_add_epi64(lo, m);
-        __mmask8 c1 = _mm512_cmplt_epu64_mask(lo, alo);
-        __mmask8 c2 = _mm512_cmplt_epu64_mask(r, m);
-        s0 = _mm512_mask_add_epi64(r, (__mmask8)(c1 | c2), r, eps);
+        __m512i small = _mm512_add_epi64(alo, _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi));
+        __m512i r = _mm512_add_epi64(_mm512_slli_epi64(ahi, 32), small);
+        __mmask8 c = _mm512_cmplt_epu64_mask(r, small);
+        if (__builtin_expect(c != 0, 0)) r = v_carry_fix(r, c);
+        s0 = r;
     }
     alignas(64) uint64_t o[8];
     _mm512_store_si512(o, _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3])));
@@ -625,6 +639,17 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
 #undef BLK_DO
 #undef init_unit
 bool poseidon_ifma_supported() { return poseidon_avx512_supported() && __builtin_cpu_supports("avx512ifma"); }
+SIPP_IFMA uint64_t poseidon_test_vmul_fast(uint64_t x, uint64_t y, int square) {
+    alignas(64) uint64_t t[8];
+    const __m512i vx = _mm512_set1_epi64((long long)x), vy = _mm512_set1_epi64((long long)y);
+    _mm512_store_si512(t, square ? v_sqr_fast(vx) : v_mul_fast(vx, vy));
+    return t[5];
+}
+SIPP_IFMA uint64_t poseidon_test_reduce_chainless(uint64_t ll, uint64_t mid, uint64_t hs) {
+    alignas(64) uint64_t t[8];
+    _mm512_store_si512(t, v_reduce_chainless(_mm512_set1_epi64((long long)ll), _mm512_set1_epi64((long long)mid), _mm512_set1_epi64((long long)hs)));
+    return t[2];
+}
 SIPP_IFMA void poseidon_test_ifma_close(const uint64_t in[5], uint64_t out[2]) {
     out[0] = row_close(in[0], in[1], in[2], in[3], in[4]);
     IfmaBlock B;
@@ -721,6 +746,8 @@ void poseidon_permute_avx512(uint64_t*, const PoseidonFastTables&) {}
 void poseidon_permute_ifma(uint64_t*, const PoseidonFastTables&, const PoseidonIfmaTables&) {}
 bool poseidon_ifma_supported() { return false; }
 void poseidon_test_ifma_close(const uint64_t*, uint64_t*) {}
+uint64_t poseidon_test_vmul_fast(uint64_t, uint64_t, int) { return 0; }
+uint64_t poseidon_test_reduce_chainless(uint64_t, uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_red128(uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_finish(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_sbox(uint64_t, uint64_t, uint64_t*) { return 0; }
