@@ -4,7 +4,7 @@
 // sequential chain of 8n + 13 + 27 log2(n) permutations (prover_native.rs:36-39 absorbs every A_i, B_i) that must stay on
 // the host; at the sizes the GPU finishes in milliseconds this chain IS the prove time, so one permutation has to be as
 // short as the machine allows.  This file computes exactly the same function as the portable code in transcript.cc
-// (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2):
+// (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2; with AVX-512 IFMA as well, the faster path described below):
 //   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products (high halves by
 //                  movehdup, the low word joined by moveldup + blend: port 5 instead of more shifts on port 0) and the
 //                  2^64 = 2^32 - 1, 2^96 = -1 reduction; the circulant MDS layer as 36 FP64 FMAs on the 32-bit halves
@@ -21,6 +21,21 @@
 // port-balanced vector product) -> 1.012 (a partial round as three hand-allocated asm blocks) -> 1.004 us per permutation (the
 // two carries of the MDS recombination decided in parallel).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
 // 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
+//
+// A second path (poseidon_permute_ifma, used when the CPU also has AVX-512 IFMA) computes the same function in 0.611 us:
+//   partial rounds every rank-1 update unrolled algebraically (PoseidonIfmaTables, poseidon_fast.h): the state after round j is a
+//                  linear function of the entering state y and the S-box outputs x_0..x_j, so the 22 x (11-term sum + 11 updates)
+//                  become 32 row sums fed by vpmadd52luq / vpmadd52huq -- seven instructions per eight 64 x 64-bit products, one
+//                  reduction per ROW instead of one per product -- and the chain variable is rescaled round by round so that a
+//                  round's dependent chain is the S-box and one modular addition (36 cycles; 22 rounds: ~950 instead of 2,020)
+//   full rounds    lanes 0..7 in ONE vector with a latency-optimised product, lanes 8..11 on the scalar ports in its shadow; MDS
+//                  layer on vpmadd52luq (32-bit halves x small entries are exact, no int <-> double conversions) with the round
+//                  constants of the next layer as initial values; 170 instead of 230 cycles
+//   lessons kept in the code: SIPP_THROUGH_MEMORY (GCC forwards stored vectors through port-5 shuffles unless told not to: 93 -> 74
+//                  cycles per MDS layer), accumulators as named variables selected by switch (an array or a pointer select keeps
+//                  them in memory), every vector compare that can be made rare moved behind a cold branch.
+// Steps on the box: 1.004 -> 0.755 (IFMA partial rounds) -> 0.742 (IFMA MDS) -> 0.726 (scalar lanes 8..11, fast product) -> 0.669
+// (real memory broadcasts) -> 0.644 (constants folded) -> 0.613 (borrow on a cold branch) -> 0.611 us (MDS carry on a cold branch).
 #include <immintrin.h>
 #include <stdint.h>
 #include <string.h>
