@@ -83,7 +83,7 @@ int sipp_device_count(void);          /* 0 when no usable GPU: callers must trea
                                          computed for all block pairs in one launch set, and log2(R) rounds take Z_L, Z_R from that matrix
                                          while the points are folded on a side stream, off the critical path */
 #define SIPP_OPT_MATRIX_FIRST 17      /* 1 [default]: the FIRST stage is built from the inputs themselves (n / 32 blocks, between 8 and 32, inside a budget
-                                         of 16 n (n <= 2^11) or 32 n Miller loops, at most 2^18) while the host still hashes A and B: Z is the
+                                         of n^2 / 128 (2^9 <= n < 2^12) or 32 n Miller loops, at most 2^18) while the host still hashes A and B: Z is the
                                          product of its diagonal and the first log2(blocks) rounds are one matrix fold each.  10..24 = the
                                          budget is 2^value loops whatever n.  0 = the first rounds run on the points */
 #define SIPP_OPT_MATRIX_BLOCK_R 16    /* blocks per look-ahead stage: 4, 8 (default), 16 or 32 (capped so that the stage ends where the tail begins) */

@@ -348,11 +348,12 @@ size_t mat_stage(size_t n) {
 // 8n-permutation absorb chain, gives Z as the product of its diagonal, and the first log2(nr) rounds cost one matrix fold each.
 // Miller loops the first stage may spend.  It has to finish inside the host's absorb of the same inputs: 8 n permutations of 0.67 us
 // against ~6 M loops/s plus ~2.5 ms of fixed work (validation, line coefficients, final exponentiations), i.e. about 32 n - 15,000
-// loops.  Measured on the box (tools/first_ab.py, profiles/r02_v8_first_stage_ab.txt): 16 n is best up to n = 2^11, 32 n from 2^12
-// (slightly over, but it saves a round); the absolute cap bounds the line table (29 KB per loop).
+// loops.  Measured on the box (tools/first_ab.py, profiles/r02_v8_first_stage_ab.txt): best are n / 128 blocks from n = 2^9 (4 blocks)
+// to 2^12 (32 blocks: slightly over, but it saves a round), 8 blocks at 2^8, 32 n loops above; the absolute cap bounds the line
+// table (29 KB per loop).
 size_t mat_first_budget(size_t n) {
     if (g_opt_matrix_first >= 10) return (size_t)1 << g_opt_matrix_first;
-    const size_t by_n = n <= 2048 ? 16 * n : 32 * n, cap = (size_t)1 << SIPP_FIRST_STAGE_LOG2_LOOPS;
+    const size_t by_n = n <= 256 ? 16 * n : n < 4096 ? n * (n / 128) : 32 * n, cap = (size_t)1 << SIPP_FIRST_STAGE_LOG2_LOOPS;
     return by_n < cap ? by_n : cap;
 }
 size_t mat_stage_first(size_t n) {

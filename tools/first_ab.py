@@ -8,7 +8,7 @@ sizes = [int(a) for a in sys.argv[1:]] or [1024, 2048, 4096, 8192]
 for n in sizes:
     A, B = sipp_b200.seeded_inputs(2, n)
     ref = None
-    for cap in (0, 14, 15, 16, 17, 18, 16, 17):
+    for cap in [int(c) for c in os.environ.get('FIRST_AB_CAPS', '0,14,15,16,17,18,16,17').split(',')]:
         sipp_b200.set_option(_lib.OPT_MATRIX_FIRST, cap)
         sipp_b200.sipp_prove_native(A, B)
         ts = []
