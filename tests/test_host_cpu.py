@@ -1,6 +1,7 @@
 """CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the header declares,
 fails loudly without a GPU, and its Poseidon transcript (host code, like the reference's) matches the golden vectors."""
 import ctypes
+import json
 import os
 import re
 
@@ -170,6 +171,41 @@ def test_poseidon_avx512_matches_portable():
         lib.sipp_poseidon_permute_portable(b)
         assert list(a) == list(b), it
         st = list(a)
+
+
+def test_poseidon_golden_on_every_backend(golden):
+    """the permutation known answers and a transcript through each implementation this CPU can run (SIPP_POSEIDON forces the
+    slower ones at load time, so each runs in its own process)"""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes, json, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import sipp_b200\n"
+        "from sipp_b200 import _lib\n"
+        "lib = _lib.load()\n"
+        "def perm(st):\n"
+        "    a = (ctypes.c_uint64 * 12)(*st); lib.sipp_poseidon_permute(a); return ['%%016x' %% v for v in a]\n"
+        "t = sipp_b200.Transcript(); t.append(list(range(1, 30)))\n"
+        "print(json.dumps({'backend': lib.sipp_poseidon_backend(), 'zero': perm([0] * 12), 'iota': perm(list(range(12))),\n"
+        "                  'pm1': perm([2**64 - 2**32] * 12), 'state': ['%%016x' %% v for v in t.state], 'ch': t.get_challenge().hex()}))\n"
+    ) % ROOT
+    seen = {}
+    for force in ("", "avx512", "portable"):
+        env = dict(os.environ)
+        env.pop("SIPP_POSEIDON", None)
+        if force:
+            env["SIPP_POSEIDON"] = force
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+        g = golden["poseidon"]
+        assert r["zero"] == g["perm_zero"] and r["iota"] == g["perm_iota"] and r["pm1"] == g["perm_pm1"], (force, r["backend"])
+        seen[force] = r
+    assert seen["portable"]["backend"] == 0
+    assert seen["avx512"]["backend"] <= 1 and seen[""]["backend"] >= seen["avx512"]["backend"]
+    assert seen[""]["state"] == seen["avx512"]["state"] == seen["portable"]["state"]
+    assert seen[""]["ch"] == seen["avx512"]["ch"] == seen["portable"]["ch"]
 
 
 def test_poseidon_avx512_rare_paths():
