@@ -304,6 +304,8 @@ int sipp_microbench(int which, int iters, double *ops_per_s, double *ms);
 /* host Poseidon self-checks (no GPU): a chain of `count` permutations by the AVX-512 and the portable code side by side, index of the
  * first mismatch or -1; the scalar helpers of the AVX-512 file on crafted operands (which = 0: (in[0] + 2^64 in[1]) mod p; 1: the closing
  * multiply-add of a partial round, in = lo, hi, top, p7, m00; 2: out[0] = in[0]^7, out[1] = in[0]^7 + in[1]; 3, 4: pieces of the IFMA path, see transcript.cc); -1 without AVX-512 / IFMA */
+/* the pairing-matrix stage policy (host logic only): blocks of the first stage (which = 0) or of a later stage (which = 1) at n points; 0 = none */
+long sipp_test_stage_blocks(int which, size_t n);
 long sipp_test_poseidon_chain(uint64_t seed, long count);
 int sipp_test_poseidon_scalar(int which, const uint64_t *in, uint64_t *out);
 /* the derived tables of the host Poseidon (sipp::PoseidonFastTables, poseidon_fast.h), for tools/probe/poseidon_lab.cc */

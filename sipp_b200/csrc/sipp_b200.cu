@@ -642,6 +642,8 @@ int sipp_set_option(int option, int value) {
         default: return fail(SIPP_ERR_ARG, "unknown option");
     }
 }
+// host-side stage policy, no device needed: blocks of the first stage (which >= 0: 0 = first stage, 1 = a later stage) for n points
+long sipp_test_stage_blocks(int which, size_t n) { return (long)(which == 0 ? mat_stage_first(n) : mat_stage(n)); }
 int sipp_get_option(int option) {
     switch (option) {
         case SIPP_OPT_FE_NORMALISATION: return g_opt_fe_norm;

@@ -173,6 +173,21 @@ def test_poseidon_avx512_matches_portable():
         st = list(a)
 
 
+def test_stage_policy_table():
+    """the sizes of the pairing-matrix stages are host logic: the first stage follows the host's absorb time (box A/B in
+    profiles/r02_v8_first_stage_ab.txt), later stages are 8 blocks from 256 points and single points from 32"""
+    from sipp_b200 import _lib
+    lib = _lib.load()
+    lib.sipp_test_stage_blocks.argtypes = [ctypes.c_int, ctypes.c_size_t]
+    lib.sipp_test_stage_blocks.restype = ctypes.c_long
+    first = {n: lib.sipp_test_stage_blocks(0, n) for n in (2, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 65536, 2**20)}
+    assert first == {2: 2, 16: 16, 32: 32, 64: 8, 128: 8, 256: 8, 512: 4, 1024: 8, 2048: 16, 4096: 32, 8192: 32, 16384: 16, 65536: 4, 2**20: 0}, first
+    later = {n: lib.sipp_test_stage_blocks(1, n) for n in (16, 32, 64, 128, 256, 512, 4096)}
+    assert later == {16: 16, 32: 32, 64: 4, 128: 8, 256: 8, 512: 0, 4096: 0}, later
+    for n, nr in first.items():
+        assert nr == 0 or (n % nr == 0 and nr * n <= 2**18)
+
+
 def test_poseidon_golden_on_every_backend(golden):
     """the permutation known answers and a transcript through each implementation this CPU can run (SIPP_POSEIDON forces the
     slower ones at load time, so each runs in its own process)"""
