@@ -622,7 +622,12 @@ def main():
                        "fe_normalisation": "exact", "fq12_transcript_order": "w-basis", "parity": parity,
                        "pairing_matrix_stages": {"tail": lib.sipp_get_option(_lib.OPT_MATRIX_TAIL), "block_n": lib.sipp_get_option(_lib.OPT_MATRIX_BLOCK_N),
                                                  "block_r": lib.sipp_get_option(_lib.OPT_MATRIX_BLOCK_R), "first": lib.sipp_get_option(_lib.OPT_MATRIX_FIRST)},
-                       "nccl_version": lib.sipp_comm_nccl_version() if world > 1 else None},
+                       "nccl_version": lib.sipp_comm_nccl_version() if world > 1 else None,
+                       "host_transcript": {"poseidon_backend": {2: "AVX-512 IFMA", 1: "AVX-512", 0: "portable"}.get(lib.sipp_poseidon_backend()),
+                                           "ns_per_permutation": lib.sipp_poseidon_ns_per_permutation(200000),
+                                           "permutations_per_prove": 8 * n + 13 + 27 * log2(n),
+                                           "note": "strictly serial chain on rank 0's host (prover_native.rs:36-39, transcript_native.rs:25-30); "
+                                                   "measured in this run on this box's CPU"}},
             "prove_s": t_res / K, "miller_loops_per_s_per_gpu": miller_loops_per_prove(n) * K / t_res / world,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / K * 1e3,
                     "note": "h2d summed over the ranks; rank 0 additionally reads the full host copy of A, B for the transcript (no device traffic)"},

@@ -197,7 +197,8 @@ void sipp_transcript_get_challenge(const sipp_transcript *t, uint8_t x[32]);    
 void sipp_transcript_append_pairs(sipp_transcript *t, const uint8_t *A, const uint8_t *B, size_t n);
 void sipp_poseidon_permute(uint64_t state[12]);          /* AVX-512 when the CPU has it, else portable */
 void sipp_poseidon_permute_portable(uint64_t state[12]);
-int sipp_poseidon_backend(void);                          /* 1 = AVX-512, 0 = portable */
+int sipp_poseidon_backend(void);                          /* 2 = AVX-512 IFMA, 1 = AVX-512, 0 = portable (SIPP_POSEIDON=avx512|portable forces a slower one) */
+double sipp_poseidon_ns_per_permutation(long count);      /* measured on this CPU: a dependent chain of `count` permutations, best of three */
 
 /* ---- whole protocol with the C++ host transcript inside (what the Python mirror and bench.py call) ------ */
 /* pub fn sipp_prove_native(A, B) -> Vec<Fq12>                  prover_native.rs:26-80

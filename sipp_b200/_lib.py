@@ -62,6 +62,8 @@ def load():
     vp, sz, u8p, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int
     lib.sipp_last_error.restype = ctypes.c_char_p
     lib.sipp_ctx_create.argtypes = [u8p, u8p, sz, ctypes.POINTER(vp)]
+    lib.sipp_poseidon_ns_per_permutation.argtypes = [ctypes.c_long]
+    lib.sipp_poseidon_ns_per_permutation.restype = ctypes.c_double
     lib.sipp_ctx_create_from_device.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     lib.sipp_ctx_destroy.argtypes = [vp]
     lib.sipp_ctx_len.argtypes = [vp]

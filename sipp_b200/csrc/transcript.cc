@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+
 #include "../../include/sipp_b200.h"
 #include "poseidon_fast.h"
 #include "poseidon_rc.h"
@@ -361,6 +363,19 @@ void sipp_poseidon_permute(uint64_t s[12]) {
 }
 int sipp_poseidon_backend(void) { return g_use_ifma ? 2 : g_use_avx512 ? 1 : 0; }
 const void* sipp_test_poseidon_ifma_tables(void) { return &g_ifma; }
+// nanoseconds per permutation of the selected back end on this CPU: a dependent chain of `count` permutations (what the absorb of
+// A, B is), best of three -- bench.py reports it next to the prove time it explains
+double sipp_poseidon_ns_per_permutation(long count) {
+    uint64_t s[12] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12};
+    double best = 1e300;
+    for (int rep = 0; rep < 3 && count > 0; rep++) {
+        auto t0 = std::chrono::steady_clock::now();
+        for (long i = 0; i < count; i++) sipp_poseidon_permute(s);
+        const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / (double)count;
+        if (ns < best) best = ns;
+    }
+    return s[0] == 0 ? -best : best;  // (keeps the chain alive)
+}
 const void* sipp_test_poseidon_tables(void) { return &g_tab; }
 // a chain of `count` permutations run by the AVX-512 and the portable code side by side; returns the index of the first
 // permutation whose outputs differ, -1 if none (or if the CPU has no AVX-512).  The rare carry paths of the vector code need
