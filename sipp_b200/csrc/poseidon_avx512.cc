@@ -474,24 +474,15 @@ SIPP_IFMA inline uint64_t sbox7(uint64_t u) {
         : "rdx", "cc");
     return a;
 }
-// (alo + 2^32 ahi) mod p for the two sums (< 2^43) of an MDS row
-SIPP_IFMA inline uint64_t s_mds_close(uint64_t alo, uint64_t ahi) {
-    unsigned long long t;
-    const uint64_t eps = EPS;
-    asm("mov %[ahi], %[t]\n\t" "shl $32, %[t]\n\t" "shr $32, %[ahi]\n\t" "add %[t], %[alo]\n\t" "adc $0, %[ahi]\n\t"
-        "mov %[ahi], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[ahi], %[t]\n\t" "add %[t], %[alo]\n\t" "lea (%[alo],%[eps]), %[t]\n\t" "cmovc %[t], %[alo]"
-        : [alo] "+r"(alo), [ahi] "+r"(ahi), [t] "=&r"(t)
-        : [eps] "r"(eps)
-        : "cc");
-    return alo;
-}
 // A full round with lanes 0..7 in one vector and lanes 8..11 on the scalar ports.  Two zmm x^7 share the two 512-bit ports and the
 // second is half empty (134 cycles for the S-box layer against 115 for one vector alone); the four scalar x^7 (33 cycles each,
 // independent) run in the shadow of the vector chain, which comes first in program order so that it is served first.  The
-// scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store.
-// Lanes 0..7 arrive with their round constant already added (the previous MDS layer starts its sums from the halves of the NEXT
-// constants, rc_next: an addition less on the vector chain); the scalar lanes add theirs here, off the chain.
-SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc16, const uint64_t* rc_next, const PoseidonIfmaTables& I) {
+// scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store
+// (every scalar instruction saved here is worth ~0.3 cycles per round: the round is bound by the total micro-op flow, see the
+// ablations in tools/probe/README.md -- so rows 8..11 are recombined on the vector side and carry their constants too).
+// All lanes arrive with their round constant already added: the previous MDS layer starts its sums from the halves of the NEXT
+// constants (rc_next) -- an addition less on the vector chain, four fewer scalar additions.
+SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc_next, const PoseidonIfmaTables& I) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
     s0 = v_pow7_fast(s0);
     // MDS layer.  The 32-bit halves of every lane are stored as (low, high) pairs: a 64-bit broadcast of either feeds rows 0..7,
@@ -500,7 +491,7 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
     alignas(64) uint64_t pr[24];
 #pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
-        const uint64_t q = sbox7(s_add1(t[i], rc16[8 + i]));
+        const uint64_t q = sbox7(t[i]);
         pr[16 + 2 * i] = (uint32_t)q;
         pr[17 + 2 * i] = q >> 32;
     }
@@ -522,27 +513,29 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cp = _mm512_load_si512(I.mds_icol_p[j]);
         al[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next) : j < 4 ? zero : al[j & 3], bl, ca);
         ah[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next + 8) : j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cp);
+        ab[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next + 16) : j < 4 ? zero : ab[j & 3], bb, cp);
     }
-    {
-        const __m512i eps = lo32;
-        const __m512i alo = _mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3]));
-        const __m512i ahi = _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3]));
-        // alo + 2^32 ahi = (alo + (ahi >> 32) (2^32 - 1)) + ((ahi mod 2^32) << 32): the first bracket is below 2^45, so the sum wraps only
-        // when the low word of ahi is within 2^13 of 2^32 -- 2^-19 per lane: a cold branch, no compare on the chain
+    // alo + 2^32 ahi = (alo + (ahi >> 32) (2^32 - 1)) + ((ahi mod 2^32) << 32): the first bracket is below 2^45, so the sum wraps only
+    // when the low word of ahi is within 2^13 of 2^32 -- 2^-19 per lane: a cold branch, no compare on the chain
+    auto combine = [&](__m512i alo, __m512i ahi) SIPP_IFMA {
         __m512i hi = _mm512_srli_epi64(ahi, 32);
         __m512i small = _mm512_add_epi64(alo, _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi));
         __m512i r = _mm512_add_epi64(_mm512_slli_epi64(ahi, 32), small);
         __mmask8 c = _mm512_cmplt_epu64_mask(r, small);
         if (__builtin_expect(c != 0, 0)) r = v_carry_fix(r, c);
-        s0 = r;
-    }
+        return r;
+    };
+    s0 = combine(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
+                 _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
+    // rows 8..11: (low, high) sums side by side; the high ones move one lane down and the same recombination leaves the rows in
+    // the even lanes -- 7 vector instructions instead of 4 x 11 scalar ones
+    const __m512i bi = _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3]));
     alignas(64) uint64_t o[8];
-    _mm512_store_si512(o, _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3])));
+    _mm512_store_si512(o, combine(bi, _mm512_alignr_epi64(bi, bi, 1)));
     SIPP_THROUGH_MEMORY(o);
     const uint64_t* om = o;
 #pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) t[i] = s_mds_close(om[2 * i], om[2 * i + 1]);
+    for (int i = 0; i < 4; i++) t[i] = om[2 * i];
 }
 // all eight lanes of a block closed at once: (a0 + 2^52 a1 - 2^8 a2) mod p
 SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
@@ -563,17 +556,18 @@ SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
 
 SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T, const PoseidonIfmaTables& I) {
     __m512i s0 = _mm512_loadu_si512(s);
-    uint64_t t[4] = {s[8], s[9], s[10], s[11]};
+    uint64_t t[4];
+    for (int i = 0; i < 4; i++) t[i] = s_add1(s[8 + i], T.rc_full[0][8 + i]);
     s0 = v_add_canon(s0, _mm512_load_si512(T.rc_full[0]));
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[k], I.rc_next[k][0], I);
+    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, I.rc_next[k][0], I);
 
     alignas(64) uint64_t y[32];  // (lanes 0..7 already carry `first`)  // y[0..11], y[16 + i] = y[i] >> 52
     _mm512_store_si512(y, s0);
     _mm512_store_si512(y + 16, _mm512_srli_epi64(s0, 52));
 #pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
-        y[8 + i] = s_add1(t[i], T.first[8 + i]);
-        y[24 + i] = y[8 + i] >> 52;
+        y[8 + i] = t[i];  // (`first` rode along in the MDS layer of the fourth full round)
+        y[24 + i] = t[i] >> 52;
     }
     // four named blocks selected by switch statements, never through a pointer or an array index: anything else keeps the twelve
     // accumulators in memory (a load and a store around every vpmadd52)
@@ -643,7 +637,7 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
         const uint64_t* om = o;
         t[0] = om[0]; t[1] = om[1]; t[2] = om[2]; t[3] = om[3];
     }
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[4 + k], I.rc_next[4 + k][0], I);
+    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, I.rc_next[4 + k][0], I);
     _mm512_storeu_si512(s, v_canon(s0));
     for (int i = 0; i < 4; i++) s[8 + i] = t[i] - (t[i] >= GL_P ? GL_P : 0);
 }

@@ -53,8 +53,9 @@ struct alignas(64) PoseidonIfmaTables {
     alignas(64) uint64_t mds_icol_a[12][8];  // PoseidonFastTables::mds_col_a / _b as integers (the MDS layer on vpmadd52luq)
     alignas(64) uint64_t mds_icol_b[12][8];
     alignas(64) uint64_t mds_icol_p[12][8];
-    alignas(64) uint64_t rc_next[8][2][8];   // [k][low | high 32-bit half][lane 0..7]: the constants the NEXT layer adds to lanes 0..7, folded into the MDS
-                                              // accumulators of full round k (k = 3: `first`; k = 7: nothing follows)  // rows 8..11 for a (low half, high half) pair broadcast: lane l holds the entry of row 8 + l / 2
+    alignas(64) uint64_t rc_next[8][3][8];   // the constants the NEXT layer adds, folded into the MDS accumulators of full round k (k = 3: `first`; k = 7:
+                                              // nothing follows): [k][0 | 1][lane 0..7] low | high 32-bit halves for lanes 0..7; [k][2][2 i | 2 i + 1] the
+                                              // (low, high) halves for lane 8 + i  // rows 8..11 for a (low half, high half) pair broadcast: lane l holds the entry of row 8 + l / 2
 };
 
 void poseidon_permute_avx512(uint64_t s[12], const PoseidonFastTables& T);

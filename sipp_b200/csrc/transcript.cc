@@ -232,8 +232,8 @@ void init_ifma_tables() {
     for (int b = 0; b < 4; b++)
         for (int l = 0; l < 8; l++) {
             const int row = row_of(b, l);
-            // U-rows 0..6 become lanes 1..7 of the state the second half of the full rounds starts from: their round constant rides along
-            const uint64_t K = row >= 32 && row - 32 < 7 ? gl_canon(gl_add(konst(row), SIPP_POSEIDON_RC[12 * 26 + 1 + (row - 32)])) : konst(row);
+            // the U-rows become lanes 1..11 of the state the second half of the full rounds starts from: their round constant rides along
+            const uint64_t K = row >= 32 ? gl_canon(gl_add(konst(row), SIPP_POSEIDON_RC[12 * 26 + 1 + (row - 32)])) : konst(row);
             g_ifma.acc_init[b][0][l] = (K & M52) + (GL_P & M52);
             g_ifma.acc_init[b][1][l] = (K >> 52) + (GL_P >> 52);
             for (int i = 0; i < 11; i++) {
@@ -256,6 +256,9 @@ void init_ifma_tables() {
             const uint64_t c = k == 7 ? 0 : k == 3 ? g_fp.first[l] : SIPP_POSEIDON_RC[12 * (k < 3 ? k + 1 : 22 + k + 1) + l];
             g_ifma.rc_next[k][0][l] = c & 0xFFFFFFFFull;
             g_ifma.rc_next[k][1][l] = c >> 32;
+            const int hl = 8 + (l >> 1);  // lanes 8..11 as (low, high) pairs
+            const uint64_t d = k == 7 ? 0 : k == 3 ? g_fp.first[hl] : SIPP_POSEIDON_RC[12 * (k < 3 ? k + 1 : 22 + k + 1) + hl];
+            g_ifma.rc_next[k][2][l] = (l & 1) ? d >> 32 : d & 0xFFFFFFFFull;
         }
 }
 struct FastPartialInit {

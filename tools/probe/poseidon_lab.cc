@@ -61,7 +61,7 @@ template <class Rep> SIPP_IFMA static void lab_ifma_layers(__m512i& s0, const Po
     for (int i = 0; i < R; i++) s0 = v_mul_fast(s0, s0);
     report("IFMA path: fast zmm modmul, chained", now() - t0, R);
     t0 = now();
-    for (int i = 0; i < R; i++) full_round_mixed(s0, t, T.rc_full[i & 7], I.rc_next[i & 7][0], I);
+    for (int i = 0; i < R; i++) full_round_mixed(s0, t, I.rc_next[i & 7][0], I);
     report("IFMA path: mixed full round, chained", now() - t0, R);
     printf("  [%llu]\n", (unsigned long long)t[0]);
 }

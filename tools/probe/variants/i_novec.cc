@@ -4,7 +4,7 @@
 // sequential chain of 8n + 13 + 27 log2(n) permutations (prover_native.rs:36-39 absorbs every A_i, B_i) that must stay on
 // the host; at the sizes the GPU finishes in milliseconds this chain IS the prove time, so one permutation has to be as
 // short as the machine allows.  This file computes exactly the same function as the portable code in transcript.cc
-// (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2):
+// (selected at run time when the CPU has AVX-512 F/DQ/VL + BMI2; with AVX-512 IFMA as well, the faster path described below):
 //   full rounds    state in two zmm registers (lanes 0..7, 8..11); x^7 with 4 x vpmuludq 64x64->128 products (high halves by
 //                  movehdup, the low word joined by moveldup + blend: port 5 instead of more shifts on port 0) and the
 //                  2^64 = 2^32 - 1, 2^96 = -1 reduction; the circulant MDS layer as 36 FP64 FMAs on the 32-bit halves
@@ -21,6 +21,21 @@
 // port-balanced vector product) -> 1.012 (a partial round as three hand-allocated asm blocks) -> 1.004 us per permutation (the
 // two carries of the MDS recombination decided in parallel).  Layer times: vector product 36 cycles latency / 12.8 throughput, S-box layer
 // 135 cycles (latency-bound: 3 dependent products), MDS layer ~95, full round 230, partial round ~92 (scalar x^7 chain 33).
+//
+// A second path (poseidon_permute_ifma, used when the CPU also has AVX-512 IFMA) computes the same function in 0.611 us:
+//   partial rounds every rank-1 update unrolled algebraically (PoseidonIfmaTables, poseidon_fast.h): the state after round j is a
+//                  linear function of the entering state y and the S-box outputs x_0..x_j, so the 22 x (11-term sum + 11 updates)
+//                  become 32 row sums fed by vpmadd52luq / vpmadd52huq -- seven instructions per eight 64 x 64-bit products, one
+//                  reduction per ROW instead of one per product -- and the chain variable is rescaled round by round so that a
+//                  round's dependent chain is the S-box and one modular addition (36 cycles; 22 rounds: ~950 instead of 2,020)
+//   full rounds    lanes 0..7 in ONE vector with a latency-optimised product, lanes 8..11 on the scalar ports in its shadow; MDS
+//                  layer on vpmadd52luq (32-bit halves x small entries are exact, no int <-> double conversions) with the round
+//                  constants of the next layer as initial values; 170 instead of 230 cycles
+//   lessons kept in the code: SIPP_THROUGH_MEMORY (GCC forwards stored vectors through port-5 shuffles unless told not to: 93 -> 74
+//                  cycles per MDS layer), accumulators as named variables selected by switch (an array or a pointer select keeps
+//                  them in memory), every vector compare that can be made rare moved behind a cold branch.
+// Steps on the box: 1.004 -> 0.755 (IFMA partial rounds) -> 0.742 (IFMA MDS) -> 0.726 (scalar lanes 8..11, fast product) -> 0.669
+// (real memory broadcasts) -> 0.644 (constants folded) -> 0.613 (borrow on a cold branch) -> 0.611 us (MDS carry on a cold branch).
 #include <immintrin.h>
 #include <stdint.h>
 #include <string.h>
@@ -385,29 +400,24 @@ SIPP_IFMA inline uint64_t chain_close(uint64_t e, uint64_t z7) {
 // Latency-optimised vector product for the path below, where ONE vector (lanes 0..7) is left on the vector ports and its x^7 chain
 // is the critical path of a full round: the partial products are summed as a shallow tree (three 32-bit middle terms, no carry
 // between them) and hl (2^32 - 1) is a shift and a subtraction instead of a multiply -- 28 instead of 35 cycles, four more micro-ops.
+// the borrow of lo - (hi >> 32) needs lo < 2^32: 2^-32 per lane.  Its fix is a cold out-of-line call behind a branch on the mask
+// (kortest + jne, predicted), so the compare is off the dependent chain of the product: 3 cycles less per product.
+SIPP_IFMA __attribute__((noinline, cold)) __m512i v_borrow_fix(__m512i t, __mmask8 b) {
+    return _mm512_mask_sub_epi64(t, b, t, _mm512_set1_epi64((long long)EPS));
+}
 SIPP_IFMA __attribute__((noinline, cold)) __m512i v_carry_fix(__m512i r, __mmask8 c) {
     return _mm512_mask_add_epi64(r, c, r, _mm512_set1_epi64((long long)EPS));
 }
-// Reduction of a 128-bit product given as (ll: low 32 bits valid, mid: bits 32.. of the low word plus its carry, hs: high word
-// without that carry) with NO compare on the dependent chain.  With hi = hs + (mid >> 32) = 2^32 hh + hl:
-//     x y = lo_lo + 2^32 lo_hi + 2^64 hi  =  (lo_lo - hl - hh) + 2^32 (lo_hi + hl)              (2^64 = 2^32 - 1, 2^96 = -1)
-// and with S = lo_hi + hl = 2^32 s_c + S_lo (s_c = 0, 1):   = 2^32 S_lo + [lo_lo - hl - hh + s_c (2^32 - 1)].
-// The bracket lies in (-2^33, 2^33), so the wrapping 64-bit sum is the exact value unless S_lo is 0, 1 or 2^32 - 1 (2^-30 per
-// lane): those lanes send the whole vector through the generic reduction, behind a branch that is never taken in practice.
-SIPP_IFMA __attribute__((noinline, cold)) __m512i v_reduce_exact(__m512i ll, __m512i mid, __m512i hi) {
-    return v_reduce(v_join(ll, mid), hi);
-}
-SIPP_IFMA inline __m512i v_reduce_chainless(__m512i ll, __m512i mid, __m512i hs) {
-    const __m512i lo32 = _mm512_set1_epi64((long long)EPS), hi32 = _mm512_set1_epi64((long long)0xFFFFFFFF00000000ull);
-    const __m512i hi = _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32));
-    const __m512i hl = _mm512_and_si512(hi, lo32), hh = _mm512_srli_epi64(hi, 32);
-    const __m512i S = _mm512_add_epi64(_mm512_and_si512(mid, lo32), hl);
-    const __m512i d = _mm512_sub_epi64(_mm512_and_si512(ll, lo32), _mm512_add_epi64(hl, hh));
-    const __m512i sce = _mm512_sub_epi64(_mm512_and_si512(S, hi32), _mm512_srli_epi64(S, 32));  // s_c (2^32 - 1)
-    const __m512i r = _mm512_add_epi64(_mm512_add_epi64(_mm512_slli_epi64(S, 32), d), sce);
-    const __mmask8 rare = _mm512_cmplt_epu64_mask(_mm512_and_si512(_mm512_add_epi64(S, _mm512_set1_epi64(1)), lo32), _mm512_set1_epi64(3));
-    if (__builtin_expect(rare != 0, 0)) return v_reduce_exact(ll, mid, hi);
-    return r;
+SIPP_IFMA inline __m512i v_reduce_fast(__m512i lo, __m512i hi) {
+    const __m512i eps = _mm512_set1_epi64((long long)EPS);
+    __m512i hh = _mm512_srli_epi64(hi, 32);
+    __m512i t = _mm512_sub_epi64(lo, hh);
+    __mmask8 b = _mm512_cmplt_epu64_mask(lo, hh);
+    if (__builtin_expect(b != 0, 0)) t = v_borrow_fix(t, b);
+    __m512i m = _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), _mm512_and_si512(hi, eps));
+    __m512i r = _mm512_add_epi64(t, m);
+    __mmask8 c = _mm512_cmplt_epu64_mask(r, m);
+    return _mm512_mask_add_epi64(r, c, r, eps);
 }
 SIPP_IFMA inline __m512i v_mul_fast(__m512i x, __m512i y) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
@@ -415,7 +425,7 @@ SIPP_IFMA inline __m512i v_mul_fast(__m512i x, __m512i y) {
     __m512i ll = _mm512_mul_epu32(x, y), lh = _mm512_mul_epu32(x, yh), hl = _mm512_mul_epu32(xh, y), hh = _mm512_mul_epu32(xh, yh);
     __m512i mid = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(ll, 32), _mm512_and_si512(lh, lo32)), _mm512_and_si512(hl, lo32));
     __m512i hs = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(lh, 32), _mm512_srli_epi64(hl, 32)), hh);
-    return v_reduce_chainless(ll, mid, hs);
+    return v_reduce_fast(v_join(ll, mid), _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32)));
 }
 SIPP_IFMA inline __m512i v_sqr_fast(__m512i x) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
@@ -424,7 +434,7 @@ SIPP_IFMA inline __m512i v_sqr_fast(__m512i x) {
     __m512i lhl = _mm512_and_si512(lh, lo32), lhh = _mm512_srli_epi64(lh, 32);
     __m512i mid = _mm512_add_epi64(_mm512_add_epi64(_mm512_srli_epi64(ll, 32), lhl), lhl);
     __m512i hs = _mm512_add_epi64(_mm512_add_epi64(lhh, lhh), hh);
-    return v_reduce_chainless(ll, mid, hs);
+    return v_reduce_fast(v_join(ll, mid), _mm512_add_epi64(hs, _mm512_srli_epi64(mid, 32)));
 }
 SIPP_IFMA inline __m512i v_pow7_fast(__m512i x) {
     __m512i x2 = v_sqr_fast(x), x4 = v_sqr_fast(x2), x3 = v_mul_fast(x2, x);
@@ -464,24 +474,15 @@ SIPP_IFMA inline uint64_t sbox7(uint64_t u) {
         : "rdx", "cc");
     return a;
 }
-// (alo + 2^32 ahi) mod p for the two sums (< 2^43) of an MDS row
-SIPP_IFMA inline uint64_t s_mds_close(uint64_t alo, uint64_t ahi) {
-    unsigned long long t;
-    const uint64_t eps = EPS;
-    asm("mov %[ahi], %[t]\n\t" "shl $32, %[t]\n\t" "shr $32, %[ahi]\n\t" "add %[t], %[alo]\n\t" "adc $0, %[ahi]\n\t"
-        "mov %[ahi], %[t]\n\t" "shl $32, %[t]\n\t" "sub %[ahi], %[t]\n\t" "add %[t], %[alo]\n\t" "lea (%[alo],%[eps]), %[t]\n\t" "cmovc %[t], %[alo]"
-        : [alo] "+r"(alo), [ahi] "+r"(ahi), [t] "=&r"(t)
-        : [eps] "r"(eps)
-        : "cc");
-    return alo;
-}
 // A full round with lanes 0..7 in one vector and lanes 8..11 on the scalar ports.  Two zmm x^7 share the two 512-bit ports and the
 // second is half empty (134 cycles for the S-box layer against 115 for one vector alone); the four scalar x^7 (33 cycles each,
 // independent) run in the shadow of the vector chain, which comes first in program order so that it is served first.  The
-// scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store.
-// Lanes 0..7 arrive with their round constant already added (the previous MDS layer starts its sums from the halves of the NEXT
-// constants, rc_next: an addition less on the vector chain); the scalar lanes add theirs here, off the chain.
-SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc16, const uint64_t* rc_next, const PoseidonIfmaTables& I) {
+// scalar lanes reach the MDS layer as plain stores of their 32-bit halves, and rows 8..11 come back through one 64-byte store
+// (every scalar instruction saved here is worth ~0.3 cycles per round: the round is bound by the total micro-op flow, see the
+// ablations in tools/probe/README.md -- so rows 8..11 are recombined on the vector side and carry their constants too).
+// All lanes arrive with their round constant already added: the previous MDS layer starts its sums from the halves of the NEXT
+// constants (rc_next) -- an addition less on the vector chain, four fewer scalar additions.
+SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s0, uint64_t* t, const uint64_t* rc_next, const PoseidonIfmaTables& I) {
     const __m512i lo32 = _mm512_set1_epi64((long long)EPS);
     s0 = v_pow7_fast(s0);
     // MDS layer.  The 32-bit halves of every lane are stored as (low, high) pairs: a 64-bit broadcast of either feeds rows 0..7,
@@ -490,7 +491,7 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
     alignas(64) uint64_t pr[24];
 #pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
-        const uint64_t q = sbox7(s_add1(t[i], rc16[8 + i]));
+        const uint64_t q = sbox7(t[i]);
         pr[16 + 2 * i] = (uint32_t)q;
         pr[17 + 2 * i] = q >> 32;
     }
@@ -512,27 +513,29 @@ SIPP_IFMA inline __attribute__((always_inline)) void full_round_mixed(__m512i& s
         const __m512i ca = _mm512_load_si512(I.mds_icol_a[j]), cp = _mm512_load_si512(I.mds_icol_p[j]);
         al[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next) : j < 4 ? zero : al[j & 3], bl, ca);
         ah[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next + 8) : j < 4 ? zero : ah[j & 3], bh, ca);
-        ab[j & 3] = _mm512_madd52lo_epu64(j < 4 ? zero : ab[j & 3], bb, cp);
+        ab[j & 3] = _mm512_madd52lo_epu64(j == 0 ? _mm512_load_si512(rc_next + 16) : j < 4 ? zero : ab[j & 3], bb, cp);
     }
-    {
-        const __m512i eps = lo32;
-        const __m512i alo = _mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3]));
-        const __m512i ahi = _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3]));
-        // alo + 2^32 ahi = (alo + (ahi >> 32) (2^32 - 1)) + ((ahi mod 2^32) << 32): the first bracket is below 2^45, so the sum wraps only
-        // when the low word of ahi is within 2^13 of 2^32 -- 2^-19 per lane: a cold branch, no compare on the chain
+    // alo + 2^32 ahi = (alo + (ahi >> 32) (2^32 - 1)) + ((ahi mod 2^32) << 32): the first bracket is below 2^45, so the sum wraps only
+    // when the low word of ahi is within 2^13 of 2^32 -- 2^-19 per lane: a cold branch, no compare on the chain
+    auto combine = [&](__m512i alo, __m512i ahi) SIPP_IFMA {
         __m512i hi = _mm512_srli_epi64(ahi, 32);
         __m512i small = _mm512_add_epi64(alo, _mm512_sub_epi64(_mm512_slli_epi64(hi, 32), hi));
         __m512i r = _mm512_add_epi64(_mm512_slli_epi64(ahi, 32), small);
         __mmask8 c = _mm512_cmplt_epu64_mask(r, small);
         if (__builtin_expect(c != 0, 0)) r = v_carry_fix(r, c);
-        s0 = r;
-    }
+        return r;
+    };
+    s0 = combine(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
+                 _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
+    // rows 8..11: (low, high) sums side by side; the high ones move one lane down and the same recombination leaves the rows in
+    // the even lanes -- 7 vector instructions instead of 4 x 11 scalar ones
+    const __m512i bi = _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3]));
     alignas(64) uint64_t o[8];
-    _mm512_store_si512(o, _mm512_add_epi64(_mm512_add_epi64(ab[0], ab[1]), _mm512_add_epi64(ab[2], ab[3])));
+    _mm512_store_si512(o, combine(bi, _mm512_alignr_epi64(bi, bi, 1)));
     SIPP_THROUGH_MEMORY(o);
     const uint64_t* om = o;
 #pragma GCC unroll 4
-    for (int i = 0; i < 4; i++) t[i] = s_mds_close(om[2 * i], om[2 * i + 1]);
+    for (int i = 0; i < 4; i++) t[i] = om[2 * i];
 }
 // all eight lanes of a block closed at once: (a0 + 2^52 a1 - 2^8 a2) mod p
 SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
@@ -553,17 +556,18 @@ SIPP_IFMA inline __m512i v_close(const IfmaBlock& A) {
 
 SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T, const PoseidonIfmaTables& I) {
     __m512i s0 = _mm512_loadu_si512(s);
-    uint64_t t[4] = {s[8], s[9], s[10], s[11]};
+    uint64_t t[4];
+    for (int i = 0; i < 4; i++) t[i] = s_add1(s[8 + i], T.rc_full[0][8 + i]);
     s0 = v_add_canon(s0, _mm512_load_si512(T.rc_full[0]));
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[k], I.rc_next[k][0], I);
+    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, I.rc_next[k][0], I);
 
     alignas(64) uint64_t y[32];  // (lanes 0..7 already carry `first`)  // y[0..11], y[16 + i] = y[i] >> 52
     _mm512_store_si512(y, s0);
     _mm512_store_si512(y + 16, _mm512_srli_epi64(s0, 52));
 #pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
-        y[8 + i] = s_add1(t[i], T.first[8 + i]);
-        y[24 + i] = y[8 + i] >> 52;
+        y[8 + i] = t[i];  // (`first` rode along in the MDS layer of the fourth full round)
+        y[24 + i] = t[i] >> 52;
     }
     // four named blocks selected by switch statements, never through a pointer or an array index: anything else keeps the twelve
     // accumulators in memory (a load and a store around every vpmadd52)
@@ -617,7 +621,7 @@ SIPP_IFMA void poseidon_permute_ifma(uint64_t s[12], const PoseidonFastTables& T
         const uint64_t* om = o;
         t[0] = om[0]; t[1] = om[1]; t[2] = om[2]; t[3] = om[3];
     }
-    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, T.rc_full[4 + k], I.rc_next[4 + k][0], I);
+    for (int k = 0; k < 4; k++) full_round_mixed(s0, t, I.rc_next[4 + k][0], I);
     _mm512_storeu_si512(s, v_canon(s0));
     for (int i = 0; i < 4; i++) s[8 + i] = t[i] - (t[i] >= GL_P ? GL_P : 0);
 }
@@ -629,11 +633,6 @@ SIPP_IFMA uint64_t poseidon_test_vmul_fast(uint64_t x, uint64_t y, int square) {
     const __m512i vx = _mm512_set1_epi64((long long)x), vy = _mm512_set1_epi64((long long)y);
     _mm512_store_si512(t, square ? v_sqr_fast(vx) : v_mul_fast(vx, vy));
     return t[5];
-}
-SIPP_IFMA uint64_t poseidon_test_reduce_chainless(uint64_t ll, uint64_t mid, uint64_t hs) {
-    alignas(64) uint64_t t[8];
-    _mm512_store_si512(t, v_reduce_chainless(_mm512_set1_epi64((long long)ll), _mm512_set1_epi64((long long)mid), _mm512_set1_epi64((long long)hs)));
-    return t[2];
 }
 SIPP_IFMA void poseidon_test_ifma_close(const uint64_t in[5], uint64_t out[2]) {
     out[0] = row_close(in[0], in[1], in[2], in[3], in[4]);
@@ -732,7 +731,6 @@ void poseidon_permute_ifma(uint64_t*, const PoseidonFastTables&, const PoseidonI
 bool poseidon_ifma_supported() { return false; }
 void poseidon_test_ifma_close(const uint64_t*, uint64_t*) {}
 uint64_t poseidon_test_vmul_fast(uint64_t, uint64_t, int) { return 0; }
-uint64_t poseidon_test_reduce_chainless(uint64_t, uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_red128(uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_finish(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
 uint64_t poseidon_test_sbox(uint64_t, uint64_t, uint64_t*) { return 0; }
